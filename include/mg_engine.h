@@ -1,0 +1,172 @@
+/*
+ * mg_engine.h -- C ABI of the B200-native engine for the reference's hot path.
+ *
+ * The reference (RohitMurali18/Music-Generation-Emotion-Adaptive) has no FFI of its own: the
+ * boundary is two Python call shapes plus two checkpoint layouts.  Every
+ * entry point below names the reference interface it replaces.  Plain pointers and sizes only; the
+ * caller owns every host buffer, the engine owns device weights, the KV arena, workspace and its
+ * CUDA stream.  No pointer into engine memory is ever returned.
+ *
+ * Error convention: 0 = MG_OK, negative = error; mg_last_error() returns the message of the last
+ * failure on the calling thread.  There is NO CPU fallback: without a usable GPU every create call
+ * returns MG_E_CUDA.
+ *
+ * Threading: one engine per GPU; calls on one engine are serialised by an internal mutex (the
+ * reference's caller is a sync FastAPI endpoint on a thread pool sharing one global model,
+ * api_cache.py:186-187,108,161).  Different engines are independent (replicas).
+ */
+#ifndef MG_ENGINE_H_
+#define MG_ENGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+enum mg_status {
+  MG_OK = 0,
+  MG_E_SHAPE = -1,           /* tensor name/shape does not match the geometry                     */
+  MG_E_PROMPT_TOO_LONG = -2, /* prompt longer than the position table (api_cache.py:99 would raise) */
+  MG_E_TOPK = -3,            /* top_k > vocab (torch.topk raises in api_cache.py:172)              */
+  MG_E_CUDA = -4,            /* CUDA error, no device, or wrong architecture                       */
+  MG_E_OOM = -5,             /* arena/workspace allocation failed or capacity exceeded             */
+  MG_E_STATE = -6,           /* call order violated (weights missing, nothing uploaded, ...)       */
+  MG_E_ARG = -7,             /* invalid argument                                                   */
+  MG_E_TOKEN = -8            /* token id outside [0, vocab)                                        */
+};
+
+enum mg_dtype_mode {
+  MG_DTYPE_FP32 = 0, /* fp32 weights, KV and arithmetic: greedy tokens bit-identical to the reference */
+  MG_DTYPE_BF16 = 1  /* bf16 weights + bf16 KV cache, fp32 accumulation                             */
+};
+
+/* Model geometry.  Replaces the shape inference of api_cache.py:31-37 plus the hard-coded n_head
+ * of api_cache.py:112; d_ff is 4*d_model in every reference trainer (train/*.py). */
+typedef struct mg_geometry {
+  int32_t vocab_size;
+  int32_t pos_rows;
+  int32_t d_model;
+  int32_t n_head;
+  int32_t n_layer;
+  int32_t d_ff;
+} mg_geometry;
+
+typedef struct mg_engine mg_engine; /* MIDI-token generator replica */
+typedef struct mg_bert mg_bert;     /* DistilBERT emotion classifier replica */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int mg_abi_version(void);
+const char* mg_last_error(void);
+/* Number of CUDA devices visible, or a negative mg_status. */
+int mg_device_count(void);
+
+/* ---- generator: construction and weights ---------------------------------------------------- */
+/* Replaces `GPTWithKV(vocab_size, seq_len, d_model, n_head, n_layer)` (api_cache.py:108-114).
+ * max_batch / max_seq size the KV arena: L * 2 * max_batch * max_seq * d_model elements. */
+int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max_batch, int max_seq,
+                     mg_engine** out);
+void mg_engine_destroy(mg_engine* e);
+
+/* Replaces `model.load_state_dict(remap_state_dict(ckpt["model"]))` (api_cache.py:118-138), one
+ * tensor at a time.  `name` is the REMAPPED name (tok_emb.weight, pos_emb, head.weight, head.bias,
+ * layers.N.{attn.in_proj_weight, attn.in_proj_bias, attn.out_proj.weight, attn.out_proj.bias,
+ * ln1.weight, ln1.bias, ln2.weight, ln2.bias, mlp.0.weight, mlp.0.bias, mlp.2.weight, mlp.2.bias}).
+ * `data` is row-major fp32 on the host ([out,in] for Linear weights). */
+int mg_load_weight(mg_engine* e, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Verifies that all 4 + 12*n_layer tensors were loaded and makes the engine ready. */
+int mg_engine_finalize(mg_engine* e);
+
+/* ---- generator: the decode path -------------------------------------------------------------- */
+/* Replaces `sample_kvcache(model, prompt, max_len, temperature, top_k, device)` (api_cache.py:159-184)
+ * for a batch of B independent prompts (row b of the result == a batch-1 reference run on prompt b).
+ *   prompt_ids / prompt_offsets : packed prompts, prompt b = ids[offsets[b] .. offsets[b+1])
+ *   max_new_tokens              : the reference's `max_len - len(prompt)`; used for every sequence
+ *                                 unless max_new_per_seq != NULL (then per sequence)
+ *   temperature                 : > 0 (the reference divides by it)
+ *   top_k                       : 0 = no top-k mask (reference top_k=None); 1 = greedy
+ *   eos_id                      : -1 = never stop (vocab without [END_SEQUENCE], api_cache.py:181)
+ *   seed                        : Philox key; stream = (seed, seq_index_base + b, step)
+ *   out_ids [B][out_stride]     : prompt followed by generated ids; out_lens[b] = total length
+ * Host buffers; H2D / D2H copies happen inside the call. */
+int mg_generate(mg_engine* e, const int32_t* prompt_ids, const int32_t* prompt_offsets, int B,
+                int max_new_tokens, const int32_t* max_new_per_seq, float temperature, int top_k,
+                int eos_id, uint64_t seed, uint64_t seq_index_base, int32_t* out_ids, int out_stride,
+                int32_t* out_lens);
+
+/* The same path split at the host/device boundary (inputs resident in HBM for timing):
+ *   mg_upload_prompts : H2D of the packed prompts                (pinned staging inside the engine)
+ *   mg_run            : prefill + decode loop, device-resident, asynchronous on the engine stream
+ *   mg_download       : D2H of the generated ids (synchronises) */
+int mg_upload_prompts(mg_engine* e, const int32_t* prompt_ids, const int32_t* prompt_offsets, int B,
+                      int max_new_tokens, const int32_t* max_new_per_seq);
+int mg_run(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t seed, uint64_t seq_index_base);
+int mg_download(mg_engine* e, int32_t* out_ids, int out_stride, int32_t* out_lens);
+int mg_synchronize(mg_engine* e);
+/* cudaStream_t of the engine (as void*), so a host framework can record its own events on it. */
+void* mg_engine_stream(mg_engine* e);
+
+/* Parity/debug: teacher-forced logits of `GPTWithKV.forward` (api_cache.py:87-106) along the
+ * reference loop.  Step 0 feeds the last prompt token against the prefilled cache (the duplicate
+ * feed of api_cache.py:167-168); step i>0 feeds forced_ids[b][i-1].  logits_out is
+ * [n_steps][B][vocab] fp32 on the host. */
+int mg_step_logits(mg_engine* e, const int32_t* prompt_ids, const int32_t* prompt_offsets, int B,
+                   const int32_t* forced_ids, int n_steps, float* logits_out);
+
+/* Recompute mode: the no-cache twin `GPT.forward` + `sample` of generate_music/generate.py:25-61
+ * (post-LN, ReLU, unmasked, true positions, whole sequence recomputed every step). Same arguments
+ * as mg_generate; prompt + max_new_tokens must fit the position table. */
+int mg_generate_nocache(mg_engine* e, const int32_t* prompt_ids, const int32_t* prompt_offsets, int B,
+                        int max_new_tokens, float temperature, int top_k, int eos_id, uint64_t seed,
+                        uint64_t seq_index_base, int32_t* out_ids, int out_stride, int32_t* out_lens);
+/* Parity/debug for recompute mode: last-position logits [B][vocab] of one full forward. */
+int mg_forward_nocache(mg_engine* e, const int32_t* ids, const int32_t* offsets, int B, float* logits_out);
+
+/* Sampler on caller-provided logits (api_cache.py:169-178: /temperature, top-k, -1e10 mask,
+ * softmax, multinomial).  logits [rows][vocab] fp32 host; out [rows] int32.  Used by the chi-square
+ * parity test; rows use Philox streams (seed, seq_index_base + row, step). */
+int mg_sample_logits(mg_engine* e, const float* logits, int rows, int vocab, float temperature, int top_k,
+                     uint64_t seed, uint64_t seq_index_base, uint32_t step, int32_t* out);
+
+/* Counters since creation: kernels launched by this library, bytes H2D, bytes D2H. */
+int mg_engine_stats(mg_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Milliseconds of the last mg_run measured with CUDA events on the engine stream
+ * (total, prefill part, decode part) and the number of decode steps it executed. */
+int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* decode_ms, int* steps);
+
+/* ---- classifier ------------------------------------------------------------------------------ */
+typedef struct mg_bert_geometry {
+  int32_t vocab_size, max_pos, dim, n_heads, n_layers, hidden_dim, num_labels;
+} mg_bert_geometry;
+
+/* Replaces `load_model()` (emotion_analysis/modeling.py:8-25) minus tokenizer and hub download. */
+int mg_bert_create(const mg_bert_geometry* geo, int device, int max_tokens, mg_bert** out);
+void mg_bert_destroy(mg_bert* b);
+/* HF DistilBertForSequenceClassification tensor names; LoRA already merged (W + (alpha/r) B A). */
+int mg_bert_load_weight(mg_bert* b, const char* name, const float* data, const int64_t* shape, int ndim);
+int mg_bert_finalize(mg_bert* b);
+/* Replaces the forward + argmax of `inference.predict` (emotion_analysis/inference.py:16-21) for N
+ * texts of T tokens (row-major ids / mask; mask 1 = token, 0 = padding).  logits_out [N][num_labels],
+ * label_out [N].  Host buffers. */
+int mg_classify(mg_bert* b, const int32_t* ids, const uint8_t* mask, int N, int T, float* logits_out,
+                int32_t* label_out);
+/* Device-resident split of the same call, for timing with inputs in HBM. */
+int mg_bert_upload(mg_bert* b, const int32_t* ids, const uint8_t* mask, int N, int T);
+int mg_bert_run(mg_bert* b);
+int mg_bert_download(mg_bert* b, float* logits_out, int32_t* label_out);
+int mg_bert_synchronize(mg_bert* b);
+void* mg_bert_stream(mg_bert* b);
+int mg_bert_stats(mg_bert* b, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* ---- kernel-level test hooks (device work, host buffers) -------------------------------------- */
+/* C[M,N] = act(A[M,K] * W[N,K]^T + bias) through the tcgen05/TMA bf16 GEMM (fp32 in/out on host,
+ * converted to bf16 on device).  act: 0 none, 1 exact GELU, 2 ReLU. */
+int mg_test_gemm_bf16(int device, const float* A, const float* W, const float* bias, int M, int N, int K,
+                      int act, float* C);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MG_ENGINE_H_ */

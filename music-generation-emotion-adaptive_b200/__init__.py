@@ -11,7 +11,15 @@ from .checkpoint import (GEOMETRIES, Geometry, expected_keys, infer_geometry, ma
 from .vocab import (build_prompt, build_synthetic_vocab, closest_bpm_token, encode,  # noqa: F401
                     normalize_key_signature, synthetic_prompts)
 
+from .bert_checkpoint import (DISTILBERT_BASE, ID2LABEL, TINY_BERT, BertGeometry, make_bert_state_dict,  # noqa: F401
+                              merge_lora_state_dict)
+from .engine import (Classifier, Generator, KVModel, load_library, sample, sample_kvcache, tc_gemm)  # noqa: F401
+from .replicas import gather_token_lists, shard, shard_range  # noqa: F401
+
 __all__ = [
+    "Classifier", "Generator", "KVModel", "load_library", "sample", "sample_kvcache", "tc_gemm", "gather_token_lists",
+    "shard", "shard_range", "DISTILBERT_BASE", "ID2LABEL", "TINY_BERT", "BertGeometry", "make_bert_state_dict",
+    "merge_lora_state_dict",
     "GEOMETRIES", "Geometry", "expected_keys", "infer_geometry", "make_checkpoint", "make_state_dict",
     "remap_state_dict", "state_dict_digest", "build_prompt", "build_synthetic_vocab",
     "closest_bpm_token", "encode", "normalize_key_signature", "synthetic_prompts",

@@ -1,0 +1,936 @@
+// mg_engine: the MIDI-token generator replica behind the C ABI of include/mg_engine.h.
+//
+// Replaces, for one GPU (reference file:line in /root/reference):
+//   model construction + weight load   api_cache.py:108-138
+//   GPTWithKV.forward / GPTBlock       api_cache.py:51-74,87-106   (pre-LN, exact GELU, no final LN)
+//   sample_kvcache                     api_cache.py:159-184        (prefill, duplicate last-token feed,
+//                                                                   pos_emb[0] on decode, top-k sampler)
+//   GPT.forward + sample (no cache)    generate_music/generate.py:25-35,46-61 (post-LN, ReLU, unmasked)
+//
+// HBM layout: weights in the engine dtype T ([out,in] row-major as in the checkpoint), biases and
+// LayerNorm parameters fp32; KV cache per layer token-major [B_max][T_max][d] for K and for V
+// (projected K/V, not the reference's LN1(x) rows: mathematically identical);
+// fp32 residual stream x; T activations y / qkv / att / h; fp32 logits [B][ld_logits].
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <type_traits>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "mg_engine.h"
+
+namespace mg {
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+std::atomic<uint64_t> g_kernel_launches{0};
+
+}  // namespace mg
+
+using namespace mg;
+
+struct LayerW {
+  void *w_in = nullptr, *w_out = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *b_in = nullptr, *b_out = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+  WMaps m_in, m_out, m_w1, m_w2;
+  void *kc = nullptr, *vc = nullptr;
+};
+
+struct mg_engine {
+  mg_geometry geo{};
+  int device = 0, dtype = 0, max_batch = 0, max_seq = 0;
+  size_t esz = 4;
+  bool use_tc = false, use_graph = true, ready = false;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  std::vector<void*> allocs;
+
+  std::vector<LayerW> layers;
+  void *tok_emb = nullptr, *pos_emb = nullptr, *head_w = nullptr;
+  float* head_b = nullptr;
+  WMaps m_head;
+  std::set<std::string> loaded;
+  float* stage_f32 = nullptr;          // fp32 staging for weight conversion
+  size_t stage_elems = 0;
+
+  // activations (rows_cap rows)
+  int rows_cap = 0;
+  float* x = nullptr;
+  void *y = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *yl = nullptr;
+  CUtensorMap tm_y, tm_att, tm_h, tm_yl;
+  float* logits = nullptr;
+  int ld_logits = 0;
+  float *ws_o = nullptr, *ws_ml = nullptr;
+  uint32_t* counters = nullptr;
+
+  // per-call device arena (int32): prompts + row maps + decode state
+  int32_t* d_arena = nullptr;
+  int32_t* h_arena = nullptr;          // pinned
+  size_t arena_cap = 0;
+  int32_t *d_prompt = nullptr, *d_offsets = nullptr, *d_row_seq = nullptr, *d_row_pos = nullptr, *d_seq_start = nullptr,
+          *d_seq_len = nullptr, *d_last_rows = nullptr;
+  DecodeState st{};
+  int32_t* d_out_block = nullptr;      // [out_len (B) | out_ids (B * stride)] contiguous for one D2H
+  int32_t* h_out_block = nullptr;      // pinned
+  size_t out_cap = 0;
+  SampleParams* d_sp = nullptr;
+  SampleParams* h_sp = nullptr;        // pinned
+  int32_t* d_active = nullptr;
+  int32_t* h_active = nullptr;         // pinned
+  int32_t* d_forced = nullptr;
+  size_t forced_cap = 0;
+
+  int cur_B = 0, cur_M = 0, cur_max_tp = 0, cur_steps = 0;
+  bool uploaded = false;
+
+  cudaGraphExec_t graph = nullptr;
+  int graph_B = -1;
+
+  uint64_t h2d = 0, d2h = 0, launches0 = 0;
+  float t_total = 0, t_prefill = 0, t_decode = 0;
+  int t_steps = 0;
+
+  template <typename P> int dmalloc(P** p, size_t bytes) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(MG_E_OOM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    allocs.push_back(q);
+    *p = reinterpret_cast<P*>(q);
+    return MG_OK;
+  }
+  void dfree(void* q) {
+    if (!q) return;
+    auto it = std::find(allocs.begin(), allocs.end(), q);
+    if (it != allocs.end()) allocs.erase(it);
+    cudaFree(q);
+  }
+};
+
+namespace {
+
+int decode_nsplit(const mg_engine* e, int B) {
+  int n = ceil_div(2 * 148, B);
+  n = std::min(n, std::max(1, e->max_seq / 64));
+  return std::max(1, n);
+}
+
+// ---- GEMM dispatch: tcgen05 for bf16 with a full enough tile, SIMT otherwise -------------------
+template <typename T>
+int gemm(mg_engine* e, const void* A, const CUtensorMap* tmA, const void* W, const WMaps* wm, int M, int N, int K,
+         GemmEpilogue epi, float* out_f32_typed, void* out_typed) {
+  // typed output: float -> out_f32, bf16 -> out_bf16
+  if (out_typed) {
+    if (std::is_same<T, float>::value) epi.out_f32 = reinterpret_cast<float*>(out_typed);
+    else epi.out_bf16 = reinterpret_cast<bf16*>(out_typed);
+  }
+  if (out_f32_typed) epi.out_f32 = out_f32_typed;
+  if (std::is_same<T, bf16>::value && e->use_tc && M >= 32 && tmA && wm && wm->ok) {
+    const int bn = pick_gemm_bn(M, N);
+    return launch_gemm_tc(e->stream, tmA, &wm->m[bn_index(bn)], M, N, K, epi, bn);
+  }
+  return launch_gemm_simt<T>(e->stream, reinterpret_cast<const T*>(A), K, reinterpret_cast<const T*>(W), M, N, K, epi);
+}
+
+int ensure_rows(mg_engine* e, int rows) {
+  if (rows <= e->rows_cap) return MG_OK;
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  const int d = e->geo.d_model, f = e->geo.d_ff;
+  rows = std::max(rows, 128);
+  e->dfree(e->x); e->dfree(e->y); e->dfree(e->qkv); e->dfree(e->att); e->dfree(e->h);
+  e->x = nullptr; e->y = e->qkv = e->att = e->h = nullptr;
+  MG_TRY(e->dmalloc(&e->x, sizeof(float) * rows * d));
+  MG_TRY(e->dmalloc(&e->y, e->esz * rows * d));
+  MG_TRY(e->dmalloc(&e->qkv, e->esz * rows * 3 * d));
+  MG_TRY(e->dmalloc(&e->att, e->esz * rows * d));
+  MG_TRY(e->dmalloc(&e->h, e->esz * rows * f));
+  MG_CUDA_OK(cudaMemsetAsync(e->y, 0, e->esz * rows * d, e->stream));
+  MG_CUDA_OK(cudaMemsetAsync(e->att, 0, e->esz * rows * d, e->stream));
+  MG_CUDA_OK(cudaMemsetAsync(e->h, 0, e->esz * rows * f, e->stream));
+  if (e->dtype == MG_DTYPE_BF16 && e->use_tc) {
+    MG_TRY(make_tmap_bf16_2d(&e->tm_y, e->y, rows, d, kGemmBM));
+    MG_TRY(make_tmap_bf16_2d(&e->tm_att, e->att, rows, d, kGemmBM));
+    MG_TRY(make_tmap_bf16_2d(&e->tm_h, e->h, rows, f, kGemmBM));
+  }
+  e->rows_cap = rows;
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+  e->graph_B = -1;
+  return MG_OK;
+}
+
+// ---- one transformer block of model (B) on M rows; `decode` picks the attention kernel ---------
+template <typename T>
+int block_kv(mg_engine* e, int l, int M, bool decode, int B, int nsplit, bool ln1_done) {
+  const mg_geometry& g = e->geo;
+  const int d = g.d_model, f = g.d_ff;
+  LayerW& w = e->layers[l];
+  T* y = reinterpret_cast<T*>(e->y);
+  T* qkv = reinterpret_cast<T*>(e->qkv);
+  T* att = reinterpret_cast<T*>(e->att);
+  if (!ln1_done) MG_TRY((launch_layernorm<float, T>(e->stream, e->x, w.ln1w, w.ln1b, y, nullptr, M, d, 1e-5f)));
+  {
+    GemmEpilogue epi; epi.bias = w.b_in; epi.ld_out = 3 * d;
+    MG_TRY(gemm<T>(e, y, &e->tm_y, w.w_in, &w.m_in, M, 3 * d, d, epi, nullptr, qkv));
+  }
+  if (decode) {
+    MG_TRY(launch_decode_attn<T>(e->stream, qkv, reinterpret_cast<T*>(w.kc), reinterpret_cast<T*>(w.vc), e->st.lens,
+                                 e->st.finished, att, e->ws_o, e->ws_ml, e->counters, B, d, g.n_head, e->max_seq, nsplit));
+  } else {
+    MG_TRY(launch_kv_append<T>(e->stream, qkv, e->d_row_seq, e->d_row_pos, reinterpret_cast<T*>(w.kc),
+                               reinterpret_cast<T*>(w.vc), M, d, e->max_seq));
+    MG_TRY(launch_encoder_attn<T>(e->stream, qkv, e->d_seq_start, e->d_seq_len, nullptr, att, B, d, g.n_head, e->cur_max_tp));
+  }
+  {
+    GemmEpilogue epi; epi.bias = w.b_out; epi.resid_f32 = e->x; epi.ld_out = d;
+    MG_TRY(gemm<T>(e, att, &e->tm_att, w.w_out, &w.m_out, M, d, d, epi, e->x, nullptr));
+  }
+  MG_TRY((launch_layernorm<float, T>(e->stream, e->x, w.ln2w, w.ln2b, y, nullptr, M, d, 1e-5f)));
+  {
+    GemmEpilogue epi; epi.bias = w.b1; epi.act = ACT_GELU; epi.ld_out = f;
+    MG_TRY(gemm<T>(e, y, &e->tm_y, w.w1, &w.m_w1, M, f, d, epi, nullptr, e->h));
+  }
+  {
+    GemmEpilogue epi; epi.bias = w.b2; epi.resid_f32 = e->x; epi.ld_out = d;
+    MG_TRY(gemm<T>(e, e->h, &e->tm_h, w.w2, &w.m_w2, M, d, f, epi, e->x, nullptr));
+  }
+  return MG_OK;
+}
+
+template <typename T>
+int prefill(mg_engine* e) {
+  const mg_geometry& g = e->geo;
+  const int M = e->cur_M, B = e->cur_B;
+  MG_TRY(launch_embed_ln<T>(e->stream, e->d_prompt, e->d_row_pos, reinterpret_cast<const T*>(e->tok_emb),
+                            reinterpret_cast<const T*>(e->pos_emb), e->layers[0].ln1w, e->layers[0].ln1b, e->x,
+                            reinterpret_cast<T*>(e->y), M, g.d_model, 1e-5f, true));
+  for (int l = 0; l < g.n_layer; ++l) MG_TRY(block_kv<T>(e, l, M, false, B, 1, l == 0));
+  // logits of the prefill are discarded by the reference (api_cache.py:163): the head is skipped
+  MG_TRY(launch_decode_init(e->stream, e->d_prompt, e->d_offsets, e->st, B));
+  return MG_OK;
+}
+
+// embed(cur_tok) + pos_emb[0] -> L blocks -> head logits            (api_cache.py:87-106 with T == 1)
+template <typename T>
+int decode_forward(mg_engine* e) {
+  const mg_geometry& g = e->geo;
+  const int B = e->cur_B, nsplit = decode_nsplit(e, B);
+  MG_TRY(launch_embed_ln<T>(e->stream, e->st.cur_tok, nullptr, reinterpret_cast<const T*>(e->tok_emb),
+                            reinterpret_cast<const T*>(e->pos_emb), e->layers[0].ln1w, e->layers[0].ln1b, e->x,
+                            reinterpret_cast<T*>(e->y), B, g.d_model, 1e-5f, true));
+  for (int l = 0; l < g.n_layer; ++l) MG_TRY(block_kv<T>(e, l, B, true, B, nsplit, l == 0));
+  // no final LayerNorm (api_cache.py:105); the head reads the residual stream -> cast it into y
+  MG_TRY((launch_gather_rows<float, T>(e->stream, e->x, e->d_last_rows, reinterpret_cast<T*>(e->y), B, g.d_model)));
+  GemmEpilogue epi; epi.bias = e->head_b; epi.ld_out = e->ld_logits;
+  MG_TRY(gemm<T>(e, e->y, &e->tm_y, e->head_w, &e->m_head, B, g.vocab_size, g.d_model, epi, e->logits, nullptr));
+  return MG_OK;
+}
+
+template <typename T>
+int decode_step(mg_engine* e) {
+  MG_TRY(decode_forward<T>(e));
+  MG_TRY(launch_sample_step(e->stream, e->logits, e->ld_logits, e->geo.vocab_size, e->d_sp, e->st, e->cur_B));
+  return MG_OK;
+}
+
+template <typename T>
+int run_decode_loop(mg_engine* e, int eos_id) {
+  const int steps = e->cur_steps;
+  bool graph_ok = false;
+  if (e->use_graph && steps > 1) {
+    if (!e->graph || e->graph_B != e->cur_B) {
+      if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+      cudaGraph_t gr = nullptr;
+      MG_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = decode_step<T>(e);
+      cudaError_t ce = cudaStreamEndCapture(e->stream, &gr);
+      if (rc != MG_OK) { if (gr) cudaGraphDestroy(gr); return rc; }
+      if (ce != cudaSuccess) return fail(MG_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&e->graph, gr, 0);
+      cudaGraphDestroy(gr);
+      if (ce != cudaSuccess) return fail(MG_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+      e->graph_B = e->cur_B;
+    }
+    graph_ok = true;
+  }
+  int done_steps = 0;
+  for (int i = 0; i < steps; ++i) {
+    if (graph_ok) MG_CUDA_OK(cudaGraphLaunch(e->graph, e->stream));
+    else MG_TRY(decode_step<T>(e));
+    ++done_steps;
+    if (eos_id >= 0 && (i % 32) == 31 && i + 1 < steps) {
+      MG_TRY(launch_count_active(e->stream, e->st.finished, e->cur_B, e->d_active));
+      MG_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+      if (*e->h_active == 0) break;
+    }
+  }
+  e->t_steps = done_steps;
+  return MG_OK;
+}
+
+template <typename T>
+int run_impl(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t seed, uint64_t seq_base) {
+  *e->h_sp = SampleParams{temperature, top_k, eos_id, 0, seed, seq_base};
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
+  MG_TRY(prefill<T>(e));
+  MG_CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
+  MG_TRY(run_decode_loop<T>(e, eos_id));
+  MG_CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
+  return MG_OK;
+}
+
+// ---- recompute mode: model (A), generate_music/generate.py:25-35 -------------------------------
+// Row layout: sequence b owns rows [b*Tcap, b*Tcap + len_b); seq_start / seq_len describe it.
+template <typename T>
+int forward_nocache(mg_engine* e, int B, int Tcap, int max_len_now) {
+  const mg_geometry& g = e->geo;
+  const int d = g.d_model, f = g.d_ff, M = B * Tcap;
+  T* y = reinterpret_cast<T*>(e->y);
+  MG_TRY(launch_nocache_embed<T>(e->stream, e->st.out_ids, e->st.out_stride, e->st.out_len,
+                                 reinterpret_cast<const T*>(e->tok_emb), reinterpret_cast<const T*>(e->pos_emb), e->x, y, B,
+                                 Tcap, d));
+  for (int l = 0; l < g.n_layer; ++l) {
+    LayerW& w = e->layers[l];
+    { GemmEpilogue epi; epi.bias = w.b_in; epi.ld_out = 3 * d;
+      MG_TRY(gemm<T>(e, y, &e->tm_y, w.w_in, &w.m_in, M, 3 * d, d, epi, nullptr, e->qkv)); }
+    MG_TRY(launch_encoder_attn<T>(e->stream, reinterpret_cast<const T*>(e->qkv), e->d_seq_start, e->st.out_len, nullptr,
+                                  reinterpret_cast<T*>(e->att), B, d, g.n_head, max_len_now));
+    { GemmEpilogue epi; epi.bias = w.b_out; epi.resid_f32 = e->x; epi.ld_out = d;
+      MG_TRY(gemm<T>(e, e->att, &e->tm_att, w.w_out, &w.m_out, M, d, d, epi, e->x, nullptr)); }
+    // post-LN: x = norm1(x + sa(x))   (nn.TransformerEncoderLayer, norm_first=False)
+    MG_TRY((launch_layernorm<float, T>(e->stream, e->x, w.ln1w, w.ln1b, y, e->x, M, d, 1e-5f)));
+    { GemmEpilogue epi; epi.bias = w.b1; epi.act = ACT_RELU; epi.ld_out = f;
+      MG_TRY(gemm<T>(e, y, &e->tm_y, w.w1, &w.m_w1, M, f, d, epi, nullptr, e->h)); }
+    { GemmEpilogue epi; epi.bias = w.b2; epi.resid_f32 = e->x; epi.ld_out = d;
+      MG_TRY(gemm<T>(e, e->h, &e->tm_h, w.w2, &w.m_w2, M, d, f, epi, e->x, nullptr)); }
+    MG_TRY((launch_layernorm<float, T>(e->stream, e->x, w.ln2w, w.ln2b, y, e->x, M, d, 1e-5f)));
+  }
+  return MG_OK;
+}
+
+int parse_layer_name(const std::string& name, int* layer, std::string* leaf) {
+  if (name.compare(0, 7, "layers.") != 0) return -1;
+  const size_t dot = name.find('.', 7);
+  if (dot == std::string::npos) return -1;
+  *layer = std::atoi(name.substr(7, dot - 7).c_str());
+  *leaf = name.substr(dot + 1);
+  return 0;
+}
+
+int upload_tensor(mg_engine* e, void* dst, bool typed, const float* data, size_t n) {
+  if (!typed || e->dtype == MG_DTYPE_FP32) {
+    MG_CUDA_OK(cudaMemcpyAsync(dst, data, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->h2d += n * sizeof(float);
+    return MG_OK;
+  }
+  if (n > e->stage_elems) {
+    e->dfree(e->stage_f32);
+    e->stage_f32 = nullptr;
+    MG_TRY(e->dmalloc(&e->stage_f32, n * sizeof(float)));
+    e->stage_elems = n;
+  }
+  MG_CUDA_OK(cudaMemcpyAsync(e->stage_f32, data, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  MG_TRY(launch_convert<bf16>(e->stream, e->stage_f32, reinterpret_cast<bf16*>(dst), n));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->h2d += n * sizeof(float);
+  return MG_OK;
+}
+
+int ensure_arena(mg_engine* e, size_t ints) {
+  if (ints <= e->arena_cap) return MG_OK;
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->dfree(e->d_arena);
+  e->d_arena = nullptr;
+  if (e->h_arena) cudaFreeHost(e->h_arena);
+  e->h_arena = nullptr;
+  ints = ints + ints / 2 + 256;
+  MG_TRY(e->dmalloc(&e->d_arena, ints * sizeof(int32_t)));
+  MG_CUDA_OK(cudaMallocHost(&e->h_arena, ints * sizeof(int32_t)));
+  e->arena_cap = ints;
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+  e->graph_B = -1;
+  return MG_OK;
+}
+
+int ensure_out(mg_engine* e, size_t ints) {
+  if (ints <= e->out_cap) return MG_OK;
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->dfree(e->d_out_block);
+  e->d_out_block = nullptr;
+  if (e->h_out_block) cudaFreeHost(e->h_out_block);
+  e->h_out_block = nullptr;
+  ints = ints + ints / 2 + 256;
+  MG_TRY(e->dmalloc(&e->d_out_block, ints * sizeof(int32_t)));
+  MG_CUDA_OK(cudaMallocHost(&e->h_out_block, ints * sizeof(int32_t)));
+  e->out_cap = ints;
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+  e->graph_B = -1;
+  return MG_OK;
+}
+
+// Validates the prompts, builds the row maps on the host and uploads everything in ONE H2D copy.
+// `kv` = true: KV-cache path (cache capacity checks); false: recompute mode (position-table check).
+int upload_impl(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, int max_new, const int32_t* max_new_per,
+                bool kv) {
+  if (!e->ready) return fail(MG_E_STATE, "engine not finalized (mg_engine_finalize)");
+  if (!ids || !offs || B <= 0) return fail(MG_E_ARG, "prompts: null pointer or empty batch");
+  if (B > e->max_batch) return fail(MG_E_OOM, "batch larger than max_batch given at mg_engine_create");
+  if (max_new < 0) return fail(MG_E_ARG, "max_new_tokens < 0");
+  const mg_geometry& g = e->geo;
+  if (offs[0] != 0) return fail(MG_E_ARG, "prompt_offsets[0] must be 0");
+  int M = 0, max_tp = 0, max_total = 0, steps = 0;
+  for (int b = 0; b < B; ++b) {
+    const int tp = offs[b + 1] - offs[b];
+    if (tp <= 0) return fail(MG_E_ARG, "empty prompt (the reference indexes generated[:, -1:], api_cache.py:167)");
+    if (tp > g.pos_rows)
+      return fail(MG_E_PROMPT_TOO_LONG, "prompt of " + std::to_string(tp) + " tokens exceeds the " +
+                                            std::to_string(g.pos_rows) + "-row position table (api_cache.py:99)");
+    const int mn = max_new_per ? max_new_per[b] : max_new;
+    if (mn < 0) return fail(MG_E_ARG, "max_new_per_seq < 0");
+    if (kv && tp + mn > e->max_seq) return fail(MG_E_OOM, "prompt + max_new_tokens exceeds max_seq given at mg_engine_create");
+    if (!kv && mn > 0 && tp + mn - 1 > g.pos_rows)
+      return fail(MG_E_PROMPT_TOO_LONG, "recompute mode: prompt + max_new_tokens - 1 exceeds the position table");
+    M += tp;
+    max_tp = std::max(max_tp, tp);
+    max_total = std::max(max_total, tp + mn);
+    steps = std::max(steps, mn);
+  }
+  for (int i = 0; i < M; ++i)
+    if (ids[i] < 0 || ids[i] >= g.vocab_size) return fail(MG_E_TOKEN, "prompt token id outside [0, vocab)");
+
+  const int stride = (max_total + 7) & ~7;
+  // arena layout (int32): prompt[M] offsets[B+1] row_seq[M] row_pos[M] seq_start[B] seq_len[B] max_new[B]
+  //                       last_rows[B] | device-only: cur_tok[B] lens[B] n_new[B] finished[B bytes]
+  const size_t up_ints = static_cast<size_t>(M) * 3 + static_cast<size_t>(B) * 5 + 1;
+  const size_t all_ints = up_ints + static_cast<size_t>(B) * 4 + 16;
+  MG_TRY(ensure_arena(e, all_ints));
+  MG_TRY(ensure_out(e, static_cast<size_t>(B) * (stride + 1)));
+  int32_t* h = e->h_arena;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+  const size_t o_prompt = take(M), o_offs = take(B + 1), o_rseq = take(M), o_rpos = take(M), o_sstart = take(B),
+               o_slen = take(B), o_maxnew = take(B), o_last = take(B);
+  std::memcpy(h + o_prompt, ids, sizeof(int32_t) * M);
+  std::memcpy(h + o_offs, offs, sizeof(int32_t) * (B + 1));
+  for (int b = 0; b < B; ++b) {
+    const int tp = offs[b + 1] - offs[b];
+    for (int t = 0; t < tp; ++t) {
+      h[o_rseq + offs[b] + t] = b;
+      h[o_rpos + offs[b] + t] = t;
+    }
+    h[o_sstart + b] = offs[b];
+    h[o_slen + b] = tp;
+    h[o_maxnew + b] = max_new_per ? max_new_per[b] : max_new;
+    h[o_last + b] = b;
+  }
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_arena, h, up_ints * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  e->h2d += up_ints * sizeof(int32_t);
+  int32_t* da = e->d_arena;
+  e->d_prompt = da + o_prompt; e->d_offsets = da + o_offs; e->d_row_seq = da + o_rseq; e->d_row_pos = da + o_rpos;
+  e->d_seq_start = da + o_sstart; e->d_seq_len = da + o_slen; e->d_last_rows = da + o_last;
+  int32_t* new_cur = da + take(B);
+  int32_t* new_lens = da + take(B);
+  int32_t* new_nnew = da + take(B);
+  uint8_t* new_fin = reinterpret_cast<uint8_t*>(da + take(B));
+  int32_t* new_outlen = e->d_out_block;
+  int32_t* new_outids = e->d_out_block + B;
+  const bool same = e->st.cur_tok == new_cur && e->st.lens == new_lens && e->st.n_new == new_nnew &&
+                    e->st.finished == new_fin && e->st.out_len == new_outlen && e->st.out_ids == new_outids &&
+                    e->st.max_new == da + o_maxnew && e->st.out_stride == stride;
+  if (!same && e->graph) {               // captured kernel arguments would be stale
+    cudaGraphExecDestroy(e->graph);
+    e->graph = nullptr;
+    e->graph_B = -1;
+  }
+  e->st.cur_tok = new_cur; e->st.lens = new_lens; e->st.n_new = new_nnew; e->st.finished = new_fin;
+  e->st.out_len = new_outlen; e->st.out_ids = new_outids; e->st.max_new = da + o_maxnew; e->st.out_stride = stride;
+  e->cur_B = B; e->cur_M = M; e->cur_max_tp = max_tp; e->cur_steps = steps;
+  MG_TRY(ensure_rows(e, std::max(M, B)));
+  e->uploaded = true;
+  return MG_OK;
+}
+
+int download_impl(mg_engine* e, int32_t* out_ids, int out_stride, int32_t* out_lens) {
+  if (!e->uploaded) return fail(MG_E_STATE, "nothing to download (call mg_upload_prompts + mg_run first)");
+  const int B = e->cur_B, stride = e->st.out_stride;
+  const size_t ints = static_cast<size_t>(B) * (stride + 1);
+  MG_CUDA_OK(cudaMemcpyAsync(e->h_out_block, e->d_out_block, ints * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->d2h += ints * sizeof(int32_t);
+  const int32_t* hl = e->h_out_block;
+  const int32_t* hi = e->h_out_block + B;
+  for (int b = 0; b < B; ++b) {
+    const int n = hl[b];
+    if (out_ids && n > out_stride) return fail(MG_E_ARG, "out_stride smaller than a generated sequence");
+    if (out_lens) out_lens[b] = n;
+    if (out_ids) std::memcpy(out_ids + static_cast<size_t>(b) * out_stride, hi + static_cast<size_t>(b) * stride, sizeof(int32_t) * n);
+  }
+  MG_CUDA_OK(cudaEventSynchronize(e->ev[2]));
+  cudaEventElapsedTime(&e->t_total, e->ev[0], e->ev[2]);
+  cudaEventElapsedTime(&e->t_prefill, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->t_decode, e->ev[1], e->ev[2]);
+  return MG_OK;
+}
+
+int check_sampling(mg_engine* e, float temperature, int top_k) {
+  if (!(temperature > 0.0f)) return fail(MG_E_ARG, "temperature must be > 0 (the reference divides by it, api_cache.py:169)");
+  if (top_k < 0) return fail(MG_E_ARG, "top_k < 0");
+  if (top_k > e->geo.vocab_size) return fail(MG_E_TOPK, "top_k larger than the vocabulary (torch.topk raises, api_cache.py:172)");
+  return MG_OK;
+}
+
+// ---- recompute mode -------------------------------------------------------------------------------
+int nocache_setup(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, int max_new, int* Tcap_out) {
+  MG_TRY(upload_impl(e, ids, offs, B, max_new, nullptr, false));
+  // rows: sequence b owns [b*Tcap, (b+1)*Tcap); Tcap = longest final length (multiple of 8)
+  const int Tcap = e->st.out_stride;
+  MG_TRY(ensure_rows(e, B * Tcap));
+  // seq_start[b] = b * Tcap (overwrites the packed starts uploaded for the KV path)
+  std::vector<int32_t> starts(B), last(B);
+  for (int b = 0; b < B; ++b) starts[b] = b * Tcap;
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_seq_start, starts.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->h2d += sizeof(int32_t) * B;
+  MG_TRY(launch_decode_init(e->stream, e->d_prompt, e->d_offsets, e->st, B));
+  *Tcap_out = Tcap;
+  return MG_OK;
+}
+
+// last_rows[b] = b*Tcap + out_len[b] - 1, computed on the device from out_len
+__global__ void nocache_last_rows_kernel(const int32_t* out_len, int32_t* last_rows, int B, int Tcap) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) last_rows[b] = b * Tcap + out_len[b] - 1;
+}
+
+template <typename T>
+int nocache_logits(mg_engine* e, int B, int Tcap, int max_len_now) {
+  MG_TRY(forward_nocache<T>(e, B, Tcap, max_len_now));
+  nocache_last_rows_kernel<<<ceil_div(B, 128), 128, 0, e->stream>>>(e->st.out_len, e->d_last_rows, B, Tcap);
+  MG_LAUNCH_CHECK();
+  if (!e->yl) {
+    MG_TRY(e->dmalloc(&e->yl, e->esz * std::max(e->max_batch, 128) * e->geo.d_model));
+    MG_CUDA_OK(cudaMemsetAsync(e->yl, 0, e->esz * std::max(e->max_batch, 128) * e->geo.d_model, e->stream));
+    if (e->use_tc) MG_TRY(make_tmap_bf16_2d(&e->tm_yl, e->yl, std::max(e->max_batch, 128), e->geo.d_model, kGemmBM));
+  }
+  MG_TRY((launch_gather_rows<T, T>(e->stream, reinterpret_cast<const T*>(e->y), e->d_last_rows, reinterpret_cast<T*>(e->yl), B,
+                                   e->geo.d_model)));
+  GemmEpilogue epi; epi.bias = e->head_b; epi.ld_out = e->ld_logits;
+  return gemm<T>(e, e->yl, &e->tm_yl, e->head_w, &e->m_head, B, e->geo.vocab_size, e->geo.d_model, epi, e->logits, nullptr);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int mg_abi_version(void) { return MG_ABI_VERSION; }
+const char* mg_last_error(void) { return t_last_error.c_str(); }
+
+int mg_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(MG_E_CUDA, cudaGetErrorString(e));
+  return n;
+}
+
+int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max_batch, int max_seq, mg_engine** out) {
+  if (!geo || !out) return fail(MG_E_ARG, "null argument");
+  *out = nullptr;
+  if (dtype_mode != MG_DTYPE_FP32 && dtype_mode != MG_DTYPE_BF16) return fail(MG_E_ARG, "unknown dtype_mode");
+  const mg_geometry g = *geo;
+  if (g.vocab_size <= 0 || g.pos_rows <= 0 || g.d_model <= 0 || g.n_head <= 0 || g.n_layer <= 0 || g.d_ff <= 0)
+    return fail(MG_E_SHAPE, "non-positive geometry field");
+  if (g.d_model % g.n_head) return fail(MG_E_SHAPE, "d_model not divisible by n_head");
+  if (g.d_model % 16 || g.d_ff % 16 || g.d_model > 1024) return fail(MG_E_SHAPE, "d_model / d_ff must be multiples of 16, d_model <= 1024");
+  const int hd = g.d_model / g.n_head;
+  if (hd % 8 || hd > 64 || (hd & (hd - 1))) return fail(MG_E_SHAPE, "head_dim must be 8, 16, 32 or 64");
+  if (max_batch <= 0 || max_seq <= 0) return fail(MG_E_ARG, "max_batch / max_seq must be positive");
+  MG_TRY(check_device(device));
+
+  mg_engine* e = new mg_engine();
+  e->geo = g; e->device = device; e->dtype = dtype_mode; e->max_batch = max_batch; e->max_seq = max_seq;
+  e->esz = dtype_mode == MG_DTYPE_BF16 ? 2 : 4;
+  const char* env_gemm = std::getenv("MG_GEMM");
+  e->use_tc = dtype_mode == MG_DTYPE_BF16 && !(env_gemm && std::strcmp(env_gemm, "simt") == 0);
+  const char* env_graph = std::getenv("MG_NO_GRAPH");
+  e->use_graph = !(env_graph && env_graph[0] == '1');
+  e->launches0 = g_kernel_launches.load();
+  int rc = MG_OK;
+  auto body = [&]() -> int {
+    MG_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (auto& ev : e->ev) MG_CUDA_OK(cudaEventCreate(&ev));
+    MG_TRY(kernels_init());
+    if (e->use_tc) MG_TRY(gemm_tc_init());
+    const size_t d = g.d_model, f = g.d_ff, V = g.vocab_size;
+    MG_TRY(e->dmalloc(&e->tok_emb, e->esz * V * d));
+    MG_TRY(e->dmalloc(&e->pos_emb, e->esz * g.pos_rows * d));
+    MG_TRY(e->dmalloc(&e->head_w, e->esz * V * d));
+    MG_TRY(e->dmalloc(&e->head_b, sizeof(float) * V));
+    e->layers.resize(g.n_layer);
+    const size_t kv_elems = static_cast<size_t>(max_batch) * max_seq * d;
+    for (auto& w : e->layers) {
+      MG_TRY(e->dmalloc(&w.w_in, e->esz * 3 * d * d));
+      MG_TRY(e->dmalloc(&w.w_out, e->esz * d * d));
+      MG_TRY(e->dmalloc(&w.w1, e->esz * f * d));
+      MG_TRY(e->dmalloc(&w.w2, e->esz * d * f));
+      MG_TRY(e->dmalloc(&w.b_in, sizeof(float) * 3 * d));
+      MG_TRY(e->dmalloc(&w.b_out, sizeof(float) * d));
+      MG_TRY(e->dmalloc(&w.b1, sizeof(float) * f));
+      MG_TRY(e->dmalloc(&w.b2, sizeof(float) * d));
+      MG_TRY(e->dmalloc(&w.ln1w, sizeof(float) * d));
+      MG_TRY(e->dmalloc(&w.ln1b, sizeof(float) * d));
+      MG_TRY(e->dmalloc(&w.ln2w, sizeof(float) * d));
+      MG_TRY(e->dmalloc(&w.ln2b, sizeof(float) * d));
+      MG_TRY(e->dmalloc(&w.kc, e->esz * kv_elems));
+      MG_TRY(e->dmalloc(&w.vc, e->esz * kv_elems));
+    }
+    e->ld_logits = (g.vocab_size + 7) & ~7;
+    MG_TRY(e->dmalloc(&e->logits, sizeof(float) * static_cast<size_t>(max_batch) * e->ld_logits));
+    const size_t ws_rows = static_cast<size_t>(2 * 148 + 2 * max_batch);
+    MG_TRY(e->dmalloc(&e->ws_o, sizeof(float) * ws_rows * d));
+    MG_TRY(e->dmalloc(&e->ws_ml, sizeof(float) * ws_rows * g.n_head * 2));
+    MG_TRY(e->dmalloc(&e->counters, sizeof(uint32_t) * max_batch));
+    MG_CUDA_OK(cudaMemsetAsync(e->counters, 0, sizeof(uint32_t) * max_batch, e->stream));
+    MG_TRY(e->dmalloc(&e->d_sp, sizeof(SampleParams)));
+    MG_TRY(e->dmalloc(&e->d_active, sizeof(int32_t)));
+    MG_CUDA_OK(cudaMallocHost(&e->h_sp, sizeof(SampleParams)));
+    MG_CUDA_OK(cudaMallocHost(&e->h_active, sizeof(int32_t)));
+    MG_TRY(ensure_rows(e, std::max(max_batch, 128)));
+    MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return MG_OK;
+  };
+  rc = body();
+  if (rc != MG_OK) {
+    const std::string keep = t_last_error;
+    mg_engine_destroy(e);
+    set_last_error(keep);
+    return rc;
+  }
+  *out = e;
+  return MG_OK;
+}
+
+void mg_engine_destroy(mg_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->graph) cudaGraphExecDestroy(e->graph);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->h_arena) cudaFreeHost(e->h_arena);
+  if (e->h_out_block) cudaFreeHost(e->h_out_block);
+  if (e->h_sp) cudaFreeHost(e->h_sp);
+  if (e->h_active) cudaFreeHost(e->h_active);
+  for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int mg_load_weight(mg_engine* e, const char* name_c, const float* data, const int64_t* shape, int ndim) {
+  if (!e || !name_c || !data || !shape) return fail(MG_E_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  const mg_geometry& g = e->geo;
+  const int64_t d = g.d_model, f = g.d_ff, V = g.vocab_size;
+  const std::string name(name_c);
+  void* dst = nullptr;
+  bool typed = true;
+  int64_t s0 = 0, s1 = 0;                 // expected shape (s1 == 0: 1-D)
+  int layer = -1;
+  std::string leaf;
+  if (name == "tok_emb.weight") { dst = e->tok_emb; s0 = V; s1 = d; }
+  else if (name == "pos_emb") { dst = e->pos_emb; s0 = g.pos_rows; s1 = d; }
+  else if (name == "head.weight") { dst = e->head_w; s0 = V; s1 = d; }
+  else if (name == "head.bias") { dst = e->head_b; s0 = V; typed = false; }
+  else if (parse_layer_name(name, &layer, &leaf) == 0 && layer >= 0 && layer < g.n_layer) {
+    LayerW& w = e->layers[layer];
+    if (leaf == "attn.in_proj_weight") { dst = w.w_in; s0 = 3 * d; s1 = d; }
+    else if (leaf == "attn.in_proj_bias") { dst = w.b_in; s0 = 3 * d; typed = false; }
+    else if (leaf == "attn.out_proj.weight") { dst = w.w_out; s0 = d; s1 = d; }
+    else if (leaf == "attn.out_proj.bias") { dst = w.b_out; s0 = d; typed = false; }
+    else if (leaf == "mlp.0.weight") { dst = w.w1; s0 = f; s1 = d; }
+    else if (leaf == "mlp.0.bias") { dst = w.b1; s0 = f; typed = false; }
+    else if (leaf == "mlp.2.weight") { dst = w.w2; s0 = d; s1 = f; }
+    else if (leaf == "mlp.2.bias") { dst = w.b2; s0 = d; typed = false; }
+    else if (leaf == "ln1.weight") { dst = w.ln1w; s0 = d; typed = false; }
+    else if (leaf == "ln1.bias") { dst = w.ln1b; s0 = d; typed = false; }
+    else if (leaf == "ln2.weight") { dst = w.ln2w; s0 = d; typed = false; }
+    else if (leaf == "ln2.bias") { dst = w.ln2b; s0 = d; typed = false; }
+  }
+  if (!dst) return fail(MG_E_SHAPE, "unknown tensor name '" + name + "' for this geometry");
+  const bool shape_ok = (s1 == 0) ? (ndim == 1 && shape[0] == s0) : (ndim == 2 && shape[0] == s0 && shape[1] == s1);
+  if (!shape_ok) return fail(MG_E_SHAPE, "shape mismatch for '" + name + "'");
+  MG_TRY(upload_tensor(e, dst, typed, data, static_cast<size_t>(s0) * (s1 ? s1 : 1)));
+  e->loaded.insert(name);
+  e->ready = false;
+  return MG_OK;
+}
+
+int mg_engine_finalize(mg_engine* e) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  const size_t want = 4 + 12 * static_cast<size_t>(e->geo.n_layer);
+  if (e->loaded.size() != want)
+    return fail(MG_E_STATE, "weights missing: " + std::to_string(e->loaded.size()) + " of " + std::to_string(want) + " tensors loaded");
+  if (e->use_tc) {
+    const int d = e->geo.d_model, f = e->geo.d_ff;
+    for (auto& w : e->layers) {
+      MG_TRY(make_wmaps(&w.m_in, w.w_in, 3 * d, d));
+      MG_TRY(make_wmaps(&w.m_out, w.w_out, d, d));
+      MG_TRY(make_wmaps(&w.m_w1, w.w1, f, d));
+      MG_TRY(make_wmaps(&w.m_w2, w.w2, d, f));
+    }
+    MG_TRY(make_wmaps(&e->m_head, e->head_w, e->geo.vocab_size, d));
+  }
+  e->ready = true;
+  return MG_OK;
+}
+
+int mg_upload_prompts(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, int max_new, const int32_t* max_new_per) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  return upload_impl(e, ids, offs, B, max_new, max_new_per, true);
+}
+
+static int run_locked(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t seed, uint64_t seq_base) {
+  if (!e->uploaded) return fail(MG_E_STATE, "mg_run before mg_upload_prompts");
+  MG_TRY(check_sampling(e, temperature, top_k));
+  return e->dtype == MG_DTYPE_BF16 ? run_impl<bf16>(e, temperature, top_k, eos_id, seed, seq_base)
+                                   : run_impl<float>(e, temperature, top_k, eos_id, seed, seq_base);
+}
+
+int mg_run(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t seed, uint64_t seq_base) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  return run_locked(e, temperature, top_k, eos_id, seed, seq_base);
+}
+
+int mg_download(mg_engine* e, int32_t* out_ids, int out_stride, int32_t* out_lens) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  return download_impl(e, out_ids, out_stride, out_lens);
+}
+
+int mg_synchronize(mg_engine* e) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return MG_OK;
+}
+
+void* mg_engine_stream(mg_engine* e) { return e ? reinterpret_cast<void*>(e->stream) : nullptr; }
+
+int mg_generate(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, int max_new, const int32_t* max_new_per,
+                float temperature, int top_k, int eos_id, uint64_t seed, uint64_t seq_base, int32_t* out_ids,
+                int out_stride, int32_t* out_lens) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  MG_TRY(check_sampling(e, temperature, top_k));
+  MG_TRY(upload_impl(e, ids, offs, B, max_new, max_new_per, true));
+  MG_TRY(run_locked(e, temperature, top_k, eos_id, seed, seq_base));
+  return download_impl(e, out_ids, out_stride, out_lens);
+}
+
+int mg_step_logits(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, const int32_t* forced, int n_steps,
+                   float* logits_out) {
+  if (!e || !logits_out) return fail(MG_E_ARG, "null argument");
+  if (n_steps <= 0) return fail(MG_E_ARG, "n_steps must be positive");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  MG_TRY(upload_impl(e, ids, offs, B, n_steps, nullptr, true));
+  const int V = e->geo.vocab_size;
+  if (n_steps > 1) {
+    if (!forced) return fail(MG_E_ARG, "forced_ids is null");
+    const size_t n = static_cast<size_t>(B) * n_steps;
+    for (size_t i = 0; i < n; ++i)
+      if (forced[i] < 0 || forced[i] >= V) return fail(MG_E_TOKEN, "forced token id outside [0, vocab)");
+    if (n > e->forced_cap) {
+      e->dfree(e->d_forced);
+      e->d_forced = nullptr;
+      MG_TRY(e->dmalloc(&e->d_forced, n * sizeof(int32_t)));
+      e->forced_cap = n;
+    }
+    MG_CUDA_OK(cudaMemcpyAsync(e->d_forced, forced, n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    e->h2d += n * sizeof(int32_t);
+  }
+  const bool is_bf16 = e->dtype == MG_DTYPE_BF16;
+  MG_TRY(is_bf16 ? prefill<bf16>(e) : prefill<float>(e));
+  for (int i = 0; i < n_steps; ++i) {
+    MG_TRY(is_bf16 ? decode_forward<bf16>(e) : decode_forward<float>(e));
+    MG_CUDA_OK(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(i) * B * V, sizeof(float) * V, e->logits,
+                                 sizeof(float) * e->ld_logits, sizeof(float) * V, B, cudaMemcpyDeviceToHost, e->stream));
+    e->d2h += sizeof(float) * V * B;
+    if (i + 1 < n_steps) MG_TRY(launch_force_next(e->stream, e->d_forced, n_steps, i, e->st, B));
+  }
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->uploaded = false;
+  return MG_OK;
+}
+
+int mg_generate_nocache(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, int max_new, float temperature,
+                        int top_k, int eos_id, uint64_t seed, uint64_t seq_base, int32_t* out_ids, int out_stride,
+                        int32_t* out_lens) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  MG_TRY(check_sampling(e, temperature, top_k));
+  int Tcap = 0;
+  MG_TRY(nocache_setup(e, ids, offs, B, max_new, &Tcap));
+  *e->h_sp = SampleParams{temperature, top_k, eos_id, 0, seed, seq_base};
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
+  MG_CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
+  const bool is_bf16 = e->dtype == MG_DTYPE_BF16;
+  int done = 0;
+  for (int i = 0; i < max_new; ++i) {
+    const int max_len_now = std::min(Tcap, e->cur_max_tp + i);
+    MG_TRY(is_bf16 ? nocache_logits<bf16>(e, B, Tcap, max_len_now) : nocache_logits<float>(e, B, Tcap, max_len_now));
+    MG_TRY(launch_sample_step(e->stream, e->logits, e->ld_logits, e->geo.vocab_size, e->d_sp, e->st, B));
+    ++done;
+    if (eos_id >= 0 && (i % 16) == 15 && i + 1 < max_new) {
+      MG_TRY(launch_count_active(e->stream, e->st.finished, B, e->d_active));
+      MG_CUDA_OK(cudaMemcpyAsync(e->h_active, e->d_active, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+      if (*e->h_active == 0) break;
+    }
+  }
+  e->t_steps = done;
+  MG_CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
+  const int rc = download_impl(e, out_ids, out_stride, out_lens);
+  e->uploaded = false;
+  return rc;
+}
+
+int mg_forward_nocache(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, float* logits_out) {
+  if (!e || !logits_out) return fail(MG_E_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  int Tcap = 0;
+  MG_TRY(nocache_setup(e, ids, offs, B, 0, &Tcap));
+  const bool is_bf16 = e->dtype == MG_DTYPE_BF16;
+  // logits of the LAST position of every sequence: [B][vocab]
+  MG_TRY(is_bf16 ? nocache_logits<bf16>(e, B, Tcap, e->cur_max_tp) : nocache_logits<float>(e, B, Tcap, e->cur_max_tp));
+  const int V = e->geo.vocab_size;
+  MG_CUDA_OK(cudaMemcpy2DAsync(logits_out, sizeof(float) * V, e->logits, sizeof(float) * e->ld_logits, sizeof(float) * V, B,
+                               cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->d2h += sizeof(float) * V * B;
+  e->uploaded = false;
+  return MG_OK;
+}
+
+int mg_sample_logits(mg_engine* e, const float* logits, int rows, int vocab, float temperature, int top_k, uint64_t seed,
+                     uint64_t seq_base, uint32_t step, int32_t* out) {
+  if (!e || !logits || !out) return fail(MG_E_ARG, "null argument");
+  if (rows <= 0 || vocab <= 0) return fail(MG_E_ARG, "rows / vocab must be positive");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  if (!(temperature > 0.0f)) return fail(MG_E_ARG, "temperature must be > 0");
+  if (top_k < 0) return fail(MG_E_ARG, "top_k < 0");
+  if (top_k > vocab) return fail(MG_E_TOPK, "top_k larger than the vocabulary");
+  float* d_logits = nullptr;
+  int32_t* d_out = nullptr;
+  const size_t n = static_cast<size_t>(rows) * vocab;
+  MG_TRY(e->dmalloc(&d_logits, n * sizeof(float)));
+  MG_TRY(e->dmalloc(&d_out, rows * sizeof(int32_t)));
+  int rc = MG_OK;
+  auto body = [&]() -> int {
+    MG_CUDA_OK(cudaMemcpyAsync(d_logits, logits, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    *e->h_sp = SampleParams{temperature, top_k, -1, 0, seed, seq_base};
+    MG_CUDA_OK(cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream));
+    MG_TRY(launch_sample_rows(e->stream, d_logits, vocab, rows, vocab, e->d_sp, step, d_out));
+    MG_CUDA_OK(cudaMemcpyAsync(out, d_out, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return MG_OK;
+  };
+  rc = body();
+  e->h2d += n * sizeof(float);
+  e->d2h += rows * sizeof(int32_t);
+  e->dfree(d_logits);
+  e->dfree(d_out);
+  return rc;
+}
+
+int mg_engine_stats(mg_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  if (kernel_launches) *kernel_launches = g_kernel_launches.load() - e->launches0;
+  if (h2d_bytes) *h2d_bytes = e->h2d;
+  if (d2h_bytes) *d2h_bytes = e->d2h;
+  return MG_OK;
+}
+
+int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* decode_ms, int* steps) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->ev[2]) {
+    if (cudaEventQuery(e->ev[2]) == cudaSuccess) {
+      cudaEventElapsedTime(&e->t_total, e->ev[0], e->ev[2]);
+      cudaEventElapsedTime(&e->t_prefill, e->ev[0], e->ev[1]);
+      cudaEventElapsedTime(&e->t_decode, e->ev[1], e->ev[2]);
+    }
+  }
+  if (total_ms) *total_ms = e->t_total;
+  if (prefill_ms) *prefill_ms = e->t_prefill;
+  if (decode_ms) *decode_ms = e->t_decode;
+  if (steps) *steps = e->t_steps;
+  return MG_OK;
+}
+
+int mg_test_gemm_bf16(int device, const float* A, const float* W, const float* bias, int M, int N, int K, int act, float* C) {
+  if (!A || !W || !C) return fail(MG_E_ARG, "null argument");
+  if (M <= 0 || N <= 0 || K <= 0 || K % 8) return fail(MG_E_SHAPE, "M, N, K must be positive, K a multiple of 8");
+  MG_TRY(check_device(device));
+  MG_TRY(gemm_tc_init());
+  float *dA32 = nullptr, *dW32 = nullptr, *dC = nullptr, *dbias = nullptr;
+  bf16 *dA = nullptr, *dW = nullptr;
+  const int Mp = ceil_div(M, 128) * 128;
+  int rc = MG_OK;
+  auto body = [&]() -> int {
+    MG_CUDA_OK(cudaMalloc(&dA32, sizeof(float) * M * K));
+    MG_CUDA_OK(cudaMalloc(&dW32, sizeof(float) * N * K));
+    MG_CUDA_OK(cudaMalloc(&dA, sizeof(bf16) * Mp * K));
+    MG_CUDA_OK(cudaMalloc(&dW, sizeof(bf16) * N * K));
+    MG_CUDA_OK(cudaMalloc(&dC, sizeof(float) * M * N));
+    MG_CUDA_OK(cudaMemset(dA, 0, sizeof(bf16) * Mp * K));
+    MG_CUDA_OK(cudaMemcpy(dA32, A, sizeof(float) * M * K, cudaMemcpyHostToDevice));
+    MG_CUDA_OK(cudaMemcpy(dW32, W, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+    if (bias) {
+      MG_CUDA_OK(cudaMalloc(&dbias, sizeof(float) * N));
+      MG_CUDA_OK(cudaMemcpy(dbias, bias, sizeof(float) * N, cudaMemcpyHostToDevice));
+    }
+    MG_TRY(launch_convert<bf16>(nullptr, dA32, dA, static_cast<size_t>(M) * K));
+    MG_TRY(launch_convert<bf16>(nullptr, dW32, dW, static_cast<size_t>(N) * K));
+    const int bn = pick_gemm_bn(M, N);
+    CUtensorMap ta, tw;
+    MG_TRY(make_tmap_bf16_2d(&ta, dA, Mp, K, kGemmBM));
+    MG_TRY(make_tmap_bf16_2d(&tw, dW, N, K, bn));
+    GemmEpilogue epi; epi.bias = dbias; epi.act = act; epi.out_f32 = dC; epi.ld_out = N;
+    MG_TRY(launch_gemm_tc(nullptr, &ta, &tw, M, N, K, epi, bn));
+    MG_CUDA_OK(cudaDeviceSynchronize());
+    MG_CUDA_OK(cudaMemcpy(C, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost));
+    return MG_OK;
+  };
+  rc = body();
+  cudaFree(dA32); cudaFree(dW32); cudaFree(dA); cudaFree(dW); cudaFree(dC); cudaFree(dbias);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+// tcgen05 / TMEM / TMA bf16 GEMM for sm_100a:  D[M,N] = epi(A[M,K] * W[N,K]^T).
+//
+// Used for every dense contraction of the hot path where the batch dimension fills a tensor-core
+// tile: QKV / out-proj / MLP / head GEMMs of the generator in prefill and in batched decode
+// (reference api_cache.py:43,45-49,68,85 -- nn.MultiheadAttention in/out projections, the MLP and the
+// head Linear), and all DistilBERT Linear layers (reference emotion_analysis/inference.py:18).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor 2D loads of the A (128x64) and W (BNx64) bf16
+//                 tiles into a kStages-deep shared-memory ring, 128B swizzle, mbarrier complete_tx
+//   warp 1      : TMEM allocator + MMA issuer -- one elected thread issues tcgen05.mma
+//                 (cta_group::1, kind::f16, M=128, N=BN, K=16) x4 per stage, accumulating in TMEM;
+//                 tcgen05.commit releases the smem stage and finally signals the epilogue
+//   warps 2..5  : epilogue -- tcgen05.ld 32x32b (each warp owns one 32-lane TMEM quarter), fused
+//                 bias / exact-GELU / ReLU / residual, vectorised global stores
+#include "gemm_tc.cuh"
+
+#include "mg_engine.h"
+#include "ptx.cuh"
+
+namespace mg {
+
+namespace {
+
+constexpr int kThreads = 192;
+
+template <int BN> struct TileCfg {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;            // 16 KB
+  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  // keep <= ~96 KB so two CTAs share an SM (their epilogues overlap the other's main loop)
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    int M, int N, int K, GemmEpilogue epi) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kGemmBM;
+  const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      ptx::mbar_init(tmem_full_bar, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * Cfg::kStageBytes;
+        uint8_t* b_dst = a_dst + Cfg::kABytes;
+        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        ptx::tma_load_2d(a_dst, &tmap_a, &full_bar[s], kb * kGemmBK, m0);
+        ptx::tma_load_2d(b_dst, &tmap_w, &full_bar[s], kb * kGemmBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kGemmBM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+        const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr);
+        const uint64_t db = ptx::make_kmajor_sw128_desc(a_addr + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < kGemmBK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128B swizzle span: +2 in 16-byte units
+          ptx::umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[s]);          // frees this smem stage once the MMAs retire
+      }
+      ptx::umma_commit(tmem_full_bar);            // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (warps 2..5) =====
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after_sync();
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < M;
+    const size_t ld = static_cast<size_t>(epi.ld_out);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, r);
+      ptx::tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (!row_ok || col0 >= N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const bool full = (col0 + 32 <= N);
+      const size_t off = static_cast<size_t>(row) * ld + col0;
+      if (full && (ld % 8 == 0) && (col0 % 8 == 0)) {
+        if (epi.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if (epi.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], epi.act);
+        }
+        if (epi.resid_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(epi.resid_f32 + off + j);
+            v[j] += x4.x; v[j + 1] += x4.y; v[j + 2] += x4.z; v[j + 3] += x4.w;
+          }
+        }
+        if (epi.resid_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+            Chunk16<bf16>::unpack(*reinterpret_cast<const uint4*>(epi.resid_bf16 + off + j), f);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[j + t] += f[t];
+          }
+        }
+        if (epi.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(epi.out_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (epi.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(epi.out_bf16 + off + j) = Chunk16<bf16>::pack(v + j);
+        }
+      } else {
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col >= N) break;
+          float x = v[j] + (epi.bias ? __ldg(epi.bias + col) : 0.0f);
+          x = apply_act(x, epi.act);
+          if (epi.resid_f32) x += epi.resid_f32[off + j];
+          if (epi.resid_bf16) x += __bfloat162float(epi.resid_bf16[off + j]);
+          if (epi.out_f32) epi.out_f32[off + j] = x;
+          if (epi.out_bf16) epi.out_bf16[off + j] = __float2bfloat16_rn(x);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+template <int BN>
+int launch_bn(cudaStream_t stream, const CUtensorMap* ta, const CUtensorMap* tw, int M, int N, int K,
+              const GemmEpilogue& epi) {
+  using Cfg = TileCfg<BN>;
+  dim3 grid(ceil_div(N, BN), ceil_div(M, kGemmBM));
+  gemm_bf16_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(*ta, *tw, M, N, K, epi);
+  MG_LAUNCH_CHECK();
+  return MG_OK;
+}
+
+template <int BN>
+int init_bn() {
+  MG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TileCfg<BN>::kSmemBytes));
+  return MG_OK;
+}
+
+}  // namespace
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+    return MG_E_CUDA;
+  }
+  if ((cols * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_last_error("TMA operand needs 16-byte aligned base and row pitch (K % 8 == 0)");
+    return MG_E_SHAPE;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return MG_E_CUDA;
+  }
+  return MG_OK;
+}
+
+int gemm_tc_init() {
+  MG_TRY(init_bn<32>());
+  MG_TRY(init_bn<64>());
+  MG_TRY(init_bn<128>());
+  MG_TRY(init_bn<256>());
+  return MG_OK;
+}
+
+int pick_gemm_bn(int M, int N) {
+  // Few row tiles (batched decode): small BN spreads the weight stream over many SMs.
+  const int m_tiles = ceil_div(M, kGemmBM);
+  if (m_tiles * ceil_div(N, 128) >= 148) return 128;
+  if (m_tiles * ceil_div(N, 64) >= 96) return 64;
+  return 32;
+}
+
+int launch_gemm_tc(cudaStream_t stream, const CUtensorMap* ta, const CUtensorMap* tw, int M, int N, int K,
+                   const GemmEpilogue& epi, int bn) {
+  if (M <= 0 || N <= 0 || K <= 0 || K % 8 != 0) {
+    set_last_error("launch_gemm_tc: bad shape");
+    return MG_E_SHAPE;
+  }
+  switch (bn) {
+    case 32: return launch_bn<32>(stream, ta, tw, M, N, K, epi);
+    case 64: return launch_bn<64>(stream, ta, tw, M, N, K, epi);
+    case 128: return launch_bn<128>(stream, ta, tw, M, N, K, epi);
+    case 256: return launch_bn<256>(stream, ta, tw, M, N, K, epi);
+    default:
+      set_last_error("launch_gemm_tc: unsupported block-N");
+      return MG_E_ARG;
+  }
+}
+
+}  // namespace mg

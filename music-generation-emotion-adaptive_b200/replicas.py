@@ -1,0 +1,70 @@
+"""Multi-GPU layout of the path: full-model replicas, requests sharded by batch, one final token gather.
+
+Every generation request is independent (reference ``sample_kvcache`` is per prompt,
+api_cache.py:159-184) and so is every ``classify`` text, so each GPU holds a full replica and a
+contiguous slice of the requests; nothing is exchanged on the decode path.  The only communication
+is the gather of the finished token lists (``[B_local, T]`` int32, <= 264 KB per GPU at config 3),
+done once per job with one ``all_gather`` of a padded tensor (NCCL over NVLink on GPUs, gloo on CPU
+in the tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [lo, hi) of ``n_items`` requests owned by ``rank`` (sizes differ by <= 1)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world_size")
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(items: Sequence, rank: int, world_size: int) -> List:
+    lo, hi = shard_range(len(items), rank, world_size)
+    return list(items[lo:hi])
+
+
+def gather_token_lists(local: Sequence[Sequence[int]], n_total: int, group=None,
+                       device: Optional[torch.device] = None) -> List[List[int]]:
+    """All ranks receive the token lists of all ``n_total`` requests in request order.
+
+    ``local`` must be this rank's ``shard_range`` slice.  One all_gather of an int32 tensor
+    ``[max_local, 1 + max_len]`` (column 0 = length); rows are padded with -1.
+    """
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if len(local) != n_total:
+            raise ValueError("single process: local must hold every request")
+        return [list(x) for x in local]
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_range(n_total, rank, world)
+    if len(local) != hi - lo:
+        raise ValueError(f"rank {rank} holds {len(local)} results, expected {hi - lo}")
+    dev = device or (torch.device("cuda", torch.cuda.current_device())
+                     if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    max_local = -(-n_total // world)
+    my_max = max((len(x) for x in local), default=0)
+    t = torch.tensor([my_max], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    max_len = int(t.item())
+    buf = torch.full((max_local, 1 + max_len), -1, dtype=torch.int32)
+    for i, x in enumerate(local):
+        buf[i, 0] = len(x)
+        if len(x):
+            buf[i, 1:1 + len(x)] = torch.tensor(list(x), dtype=torch.int32)
+    buf = buf.to(dev)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    result: List[List[int]] = []
+    for r, o in enumerate(outs):
+        o = o.cpu()
+        rlo, rhi = shard_range(n_total, r, world)
+        for i in range(rhi - rlo):
+            n = int(o[i, 0])
+            result.append(o[i, 1:1 + n].tolist())
+    return result

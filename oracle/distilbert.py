@@ -55,7 +55,8 @@ def forward(sd: Dict[str, torch.Tensor], input_ids: torch.Tensor, attention_mask
     hd = d // n_heads
     neg = torch.finfo(dtype).min
     key_mask = (attention_mask == 0).view(N, 1, 1, T)
-    for i in range(N_LAYERS):
+    n_layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("distilbert.transformer.layer."))
+    for i in range(n_layers):
         p = f"distilbert.transformer.layer.{i}."
         lin = lambda name, t: t @ g(p + name + ".weight").T + g(p + name + ".bias")
         q = lin("attention.q_lin", x).view(N, T, n_heads, hd).transpose(1, 2)

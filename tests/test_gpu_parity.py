@@ -1,0 +1,335 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+
+Tolerances (stated here, BASELINE.json north_star):
+  fp32 mode : greedy tokens bit-identical to the reference; teacher-forced logits max-abs <= 2e-4
+  bf16 mode : teacher-forced logits vs the fp64 reference run  max-abs <= 6e-2 and
+              relative-to-logit-range <= 2e-2 at every step
+  sampler   : chi-square against the reference top-k softmax, p > 0.001, 2e5 draws
+  classifier: labels identical, logits max-abs <= 0.25 on logits of spread ~ +-10 (bf16 path)
+"""
+import numpy as np
+import pytest
+import torch
+
+import mgea_b200 as mg
+from conftest import checkpoint, load_golden
+from oracle import distilbert as obert
+from oracle import gpt_kv, gpt_nocache
+
+pytestmark = pytest.mark.gpu
+
+_engines = {}
+
+
+def engine(geo_name, seed, dtype, max_batch=8, max_seq=None):
+    key = (geo_name, seed, dtype, max_batch, max_seq)
+    if key not in _engines:
+        if len(_engines) > 6:
+            for k in list(_engines)[:3]:
+                _engines.pop(k).close()
+        geo = mg.GEOMETRIES[geo_name]
+        ck = checkpoint(geo_name, seed)
+        _engines[key] = mg.Generator(ck["model"], n_head=geo.n_head, dtype=dtype, max_batch=max_batch,
+                                     max_seq=max_seq or max(2 * geo.pos_rows, 64))
+    return _engines[key]
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05 / TMA GEMM kernel
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,act", [(128, 128, 64, 0), (64, 768, 256, 0), (200, 260, 256, 1), (33, 8324, 256, 0),
+                                       (384, 1024, 256, 1), (130, 256, 1024, 2), (1024, 2304, 768, 0), (5, 40, 64, 0)])
+def test_tc_gemm_matches_fp32_reference_on_bf16_inputs(M, N, K, act):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g) * 0.1
+    C = mg.tc_gemm(A.numpy(), W.numpy(), bias.numpy(), act)
+    Ab, Wb = A.bfloat16().float(), W.bfloat16().float()
+    ref = Ab @ Wb.T + bias
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    err = np.max(np.abs(C - ref.numpy()))
+    assert err < 2e-3, err
+
+
+# ---------------------------------------------------------------------------------------------------
+# fp32 mode: greedy bit-identity with the reference (golden tokens from the reference's sample_kvcache)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("geo", ["tiny", "tiny_hd64", "train_mini", "train_large", "train_large2"])
+def test_fp32_greedy_tokens_identical_to_reference(geo):
+    z, meta = load_golden("kv_greedy")
+    cases = [m for m in meta if m["geometry"] == geo]
+    assert cases
+    for m in cases:
+        e = engine(geo, m["seed"], "fp32")
+        prompt = z[m["key"] + "_prompt"].tolist()
+        want = z[m["key"] + "_tokens"].tolist()
+        got = e.generate([prompt], m["max_len"] - len(prompt), 1.0, 1, eos_id=m["eos_id"])[0]
+        assert got == want, (m["key"], next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), None))
+
+
+def test_fp32_batched_rows_equal_batch1_reference_runs():
+    """Batch semantics: row b of a batch == the reference's batch-1 run on prompt b, with
+    ragged prompt lengths and per-row EOS stops in one batch."""
+    z, meta = load_golden("kv_greedy")
+    for geo, seed in (("tiny", 0), ("train_large", 1)):
+        cases = [m for m in meta if m["geometry"] == geo and m["seed"] == seed]
+        e = engine(geo, seed, "fp32")
+        prompts = [z[m["key"] + "_prompt"].tolist() for m in cases]
+        max_new = [m["max_len"] - len(p) for m, p in zip(cases, prompts)]
+        # one EOS setting per call: group by eos_id
+        for eos in sorted({m["eos_id"] for m in cases}):
+            idx = [i for i, m in enumerate(cases) if m["eos_id"] == eos]
+            got = e.generate([prompts[i] for i in idx], [max_new[i] for i in idx], 1.0, 1, eos_id=eos)
+            for j, i in enumerate(idx):
+                assert got[j] == z[cases[i]["key"] + "_tokens"].tolist(), cases[i]["key"]
+
+
+def test_fp32_teacher_forced_logits_within_2e_4():
+    z, meta = load_golden("kv_logits")
+    for m in meta:
+        e = engine(m["geometry"], m["seed"], "fp32")
+        prompts = [z[f"{m['key']}_b{b}_prompt"].tolist() for b in range(m["batch"])]
+        got = e.step_logits(prompts, z[m["key"] + "_forced"], m["n_steps"])
+        for b in range(m["batch"]):
+            want = z[f"{m['key']}_b{b}_logits_f32"]
+            assert np.max(np.abs(got[:, b, :] - want)) < 2e-4, (m["key"], b)
+
+
+def test_bf16_teacher_forced_logits_within_tolerance():
+    z, meta = load_golden("kv_logits")
+    for m in meta:
+        e = engine(m["geometry"], m["seed"], "bf16")
+        prompts = [z[f"{m['key']}_b{b}_prompt"].tolist() for b in range(m["batch"])]
+        got = e.step_logits(prompts, z[m["key"] + "_forced"], m["n_steps"])
+        for b in range(m["batch"]):
+            want = z[f"{m['key']}_b{b}_logits_f64"]
+            err = np.max(np.abs(got[:, b, :] - want), axis=1)
+            span = want.max(axis=1) - want.min(axis=1)
+            assert err.max() < 6e-2, (m["key"], b, err.max())
+            assert (err / span).max() < 2e-2, (m["key"], b)
+
+
+def test_bf16_tensor_core_batch_matches_small_batch_path():
+    """Batch >= 32 goes through the tcgen05 GEMMs, batch < 32 through the SIMT GEMV: same numbers."""
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 40, seed=3)]
+    forced = np.random.default_rng(0).integers(0, geo.vocab_size, (40, 4)).astype(np.int32)
+    big = engine("train_large", 0, "bf16", max_batch=64, max_seq=320)
+    a = big.step_logits(prompts, forced, 4)                       # B = 40 -> tensor cores
+    b = big.step_logits(prompts[:3], forced[:3], 4)               # B = 3  -> GEMV
+    assert np.max(np.abs(a[:, :3, :] - b)) < 4e-2
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head, torch.float64)
+    want = gpt_kv.teacher_forced_logits(ora, prompts[17], forced[17].tolist(), 4).numpy()
+    assert np.max(np.abs(a[:, 17, :] - want)) < 6e-2
+
+
+# ---------------------------------------------------------------------------------------------------
+# sampler
+# ---------------------------------------------------------------------------------------------------
+def _chi_square_p(counts, probs):
+    from scipy import stats
+    keep = probs > 0
+    assert counts[~keep].sum() == 0, "sampled a token outside the reference's top-k set"
+    n = counts.sum()
+    exp = probs[keep] * n
+    obs = counts[keep]
+    # pool tiny expectations
+    small = exp < 5
+    if small.any():
+        exp = np.append(exp[~small], exp[small].sum())
+        obs = np.append(obs[~small], obs[small].sum())
+    chi2 = ((obs - exp) ** 2 / exp).sum()
+    return float(stats.chi2.sf(chi2, len(exp) - 1))
+
+
+@pytest.mark.parametrize("name", ["v8324_k40", "v8324_k50_t08", "v96_k5", "v8324_full"])
+def test_sampler_matches_reference_topk_distribution_chi_square(name):
+    z, _ = load_golden("topk_probs")
+    logits, probs = z[name + "_logits"], z[name + "_probs"].astype(np.float64)
+    k, temp = int(z[name + "_k"]), float(z[name + "_temp"])
+    e = engine("tiny", 0, "fp32")
+    draws, rows = 200_000, 20_000
+    counts = np.zeros(len(logits), np.int64)
+    tile = np.tile(logits, (rows, 1))
+    for i in range(draws // rows):
+        toks = e.sample_logits(tile, temp, None if k < 0 else k, seed=1234, seq_index_base=i * rows, step=5)
+        counts += np.bincount(toks, minlength=len(logits))
+    assert _chi_square_p(counts, probs / probs.sum()) > 1e-3
+
+
+def test_sampler_greedy_and_determinism():
+    rng = np.random.default_rng(1)
+    lg = rng.normal(size=(64, 8324)).astype(np.float32)
+    e = engine("tiny", 0, "fp32")
+    assert (e.sample_logits(lg, 1.0, 1) == lg.argmax(1)).all()
+    a = e.sample_logits(lg, 0.9, 40, seed=7, step=3)
+    assert (a == e.sample_logits(lg, 0.9, 40, seed=7, step=3)).all()
+    assert (a != e.sample_logits(lg, 0.9, 40, seed=8, step=3)).any()
+    # every draw lies inside the top-40 set of its row
+    top = np.argsort(-lg, axis=1)[:, :40]
+    assert all(a[i] in top[i] for i in range(64))
+    with pytest.raises(RuntimeError):
+        e.sample_logits(lg[:, :30], 1.0, 31)                      # top_k > vocab (torch.topk raises)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE config 3 / 4 shapes)
+# ---------------------------------------------------------------------------------------------------
+def test_config3_shape_properties_batch64_bf16():
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 64, seed=0)]
+    e = engine("train_large", 0, "bf16", max_batch=64, max_seq=1088)
+    out = e.generate(prompts, 1024, 1.0, 40, eos_id=-1, seed=11)
+    assert all(len(o) == len(p) + 1024 and o[:len(p)] == p for o, p in zip(out, prompts))
+    assert all(0 <= t < geo.vocab_size for o in out for t in o)
+    assert out == e.generate(prompts, 1024, 1.0, 40, eos_id=-1, seed=11)          # deterministic in the seed
+    # EOS: every row stops on its first occurrence, inclusive (api_cache.py:179-182); same batch shape,
+    # so the numerics of the surviving rows are unchanged
+    eos = out[3][len(prompts[3]) + 10]
+    stopped = e.generate(prompts, 1024, 1.0, 40, eos_id=eos, seed=11)
+    for o, p, s_ in zip(out, prompts, stopped):
+        first = o.index(eos, len(p)) if eos in o[len(p):] else len(o) - 1
+        assert s_ == o[:first + 1]
+    assert len(stopped[3]) == len(prompts[3]) + 11
+
+
+def test_batch_rows_are_independent_fp32_greedy_batch64_vs_batch1():
+    """Var-len batch: no padding token ever enters attention, so a row does not depend on its neighbours."""
+    ck = checkpoint("train_large", 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 64, seed=0)]
+    e = engine("train_large", 0, "fp32", max_batch=64, max_seq=320)
+    g64 = e.generate(prompts, 96, 1.0, 1)
+    for b in (0, 5, 63):
+        assert g64[b] == e.generate(prompts[b:b + 1], 96, 1.0, 1)[0]
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), 8)
+    assert g64[17] == gpt_kv.sample_ids(ora, prompts[17], max_len=len(prompts[17]) + 96, temperature=1.0, top_k=1)
+
+
+def test_philox_streams_are_keyed_by_sequence_index():
+    lg = np.random.default_rng(2).normal(size=(16, 8324)).astype(np.float32)
+    e = engine("tiny", 0, "fp32")
+    full = e.sample_logits(lg, 1.0, 40, seed=5, seq_index_base=0, step=9)
+    part = e.sample_logits(lg[8:], 1.0, 40, seed=5, seq_index_base=8, step=9)
+    assert (full[8:] == part).all()
+
+
+def test_config4_shape_long_context_split_k_fp32_matches_oracle():
+    """256-token prompt, long decode: exercises bidirectional prefill + split-K decode attention."""
+    geo = mg.GEOMETRIES["train_large_pos512"]
+    ck = checkpoint("train_large_pos512", 0)
+    rng = np.random.default_rng(0)
+    prompts = [rng.integers(0, geo.vocab_size, 256).tolist() for _ in range(2)]
+    e = engine("train_large_pos512", 0, "fp32", max_batch=16, max_seq=4352)
+    n = 6
+    forced = rng.integers(0, geo.vocab_size, (2, n)).astype(np.int32)
+    got = e.step_logits(prompts, forced, n)
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head)
+    for b in range(2):
+        want = gpt_kv.teacher_forced_logits(ora, prompts[b], forced[b].tolist(), n).numpy()
+        assert np.max(np.abs(got[:, b, :] - want)) < 3e-4
+    out = e.generate(prompts, 700, 1.0, 1)
+    ref = gpt_kv.sample_ids(ora, prompts[0], max_len=256 + 160, temperature=1.0, top_k=1)
+    assert out[0][:len(ref)] == ref
+    assert len(out[0]) == 256 + 700
+
+
+# ---------------------------------------------------------------------------------------------------
+# error behaviour of the reference, kept
+# ---------------------------------------------------------------------------------------------------
+def test_errors_match_reference_behaviour():
+    geo = mg.GEOMETRIES["tiny"]
+    e = engine("tiny", 0, "fp32")
+    with pytest.raises(RuntimeError):                              # api_cache.py:99 broadcast error
+        e.generate([list(range(geo.pos_rows + 1))], 1, 1.0, 1)
+    with pytest.raises(RuntimeError):                              # torch.topk: k out of range
+        e.generate([[1, 2, 3]], 4, 1.0, geo.vocab_size + 1)
+    with pytest.raises(ValueError):
+        e.generate([[1, 2, geo.vocab_size]], 4, 1.0, 1)
+    with pytest.raises(ValueError):
+        e.generate([[1, 2, 3]], 4, 0.0, 1)
+    with pytest.raises(MemoryError):
+        e.generate([[1, 2, 3]], 10_000, 1.0, 1)
+    # prompt exactly as long as the table is legal; decode then runs past it (pos_emb[0] quirk)
+    out = e.generate([list(range(geo.pos_rows))], 5, 1.0, 1)[0]
+    assert len(out) == geo.pos_rows + 5
+
+
+def test_sample_kvcache_drop_in_string_api():
+    z, meta = load_golden("kv_greedy")
+    m = next(x for x in meta if x["geometry"] == "train_mini" and x["eos_id"] == -1)
+    ck = checkpoint("train_mini", m["seed"])
+    vocab = {("[EOS_DISABLED]" if t == "[END_SEQUENCE]" else t): i for t, i in ck["vocab"].items()}
+    model = mg.KVModel({"model": ck["model"], "vocab": vocab}, n_head=4, dtype="fp32")
+    id2tok = {i: t for t, i in vocab.items()}
+    prompt = [id2tok[i] for i in z[m["key"] + "_prompt"].tolist()]
+    toks = mg.sample_kvcache(model, prompt, max_len=m["max_len"], temperature=1.0, top_k=1, device="cpu")
+    assert [vocab[t] for t in toks] == z[m["key"] + "_tokens"].tolist()
+    with pytest.raises(KeyError):
+        mg.sample_kvcache(model, ["[NOT IN VOCAB]"], max_len=8)
+    model.engine.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# recompute mode: model (A), generate_music/generate.py
+# ---------------------------------------------------------------------------------------------------
+def test_nocache_mode_matches_reference_model_a():
+    z, meta = load_golden("nocache_greedy")
+    for m in meta:
+        e = engine(m["geometry"], m["seed"], "fp32")
+        prompt = z[m["key"] + "_prompt"].tolist()
+        first = e.forward_nocache([prompt])[0]
+        assert np.max(np.abs(first - z[m["key"] + "_first_logits"])) < 3e-4, m["key"]
+        got = e.generate_nocache([prompt], m["max_len"] - len(prompt), 1.0, 1)[0]
+        assert got == z[m["key"] + "_tokens"].tolist(), m["key"]
+
+
+def test_nocache_batched_ragged_rows_match_oracle():
+    ck = checkpoint("tiny_hd64", 0)
+    geo = mg.GEOMETRIES["tiny_hd64"]
+    ora = gpt_nocache.NoCacheModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head)
+    prompts = [[5, 9, 100], [7, 7, 7, 1, 2, 3], [64]]
+    e = engine("tiny_hd64", 0, "fp32")
+    got = e.generate_nocache(prompts, 12, 1.0, 1)
+    for p, g in zip(prompts, got):
+        assert g == gpt_nocache.sample_ids(ora, p, max_len=len(p) + 12, temperature=1.0, top_k=1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# classifier
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["tiny", "base"])
+def test_classifier_labels_identical_logits_within_tolerance(key):
+    z, meta = load_golden("distilbert")
+    m = next(x for x in meta if x["key"] == key)
+    geo = mg.TINY_BERT if key == "tiny" else mg.DISTILBERT_BASE
+    sd = mg.make_bert_state_dict(geo, m["seed"])
+    clf = mg.Classifier(sd, n_heads=geo.n_heads, max_tokens=4096)
+    labels, logits = clf.classify(z[key + "_ids"], z[key + "_mask"])
+    want = z[key + "_logits"]
+    assert (labels == want.argmax(1)).all()
+    assert np.max(np.abs(logits - want)) < 0.25, np.max(np.abs(logits - want))
+    assert clf.predict_ids(z[key + "_ids"], z[key + "_mask"]) == [mg.ID2LABEL[int(i)] for i in want.argmax(1)]
+    clf.close()
+
+
+def test_classifier_config2_shape_matches_oracle_rows():
+    geo = mg.DISTILBERT_BASE
+    sd = mg.make_bert_state_dict(geo, 0)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(1000, 30000, (256, 64), generator=g)
+    ids[:, 0], ids[:, 63] = 101, 102
+    clf = mg.Classifier(sd, n_heads=12, max_tokens=16384)
+    labels, logits = clf.classify(ids.numpy())
+    want = obert.forward(mg.merge_lora_state_dict(sd), ids[:16], None, n_heads=12).numpy()
+    assert np.max(np.abs(logits[:16] - want)) < 0.25
+    assert (labels[:16] == want.argmax(1)).all()
+    # batch invariance: a text classified alone (SIMT small-M path + padding-free) gives the same label
+    l1, lg1 = clf.classify(ids[3:4].numpy())
+    assert l1[0] == labels[3] and np.max(np.abs(lg1[0] - logits[3])) < 0.1
+    clf.close()

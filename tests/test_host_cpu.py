@@ -1,0 +1,107 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mgea_b200 as mg
+from mgea_b200 import engine as eng
+from conftest import ROOT, has_gpu
+
+
+def test_geometry_inference_and_remap_follow_the_reference_rules():
+    geo = mg.GEOMETRIES["train_large"]
+    sd = mg.make_state_dict(geo, 0)
+    assert len(sd) == 4 + 12 * geo.n_layer
+    assert mg.infer_geometry(sd, 8) == geo                       # api_cache.py:31-37 (+ n_head :112)
+    r = mg.remap_state_dict(sd)
+    assert set(r) == set(mg.expected_keys(geo))
+    assert r["layers.3.mlp.2.weight"].shape == (256, 1024) and r["pos_emb"].shape == (255, 256)
+    assert r["layers.0.attn.in_proj_weight"] is sd["tr.layers.0.self_attn.in_proj_weight"]   # tensors untouched
+    with pytest.raises(ValueError):
+        mg.infer_geometry(sd, 7)
+
+
+def test_synthetic_vocab_satisfies_the_prompt_builder_contract():
+    v = mg.build_synthetic_vocab(8324)
+    assert len(v) == 8324 and sorted(v.values()) == list(range(8324))
+    assert [t for t, _ in sorted(v.items(), key=lambda kv: kv[1])] == sorted(v)      # ids by sorted() order
+    p = mg.build_prompt(v, 121.7, "E♭ Major", ["Strings", "Piano"])
+    assert p == ["[START_SEQUENCE]", "[BPM] 122.0", "[KEY_SIGNATURE] E- major", "[INSTRUMENT] Violin",
+                 "[INSTRUMENT] Acoustic Grand Piano"]
+    assert all(t in v for t in p)
+    with pytest.raises(KeyError):
+        mg.encode(v, ["[NOT A TOKEN]"])                          # api_cache.py:162 raises KeyError
+    prompts = mg.synthetic_prompts(v, 64, seed=0)
+    assert all(3 <= len(q) <= 6 for q in prompts) and prompts == mg.synthetic_prompts(v, 64, seed=0)
+
+
+def test_shard_range_is_a_balanced_partition():
+    for n in (0, 1, 7, 64, 512, 513):
+        for w in (1, 2, 4, 8):
+            parts = [mg.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        mg.shard_range(4, 2, 2)
+
+
+def test_header_symbols_are_all_exported_by_the_library():
+    header = open(os.path.join(ROOT, "include", "mg_engine.h")).read()
+    declared = sorted(set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(eng.EXPORTED_SYMBOLS)
+    lib = mg.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mg_abi_version() == 1
+
+
+def test_pack_prompts_and_status_mapping():
+    flat, offs = eng._pack_prompts([[1, 2, 3], [4], [5, 6]])
+    assert flat.tolist() == [1, 2, 3, 4, 5, 6] and offs.tolist() == [0, 3, 4, 6]
+    with pytest.raises(ValueError):
+        eng._pack_prompts([])
+    lib = mg.load_library()
+    for rc, exc in ((eng.MG_E_ARG, ValueError), (eng.MG_E_TOKEN, ValueError), (eng.MG_E_OOM, MemoryError),
+                    (eng.MG_E_TOPK, RuntimeError), (eng.MG_E_PROMPT_TOO_LONG, RuntimeError), (eng.MG_E_CUDA, RuntimeError)):
+        with pytest.raises(exc):
+            eng._check(lib, rc)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_engine_creation_fails_loudly_without_a_gpu():
+    ck = mg.make_checkpoint(mg.GEOMETRIES["tiny"], 0)
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        mg.Generator(ck["model"], n_head=2, dtype="fp32")
+    with pytest.raises(RuntimeError):
+        mg.Classifier(mg.make_bert_state_dict(mg.TINY_BERT, 0), n_heads=2)
+    with pytest.raises(RuntimeError, match="not found"):
+        mg.load_library("/nonexistent/libmgea_b200.so")
+
+
+def test_missing_library_is_an_error_not_a_fallback(tmp_path):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mg.load_library(str(tmp_path / "libmgea_b200.so"))
+
+
+def test_bert_geometry_inference_and_key_count():
+    sd = mg.merge_lora_state_dict(mg.make_bert_state_dict(mg.DISTILBERT_BASE, 0))
+    assert len(sd) == 104                                          # 104 tensors
+    assert sum(v.numel() for v in sd.values()) == 66_975_004
+    from mgea_b200.bert_checkpoint import infer_bert_geometry
+    assert infer_bert_geometry(sd) == mg.DISTILBERT_BASE
+    assert mg.ID2LABEL[27] == "neutral" and len(mg.ID2LABEL) == 28
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "music-generation-emotion-adaptive_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("test oracle", ""), f
