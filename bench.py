@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched KV-cache MIDI-token decoding (BASELINE.json config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one whole generation job of the workload: prefill of 64 production-shaped prompts +
+1024 decode steps with top-k-40 Philox sampling, bf16 weights + bf16 KV cache, on ONE GPU
+(65,536 new tokens per step per GPU).  At N > 1 every rank is a full replica running its own batch of
+64 (weak scaling; no collective on the decode path); only the end-to-end leg gathers the
+finished token lists.
+
+  value    tokens/s, device time (CUDA events on the engine's own stream), prompts already resident in HBM
+  e2e      the same metric through the public host call (host prompt buffers -> host token buffers)
+  roofline algorithmic HBM bytes of the decode steps (SURVEY.md 8d formula) / device time of the decode
+           loop, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the reference's CPU loop (oracle port of api_cache.py:159-184; the
+           reference tree itself does not exist on the GPU box) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GEOMETRY = "train_large"          # d 256, 8 heads (hd 32), 4 layers, 255 position rows, V 8324
+BATCH, NEW_TOKENS, TOP_K, TEMPERATURE = 64, 1024, 40, 1.0
+WORKLOAD = ("config3: MIDI GPT-2 (train_large.py size) top-k=40 sampling, 1024 new tokens, batch 64, "
+            "bf16 weights + bf16 KV cache")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(geo, prompt_lens, n_steps, s_w=2, s_kv=2):
+    """bytes(step) = W + sum_b (T_b + 1) kappa + B kappa + B d s_w."""
+    d, L, V, B = geo.d_model, geo.n_layer, geo.vocab_size, len(prompt_lens)
+    W = (L * (12 * d * d + 13 * d) + V * d + V) * s_w
+    kappa = L * 2 * d * s_kv
+    total = 0
+    for i in range(n_steps):
+        kv_read = sum((tp + i + 1) * kappa for tp in prompt_lens)
+        total += W + kv_read + B * kappa + B * d * s_w
+    return total, W, kappa
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.ok and self.is_alive():
+            self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def host_threads():
+    """Host cores this process may actually use (cgroup / affinity aware), capped at 32 for the small GEMMs."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
+
+
+def build_workload(mg):
+    geo = mg.GEOMETRIES[GEOMETRY]
+    ck = mg.make_checkpoint(geo, 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], BATCH, seed=0)]
+    return geo, ck, prompts
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference loop (oracle port of the reference's sample_kvcache; batch-1 like the reference)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_sample(ck, geo, prompt, n_new, threads):
+    from oracle import gpt_kv
+    import mgea_b200 as mg
+    torch.set_num_threads(threads)
+    model = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head)
+    g = torch.Generator().manual_seed(0)
+    t0 = time.perf_counter()
+    out = gpt_kv.sample_ids(model, prompt, max_len=len(prompt) + n_new, temperature=TEMPERATURE, top_k=TOP_K, eos_id=-1,
+                            generator=g)
+    dt = time.perf_counter() - t0
+    assert len(out) == len(prompt) + n_new
+    return n_new / dt, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU path (batch-1 loop, api_cache.py:159-184) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import mgea_b200 as mg
+    geo, ck, prompts = build_workload(mg)
+    threads = host_threads()
+    n_new = 192                                   # bounded sample per step: one prompt, 192 new tokens
+    for _ in range(args.warmup):
+        cpu_reference_sample(ck, geo, prompts[0], 32, threads)
+    rates, t_all = [], 0.0
+    for i in range(args.steps):
+        r, dt = cpu_reference_sample(ck, geo, prompts[i % len(prompts)], n_new, threads)
+        rates.append(r)
+        t_all += dt
+    value = args.steps * n_new / t_all
+    sample = (f"oracle port of the reference batch-1 sample_kvcache loop (the reference is batch-1 only): 1 of the 64 "
+              f"prompts, {n_new} new tokens per step (cache length <= {6 + n_new}; the full workload runs to 1030, where "
+              f"the reference's per-token cost is higher), fp32, torch CPU, {threads} threads")
+    line = {
+        "impl": "reference", "metric": "midi_decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "geometry": GEOMETRY, "batch": 1, "new_tokens": n_new, "top_k": TOP_K},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 latency and classifier side measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.warmup < 3:
+        args.warmup = 3                                           # timing rule: W >= 3
+
+    import mgea_b200 as mg
+    geo, ck, prompts = build_workload(mg)
+    prompt_lens = [len(p) for p in prompts]
+    eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=BATCH, max_seq=1088, device=local_rank)
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.synchronize()
+
+    def device_step(seed):
+        eng.upload(prompts, NEW_TOKENS)                           # inputs resident in HBM before the timed region
+        eng.synchronize()
+        eng.run(TEMPERATURE, TOP_K, eos_id=-1, seed=seed, seq_index_base=rank * BATCH)
+        eng.synchronize()
+        return eng.last_timing()
+
+    for i in range(args.warmup):
+        device_step(100 + i)
+    launches0 = eng.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    tot_ms = dec_ms = 0.0
+    dec_steps = 0
+    for i in range(args.steps):
+        t = device_step(i)
+        tot_ms += t["total_ms"]
+        dec_ms += t["decode_ms"]
+        dec_steps += t["steps"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.result()
+    launches = eng.stats()["kernel_launches"] - launches0
+    tokens_out = eng.download()
+    assert all(len(o) == len(p) + NEW_TOKENS for o, p in zip(tokens_out, prompts))
+
+    # ---- end to end: host prompt buffers -> host token buffers through the public call ----
+    st0 = eng.stats()
+    barrier()
+    e0 = time.perf_counter()
+    for i in range(args.steps):
+        out = eng.generate(prompts, NEW_TOKENS, TEMPERATURE, TOP_K, eos_id=-1, seed=i, seq_index_base=rank * BATCH)
+        if world > 1:
+            mg.gather_token_lists(out, BATCH * world)             # the only exchange of the path: final token gather
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    st1 = eng.stats()
+
+    t_dev = torch.tensor([tot_ms, dec_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    tot_ms, dec_ms, e2e_ms = [float(x) for x in t_dev.tolist()]
+
+    tokens_per_step = BATCH * NEW_TOKENS * world
+    value = tokens_per_step * args.steps / (tot_ms * 1e-3)
+    e2e_value = tokens_per_step * args.steps / (e2e_ms * 1e-3)
+    alg_bytes, W_bytes, kappa = algorithmic_bytes(geo, prompt_lens, NEW_TOKENS)
+    achieved = alg_bytes * args.steps / (dec_ms * 1e-3) / 1e9     # GB/s per GPU over the decode loop
+    line = {
+        "metric": "midi_decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "geometry": GEOMETRY, "d_model": geo.d_model, "n_head": geo.n_head,
+                   "n_layer": geo.n_layer, "vocab": geo.vocab_size, "batch_per_gpu": BATCH, "new_tokens": NEW_TOKENS,
+                   "top_k": TOP_K, "temperature": TEMPERATURE, "prompt_tokens": f"{min(prompt_lens)}-{max(prompt_lens)}",
+                   "parallelism": f"replicas x{world} (batch sharded, no decode-path collective)",
+                   "weights": "random-init (seed 0), synthetic 8324-token vocab",
+                   "l2": "KV working set grows to 270 MB per GPU (> 126 MB L2) and is rewritten every step: inputs "
+                         "larger than L2, no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": "tokens/s",
+                "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,
+                "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "decode step (all kernels of the captured step graph); dominant kernel decode_attn_kernel",
+                     "algorithmic_bytes_per_job": alg_bytes, "weight_bytes_per_step": W_bytes, "kv_bytes_per_position": kappa,
+                     "frac_of_nominal_8TBs": achieved / 8000.0, "decode_ms_per_step": dec_ms / max(dec_steps, 1)},
+        "wall_s_timed_region": wall,
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["batch1"] = batch1_latency(mg)
+        line["classifier"] = classifier_throughput(mg, tf_peak, peak_src)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        n_new = 1024
+        v, dt = cpu_reference_sample(ck, geo, prompts[0], n_new, threads)
+        bt0 = time.perf_counter()
+        from oracle import gpt_kv
+        eq = [p for p in prompts if len(p) == 5][:16]
+        gpt_kv.batched_decode_step_time_port(gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head), eq, 96,
+                                             TEMPERATURE, TOP_K, torch.Generator().manual_seed(0))
+        batched = len(eq) * 96 / (time.perf_counter() - bt0)
+        line["cpu_baseline"] = {
+            "batched_restatement_tokens_per_s": batched,
+            "batched_restatement_note": (f"NOT the reference's loop: GPTWithKV.forward fed idx [{len(eq)},1] with the .item() "
+                                         "stop removed (SURVEY 8d), 96 steps, same host threads"),
+            "value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": (f"oracle port of the reference batch-1 sample_kvcache loop on 1 of the 64 prompts, all {n_new} new "
+                       f"tokens, top-k 40, fp32 torch CPU ({dt:.1f} s); the reference sampler is batch-1 only, so a "
+                       f"64-prompt job costs 64 such runs")}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def batch1_latency(mg):
+    """BASELINE metric part 2: p50 ms/token @ batch 1 (config 1 shape: train_mini, 5-token prompt, 507 new tokens)."""
+    geo = mg.GEOMETRIES["train_mini"]
+    ck = mg.make_checkpoint(geo, 0)
+    prompt = mg.encode(ck["vocab"], mg.synthetic_prompts(ck["vocab"], 1, seed=1)[0])
+    out = {}
+    for dtype in ("fp32", "bf16"):
+        eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype=dtype, max_batch=1, max_seq=1088)
+        per_tok = []
+        n_new = 512 - len(prompt)
+        for i in range(9):
+            eng.upload([prompt], n_new)
+            eng.run(1.0, 1, eos_id=-1)
+            eng.synchronize()
+            t = eng.last_timing()
+            if i >= 2:
+                per_tok.append(t["decode_ms"] / max(t["steps"], 1))
+        out[dtype] = {"p50_ms_per_token": statistics.median(per_tok), "runs": len(per_tok), "new_tokens": n_new,
+                      "note": "median over runs of (decode-loop device time / tokens); greedy (top_k=1)"}
+        eng.close()
+    return out
+
+
+def classifier_throughput(mg, tf_peak, peak_src):
+    """BASELINE config 2: DistilBERT-base, 256 synthetic texts x 64 tokens, bf16 (device time, ids resident)."""
+    geo = mg.DISTILBERT_BASE
+    sd = mg.make_bert_state_dict(geo, 0)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(1000, 30000, (256, 64), generator=g)
+    ids[:, 0], ids[:, 63] = 101, 102
+    clf = mg.Classifier(sd, n_heads=12, max_tokens=16384)
+    ids_np = ids.numpy()
+    clf.upload(ids_np)
+    for _ in range(3):
+        clf.run()
+    clf.synchronize()
+    times = []
+    for _ in range(10):
+        clf.upload(ids_np)
+        clf.synchronize()
+        t0 = time.perf_counter()
+        clf.run()
+        clf.synchronize()
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    e0 = time.perf_counter()
+    for _ in range(5):
+        clf.classify(ids_np)
+    e2e = (time.perf_counter() - e0) / 5
+    flop = 16384 * 6 * (4 * 2 * 768 * 768 + 2 * 2 * 768 * 3072 + 4 * 64 * 768) + 256 * 2 * (768 * 768 + 768 * 28)
+    clf.close()
+    return {"workload": "config2: DistilBERT-base, 256 texts x 64 tokens, bf16", "texts_per_s": 256 / t, "ms": t * 1e3,
+            "e2e_texts_per_s": 256 / e2e, "tflops": flop / t / 1e12, "tensor_peak_tflops": tf_peak,
+            "frac_of_tensor_peak": flop / t / 1e12 / tf_peak, "peak_source": peak_src,
+            "timing": "host wall clock around run + stream sync, median of 10"}
+
+
+if __name__ == "__main__":
+    main()

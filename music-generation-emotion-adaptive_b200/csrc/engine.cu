@@ -96,6 +96,7 @@ struct mg_engine {
 
   cudaGraphExec_t graph = nullptr;
   int graph_B = -1;
+  uint64_t graph_kernels = 0;          // kernels inside the captured decode step (counted per replay)
 
   uint64_t h2d = 0, d2h = 0, launches0 = 0;
   float t_total = 0, t_prefill = 0, t_decode = 0;
@@ -251,7 +252,10 @@ int run_decode_loop(mg_engine* e, int eos_id) {
       if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
       cudaGraph_t gr = nullptr;
       MG_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      const uint64_t before = g_kernel_launches.load();
       const int rc = decode_step<T>(e);
+      e->graph_kernels = g_kernel_launches.load() - before;
+      g_kernel_launches.fetch_sub(e->graph_kernels);          // capture launches nothing; replays are counted
       cudaError_t ce = cudaStreamEndCapture(e->stream, &gr);
       if (rc != MG_OK) { if (gr) cudaGraphDestroy(gr); return rc; }
       if (ce != cudaSuccess) return fail(MG_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
@@ -264,8 +268,12 @@ int run_decode_loop(mg_engine* e, int eos_id) {
   }
   int done_steps = 0;
   for (int i = 0; i < steps; ++i) {
-    if (graph_ok) MG_CUDA_OK(cudaGraphLaunch(e->graph, e->stream));
-    else MG_TRY(decode_step<T>(e));
+    if (graph_ok) {
+      MG_CUDA_OK(cudaGraphLaunch(e->graph, e->stream));
+      g_kernel_launches.fetch_add(e->graph_kernels, std::memory_order_relaxed);
+    } else {
+      MG_TRY(decode_step<T>(e));
+    }
     ++done_steps;
     if (eos_id >= 0 && (i % 32) == 31 && i + 1 < steps) {
       MG_TRY(launch_count_active(e->stream, e->st.finished, e->cur_B, e->d_active));

@@ -738,15 +738,34 @@ __device__ int sample_row(const float* __restrict__ row, int V, float temperatur
         if ((u & mask) == prefix) atomicAdd(&ss.hist[(u >> shift) & 255u], 1u);
       }
       __syncthreads();
-      if (tid == 0) {
-        int remaining = ss.remaining, cum = 0, bin = 255;
-        for (; bin > 0; --bin) {
-          const int hcount = static_cast<int>(ss.hist[bin]);
-          if (cum + hcount >= remaining) break;
-          cum += hcount;
+      if (warp == 0) {
+        // bins 255..0 in descending order, 8 per lane: lane 0 owns bins 255..248, lane 31 owns 7..0
+        const int remaining = ss.remaining;
+        int hb[8], mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hb[j] = static_cast<int>(ss.hist[255 - (lane * 8 + j)]);
+          mine += hb[j];
         }
-        ss.remaining = remaining - cum;
-        ss.prefix = prefix | (static_cast<uint32_t>(bin) << shift);
+        int inc = mine;                                  // inclusive prefix over lanes (descending bins)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const int before = inc - mine;                   // elements in strictly higher bins of earlier lanes
+        const bool here = before < remaining && inc >= remaining;
+        const unsigned who = __ballot_sync(0xffffffffu, here);
+        // `who` has exactly one bit unless the row holds fewer than `remaining` candidates (cannot happen: k <= V)
+        if (here && (who & ((1u << lane) - 1)) == 0) {
+          int cum = before, j = 0;
+          for (; j < 7; ++j) {
+            if (cum + hb[j] >= remaining) break;
+            cum += hb[j];
+          }
+          ss.remaining = remaining - cum;
+          ss.prefix = prefix | (static_cast<uint32_t>(255 - (lane * 8 + j)) << shift);
+        }
       }
       __syncthreads();
       prefix = ss.prefix;
