@@ -44,7 +44,7 @@ enum mg_dtype_mode {
 };
 
 /* Model geometry.  Replaces the shape inference of api_cache.py:31-37 plus the hard-coded n_head
- * of api_cache.py:112; d_ff is 4*d_model in every reference trainer (train/*.py). */
+ * of api_cache.py:112; d_ff is 4*d_model in every reference trainer (all scripts under train/). */
 typedef struct mg_geometry {
   int32_t vocab_size;
   int32_t pos_rows;

@@ -1,0 +1,58 @@
+// Host interface of the persistent cluster decode kernel (implementation: decode_mega.cu).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mg {
+namespace mega {
+
+constexpr int kMegaCluster = 4;       // CTAs per cluster = d_model / 64 feature slices
+constexpr int kMegaMaxTopK = 64;      // the in-kernel sampler handles 1 <= top_k <= 64
+constexpr int kMegaMaxNL = 2304;      // vocabulary rows per CTA, padded to 256: ceil(V / 4) <= 2304
+constexpr int kMegaStageBytes = 32768;
+constexpr int kMegaStagesPerLayer = 13;   // in_proj 4 + out_proj 1 + mlp.0 4 + mlp.2 4 stages of 32 KB
+constexpr int kMegaMaxLayers = 8;
+constexpr int kMegaMaxLayersSmem = 4;  // layers whose LN / bias parameters are kept in shared memory
+constexpr int kMegaStages2 = 4;       // ring depth (32 KB stages) when <= 2 sequences per cluster
+constexpr int kMegaStages4 = 2;       // ... when 3..4 sequences per cluster
+constexpr int kMegaMaxSeqPerCluster = 4;
+
+struct MegaLayer {
+  const float *b_in, *b_out, *b1, *b2, *ln1w, *ln1b, *ln2w, *ln2b;
+  bf16 *kc, *vc;                      // cache slices [B][4][Tmax][64]
+};
+
+struct MegaParams {
+  const uint8_t* packed;              // pre-tiled weight stream (mega_pack_weights), [4 ranks][stages][32 KB]
+  const MegaLayer* layers;            // device array [n_layer]
+  const bf16* tok_emb;
+  const bf16* pos_emb;
+  const float* head_b;
+  const SampleParams* sp;
+  DecodeState st;
+  int n_layer, head_dim, V, VS, NP;   // VS = ceil(V / 4) vocabulary rows per CTA, NP = ceil(VS / 256) tile pairs
+  int B, S, Tmax, n_steps;            // S = sequences per cluster
+  // parity/debug (mg_step_logits): raw logits [n_steps][B][V] and teacher-forced next tokens [B][forced_stride]
+  float* dbg_logits;
+  const int32_t* forced;
+  int forced_stride;
+  // optional phase timeline of one step (globaltimer ns), written by cluster 0 / CTA 0: [64] entries
+  unsigned long long* prof;
+  int prof_step;
+  int dbg_skip_loads;                 // timing experiment only: signal the stages without copying (results are garbage)
+};
+
+int mega_init();
+size_t mega_packed_bytes(int n_layer, int NP);
+int mega_pack_weights(cudaStream_t stream, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1,
+                      const bf16* const* w2, const bf16* head, int n_layer, int V, int VS, int NP, void* dst);
+int mega_max_clusters(int smax);      // co-resident clusters (0 when the query fails)
+int launch_decode_mega(cudaStream_t stream, const MegaParams& p, int n_clusters);
+
+}  // namespace mega
+}  // namespace mg

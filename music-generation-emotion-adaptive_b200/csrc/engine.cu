@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -24,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "decode_mega.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "mg_engine.h"
@@ -94,6 +96,13 @@ struct mg_engine {
   int cur_B = 0, cur_M = 0, cur_max_tp = 0, cur_steps = 0;
   bool uploaded = false;
 
+  // persistent cluster decode kernel (decode_mega.cu): bf16, d_model 256, d_ff 1024
+  bool mega_ok = false, use_mega = true, last_run_mega = false;
+  uint8_t* d_mega_packed = nullptr;
+  mega::MegaLayer* d_mega_layers = nullptr;
+  unsigned long long* d_prof = nullptr;
+  int mega_clusters2 = 0, mega_clusters4 = 0;   // co-resident clusters for <= 2 / <= 4 sequences per cluster
+
   cudaGraphExec_t graph = nullptr;
   int graph_B = -1;
   uint64_t graph_kernels = 0;          // kernels inside the captured decode step (counted per replay)
@@ -119,6 +128,10 @@ struct mg_engine {
 };
 
 namespace {
+
+bool run_decode_mega(mg_engine* e, int top_k, int* rc, float* dbg_logits = nullptr, const int32_t* forced = nullptr,
+                     int forced_stride = 0);
+int setup_mega(mg_engine* e);
 
 int decode_nsplit(const mg_engine* e, int B) {
   int n = ceil_div(2 * 148, B);
@@ -293,7 +306,10 @@ int run_impl(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t se
   MG_CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
   MG_TRY(prefill<T>(e));
   MG_CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
-  MG_TRY(run_decode_loop<T>(e, eos_id));
+  int mrc = MG_OK;
+  e->last_run_mega = std::is_same<T, bf16>::value && run_decode_mega(e, top_k, &mrc);
+  MG_TRY(mrc);
+  if (!e->last_run_mega) MG_TRY(run_decode_loop<T>(e, eos_id));
   MG_CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
   return MG_OK;
 }
@@ -325,6 +341,88 @@ int forward_nocache(mg_engine* e, int B, int Tcap, int max_len_now) {
     MG_TRY((launch_layernorm<float, T>(e->stream, e->x, w.ln2w, w.ln2b, y, e->x, M, d, 1e-5f)));
   }
   return MG_OK;
+}
+
+// ---- persistent cluster decode kernel: eligibility, tables, launch ------------------------------
+int setup_mega(mg_engine* e) {
+  const mg_geometry& g = e->geo;
+  e->mega_ok = false;
+  const int hd = g.d_model / g.n_head;
+  const int VS = ceil_div(g.vocab_size, mega::kMegaCluster);
+  if (!e->use_mega || e->dtype != MG_DTYPE_BF16 || g.d_model != 256 || g.d_ff != 1024 || (hd != 32 && hd != 64) ||
+      ceil_div(VS, 256) * 256 > mega::kMegaMaxNL || VS < mega::kMegaMaxTopK)
+    return MG_OK;
+  MG_TRY(mega::mega_init());
+  e->mega_clusters2 = mega::mega_max_clusters(2);
+  e->mega_clusters4 = mega::mega_max_clusters(4);
+  if (e->mega_clusters2 <= 0 && e->mega_clusters4 <= 0) return MG_OK;
+  const int L = g.n_layer;
+  if (L > mega::kMegaMaxLayers || L > mega::kMegaMaxLayersSmem) return MG_OK;
+  const int NP = ceil_div(VS, 256);
+  std::vector<mega::MegaLayer> lay(L);
+  std::vector<const bf16*> w_in(L), w_out(L), w1(L), w2(L);
+  for (int l = 0; l < L; ++l) {
+    LayerW& w = e->layers[l];
+    w_in[l] = reinterpret_cast<const bf16*>(w.w_in); w_out[l] = reinterpret_cast<const bf16*>(w.w_out);
+    w1[l] = reinterpret_cast<const bf16*>(w.w1); w2[l] = reinterpret_cast<const bf16*>(w.w2);
+    lay[l] = mega::MegaLayer{w.b_in, w.b_out, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
+                             reinterpret_cast<bf16*>(w.kc), reinterpret_cast<bf16*>(w.vc)};
+  }
+  if (!e->d_mega_packed) {
+    MG_TRY(e->dmalloc(&e->d_mega_packed, mega::mega_packed_bytes(L, NP)));
+    MG_TRY(e->dmalloc(&e->d_mega_layers, sizeof(mega::MegaLayer) * L));
+  }
+  MG_TRY(mega::mega_pack_weights(e->stream, w_in.data(), w_out.data(), w1.data(), w2.data(),
+                                 reinterpret_cast<const bf16*>(e->head_w), L, g.vocab_size, VS, NP, e->d_mega_packed));
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_mega_layers, lay.data(), sizeof(mega::MegaLayer) * L, cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->mega_ok = true;
+  return MG_OK;
+}
+
+// Returns true (and launches) when the persistent kernel can serve this call.
+bool run_decode_mega(mg_engine* e, int top_k, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride) {
+  *rc = MG_OK;
+  if (!e->mega_ok || top_k < 1 || top_k > mega::kMegaMaxTopK || e->cur_steps <= 0) return false;
+  const int B = e->cur_B;
+  int S = 0, n_clusters = 0;
+  for (int s_try = 1; s_try <= mega::kMegaMaxSeqPerCluster; ++s_try) {
+    const int avail = s_try <= 2 ? e->mega_clusters2 : e->mega_clusters4;
+    const int need = ceil_div(B, s_try);
+    if (avail > 0 && need <= avail) { S = s_try; n_clusters = need; break; }
+  }
+  if (S == 0) return false;
+  const mg_geometry& g = e->geo;
+  mega::MegaParams p{};
+  p.packed = e->d_mega_packed; p.layers = e->d_mega_layers;
+  p.tok_emb = reinterpret_cast<const bf16*>(e->tok_emb); p.pos_emb = reinterpret_cast<const bf16*>(e->pos_emb);
+  p.head_b = e->head_b; p.sp = e->d_sp; p.st = e->st;
+  p.n_layer = g.n_layer; p.head_dim = g.d_model / g.n_head; p.V = g.vocab_size;
+  p.VS = ceil_div(g.vocab_size, mega::kMegaCluster); p.NP = ceil_div(p.VS, 256);
+  p.B = B; p.S = S; p.Tmax = e->max_seq; p.n_steps = e->cur_steps;
+  p.dbg_logits = dbg_logits; p.forced = forced; p.forced_stride = forced_stride;
+  p.prof = nullptr; p.prof_step = -1;
+  p.dbg_skip_loads = std::getenv("MG_MEGA_SKIP_LOADS") ? 1 : 0;
+  if (const char* ps = std::getenv("MG_MEGA_PROF_STEP")) {       // debug: phase timeline of one decode step -> stderr
+    if (!e->d_prof) { if (e->dmalloc(&e->d_prof, 128 * sizeof(unsigned long long)) != MG_OK) e->d_prof = nullptr; }
+    if (e->d_prof) {
+      cudaMemsetAsync(e->d_prof, 0, 128 * sizeof(unsigned long long), e->stream);
+      p.prof = e->d_prof; p.prof_step = std::atoi(ps);
+    }
+  }
+  *rc = mega::launch_decode_mega(e->stream, p, n_clusters);
+  if (p.prof && *rc == MG_OK) {
+    unsigned long long h[128];
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(h, e->d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[mega prof] step %d (ns since first stamp):", p.prof_step);
+    for (int i = 0; i < 64 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
+    fprintf(stderr, "\n[mega prof] MMA thread, layer 0 (wait-B, B-ready, committed per GEMM):");
+    for (int i = 64; i < 128 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[0]));
+    fprintf(stderr, "\n");
+  }
+  e->t_steps = e->cur_steps;
+  return true;
 }
 
 int parse_layer_name(const std::string& name, int* layer, std::string* leaf) {
@@ -563,7 +661,8 @@ int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max
   if (g.vocab_size <= 0 || g.pos_rows <= 0 || g.d_model <= 0 || g.n_head <= 0 || g.n_layer <= 0 || g.d_ff <= 0)
     return fail(MG_E_SHAPE, "non-positive geometry field");
   if (g.d_model % g.n_head) return fail(MG_E_SHAPE, "d_model not divisible by n_head");
-  if (g.d_model % 16 || g.d_ff % 16 || g.d_model > 1024) return fail(MG_E_SHAPE, "d_model / d_ff must be multiples of 16, d_model <= 1024");
+  if (g.d_model % 64 || g.d_ff % 16 || g.d_model > 1024)
+    return fail(MG_E_SHAPE, "d_model must be a multiple of 64 (KV-cache slices) and <= 1024, d_ff a multiple of 16");
   const int hd = g.d_model / g.n_head;
   if (hd % 8 || hd > 64 || (hd & (hd - 1))) return fail(MG_E_SHAPE, "head_dim must be 8, 16, 32 or 64");
   if (max_batch <= 0 || max_seq <= 0) return fail(MG_E_ARG, "max_batch / max_seq must be positive");
@@ -576,6 +675,8 @@ int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max
   e->use_tc = dtype_mode == MG_DTYPE_BF16 && !(env_gemm && std::strcmp(env_gemm, "simt") == 0);
   const char* env_graph = std::getenv("MG_NO_GRAPH");
   e->use_graph = !(env_graph && env_graph[0] == '1');
+  const char* env_mega = std::getenv("MG_NO_MEGA");
+  e->use_mega = !(env_mega && env_mega[0] == '1');
   e->launches0 = g_kernel_launches.load();
   int rc = MG_OK;
   auto body = [&]() -> int {
@@ -704,6 +805,7 @@ int mg_engine_finalize(mg_engine* e) {
     }
     MG_TRY(make_wmaps(&e->m_head, e->head_w, e->geo.vocab_size, d));
   }
+  MG_TRY(setup_mega(e));
   e->ready = true;
   return MG_OK;
 }
@@ -781,6 +883,26 @@ int mg_step_logits(mg_engine* e, const int32_t* ids, const int32_t* offs, int B,
   }
   const bool is_bf16 = e->dtype == MG_DTYPE_BF16;
   MG_TRY(is_bf16 ? prefill<bf16>(e) : prefill<float>(e));
+  if (is_bf16 && e->mega_ok) {
+    // the persistent cluster kernel in teacher-forcing mode: same code path as mg_run, logits dumped per step
+    float* d_lg = nullptr;
+    const size_t n = static_cast<size_t>(n_steps) * B * V;
+    MG_TRY(e->dmalloc(&d_lg, n * sizeof(float)));
+    *e->h_sp = SampleParams{1.0f, 1, -1, 0, 0, 0};
+    int rc = cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream) == cudaSuccess ? MG_OK : MG_E_CUDA;
+    int mrc = MG_OK;
+    if (rc == MG_OK && run_decode_mega(e, 1, &mrc, d_lg, n_steps > 1 ? e->d_forced : nullptr, n_steps)) {
+      rc = mrc;
+      if (rc == MG_OK && cudaMemcpyAsync(logits_out, d_lg, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = MG_E_CUDA;
+      if (rc == MG_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(MG_E_CUDA, std::string("persistent decode kernel: ") + cudaGetErrorString(cudaGetLastError()));
+      e->dfree(d_lg);
+      e->d2h += n * sizeof(float);
+      e->uploaded = false;
+      return rc;
+    }
+    e->dfree(d_lg);
+    MG_TRY(rc);
+  }
   for (int i = 0; i < n_steps; ++i) {
     MG_TRY(is_bf16 ? decode_forward<bf16>(e) : decode_forward<float>(e));
     MG_CUDA_OK(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(i) * B * V, sizeof(float) * V, e->logits,

@@ -286,13 +286,16 @@ __global__ void kv_append_kernel(const T* __restrict__ qkv, const int32_t* __res
     const int rem = i - r * 2 * C;
     const int which = rem / C, c = rem - which * C;
     const uint4 v = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(r) * 3 * d + (1 + which) * d + c * CH);
-    T* dst = (which ? vcache : kcache) + (static_cast<size_t>(row_seq[r]) * Tmax + row_pos[r]) * d + c * CH;
+    // cache layout [B][d/64 slices][Tmax][64]: one (sequence, slice) stream is contiguous 64-feature rows
+    const int fo = c * CH, sl = fo >> 6, within = fo & 63;
+    T* dst = (which ? vcache : kcache) +
+             ((static_cast<size_t>(row_seq[r]) * (d >> 6) + sl) * Tmax + row_pos[r]) * 64 + within;
     *reinterpret_cast<uint4*>(dst) = v;
   }
 }
 
 // =================================================================================================
-// Split-K flash-decoding attention (token-major cache: one 16-byte chunk per lane per row pass)
+// Split-K flash-decoding attention (cache [B][d/64][Tmax][64]: one 16-byte chunk per lane per row pass)
 // =================================================================================================
 constexpr int kAttnWarps = 8;
 
@@ -334,16 +337,19 @@ decode_attn_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restr
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
       const int which = c / C, cc = c - which * C;
       const uint4 v = *reinterpret_cast<const uint4*>((which ? vnew : knew) + cc * CH);
-      *reinterpret_cast<uint4*>((which ? vc : kc) + static_cast<size_t>(len) * d + cc * CH) = v;
+      const int fo = cc * CH;
+      *reinterpret_cast<uint4*>((which ? vc : kc) + (static_cast<size_t>(fo >> 6) * Tmax + len) * 64 + (fo & 63)) = v;
     }
   }
 
   float q[CPL][CH], acc[CPL][CH], m_run[CPL], l_run[CPL];
   bool act[CPL];
+  size_t coff[CPL];                                   // offset of this lane's chunk inside the [slice][Tmax][64] block
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
     const int c = lane + 32 * j;
     act[j] = c < C;
+    coff[j] = (static_cast<size_t>((c * CH) >> 6) * Tmax) * 64 + ((c * CH) & 63);
     m_run[j] = -INFINITY;
     l_run[j] = 0.0f;
 #pragma unroll
@@ -364,13 +370,13 @@ decode_attn_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restr
     for (int i = 0; i < R; ++i) {
       const int rr = r + i;
       // the new token's row is not in the cache from this kernel's point of view (read-only path)
-      const T* kp = (rr == len) ? knew : kc + static_cast<size_t>(rr) * d;
-      const T* vp = (rr == len) ? vnew : vc + static_cast<size_t>(rr) * d;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         if (rr < r1 && act[j]) {
-          kraw[i][j] = ld_stream16(kp + (lane + 32 * j) * CH);
-          vraw[i][j] = ld_stream16(vp + (lane + 32 * j) * CH);
+          const T* kp = (rr == len) ? knew + (lane + 32 * j) * CH : kc + coff[j] + static_cast<size_t>(rr) * 64;
+          const T* vp = (rr == len) ? vnew + (lane + 32 * j) * CH : vc + coff[j] + static_cast<size_t>(rr) * 64;
+          kraw[i][j] = ld_stream16(kp);
+          vraw[i][j] = ld_stream16(vp);
         } else {
           kraw[i][j] = make_uint4(0, 0, 0, 0);
           vraw[i][j] = make_uint4(0, 0, 0, 0);

@@ -53,7 +53,7 @@ int launch_layernorm(cudaStream_t s, const TI* x, const float* w, const float* b
 template <typename T>
 int launch_gemm_simt(cudaStream_t s, const T* A, int lda, const T* W, int M, int N, int K, const GemmEpilogue& epi);
 
-// Prefill: scatter the K and V thirds of qkv [M,3d] into the token-major caches [B][Tmax][d].
+// Prefill: scatter the K and V thirds of qkv [M,3d] into the caches [B][d/64 slices][Tmax][64].
 template <typename T>
 int launch_kv_append(cudaStream_t s, const T* qkv, const int32_t* row_seq, const int32_t* row_pos, T* kcache, T* vcache,
                      int M, int d, int Tmax);
