@@ -175,10 +175,11 @@ __device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_
       breg[ks][1] = *reinterpret_cast<const uint32_t*>(bp + ks * 16 + 8);
     }
   }
+  float acc2[2][4];                                        // odd k-steps: halves the dependent MMA chains
 #pragma unroll
   for (int t = 0; t < 2; ++t)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+    for (int e = 0; e < 4; ++e) { acc[t][e] = 0.f; acc2[t][e] = 0.f; }
   // ldmatrix row address of this lane: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, k chunk (m >> 1)
   const int lrow = ((lane >> 3) & 1) * 8 + (lane & 7);
   const int lchunk = lane >> 4;
@@ -195,7 +196,8 @@ __device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_
         for (int ks = 0; ks < 4; ++ks) {
           uint32_t a[4];
           ldmatrix_x4(rbase + (((ks * 2 + lchunk) ^ (i & 7)) << 4), a);
-          mma_bf16_16816(acc[t], a, breg[kb * 4 + ks][0], breg[kb * 4 + ks][1]);
+          if (ks & 1) mma_bf16_16816(acc2[t], a, breg[kb * 4 + ks][0], breg[kb * 4 + ks][1]);
+          else mma_bf16_16816(acc[t], a, breg[kb * 4 + ks][0], breg[kb * 4 + ks][1]);
         }
       }
     }
@@ -203,6 +205,10 @@ __device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_
     if (lane == 0) ptx::mbar_arrive(&empty[rp.stage]);
     rp.template advance<NSTAGE>();
   }
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[t][e] += acc2[t][e];
 }
 
 template <int SMAX, int NSTAGE>
@@ -446,6 +452,18 @@ decode_mega_kernel(const MegaParams p) {
                         ((static_cast<size_t>(b0 + s) * CL + r) * p.Tmax + misc.len[s]) * FS + c * 8;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>((which ? vnew : knew) + s * FS + c * 8);
           }
+          // L2 prefetch of the NEXT layer's K/V streams of this CTA (next step's layer 0 after the last layer):
+          // HBM keeps streaming while the GEMM / exchange / sampler phases run; four bulk prefetches per layer
+          if (cw == NCW - 1 && lane < 2 * S) {
+            const int s = lane >> 1, which = lane & 1;
+            const int ln = (l + 1 < n_layer) ? l + 1 : 0;
+            const int rows = misc.len[s] + (ln == 0 ? 1 : 0);
+            if (!misc.fin[s] && rows > 0) {
+              const MegaLayer& nx = p.layers[ln];
+              const bf16* src = (which ? nx.vc : nx.kc) + (static_cast<size_t>(b0 + s) * CL + r) * p.Tmax * FS;
+              ptx::prefetch_l2_bulk(src, static_cast<uint32_t>(rows) * FS * 2);
+            }
+          }
           {
             // warps are dealt round-robin to the sequences: warp cw serves sequence cw % S as its (cw / S)-th worker
             const int s = cw % S, wi = cw / S, nws = (NCW - s + S - 1) / S;
@@ -459,7 +477,9 @@ decode_mega_kernel(const MegaParams p) {
             float m_run = -INFINITY, l_run = 0.f, acc[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-            constexpr int U = 8;                              // 4-row groups in flight per warp
+            // Batches of U four-row groups: all 2 x U 16-byte loads of a batch are issued before the first use
+            // (the scoreboard tracks loads per batch, so finer-grained register pipelining serialises them).
+            constexpr int U = 8;
             for (int base = wi * 4 * U; base < len; base += nws * 4 * U) {
               uint4 kr[U], vr[U];
 #pragma unroll
@@ -768,6 +788,21 @@ decode_mega_kernel(const MegaParams p) {
               }
             }
             ptx::named_bar_sync(gbar, gn);
+            // the owner merges sorted lists: sort the k gathered entries (value descending, index ascending)
+            for (int j = gt; j < k; j += gn) {
+              const uint2 mine = gl[j];
+              const float mv = __uint_as_float(mine.x);
+              int rank_j = 0;
+              for (int i = 0; i < k; ++i) {
+                const uint2 o = gl[i];
+                const float ov = __uint_as_float(o.x);
+                rank_j += (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && i < j)));
+              }
+              clist[rank_j] = mine;
+            }
+            ptx::named_bar_sync(gbar, gn);
+            for (int j = gt; j < k; j += gn) gl[j] = clist[j];
+            ptx::named_bar_sync(gbar, gn);
           }
           // ship the k local candidates to the owner CTA of sequence s
           const uint32_t owner = static_cast<uint32_t>(s % CL);
@@ -791,6 +826,8 @@ decode_mega_kernel(const MegaParams p) {
           ptx::mbar_wait(&bars.cand, cand_use & 1);
           ++cand_use;
           bar_compute();
+          // every CTA's list arrives sorted (value descending, index ascending): the global rank of an entry is
+          // its own position plus, for each other list, the number of entries that precede it (binary search)
           const int n = CL * k;                               // <= 256 candidates, one per thread
           uint2 mine = make_uint2(0, 0);
           int rk = 0;
@@ -798,14 +835,20 @@ decode_mega_kernel(const MegaParams p) {
             const int src = ct / k, j = ct - src * k;
             mine = cand[src * KMAX + j];
             const float mv = __uint_as_float(mine.x);
-            int flat = 0;
-            for (int si = 0; si < CL; ++si)
-#pragma unroll 4
-              for (int ji = 0; ji < k; ++ji, ++flat) {
-                const uint2 o = cand[si * KMAX + ji];
+            rk = j;
+            for (int si = 0; si < CL; ++si) {
+              if (si == src) continue;
+              const uint2* lst = cand + si * KMAX;
+              int lo = 0, hi = k;                             // first position whose entry does NOT precede `mine`
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint2 o = lst[mid];
                 const float ov = __uint_as_float(o.x);
-                rk += (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && flat < ct)));
+                const bool before = (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && si < src)));
+                if (before) lo = mid + 1; else hi = mid;
               }
+              rk += lo;
+            }
           }
           uint2* sorted = local_list + SMAX * KMAX;           // [KMAX] behind the per-sequence local lists
           if (ct < n && rk < k) sorted[rk] = mine;            // value descending, index ascending
