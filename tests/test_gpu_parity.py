@@ -333,3 +333,90 @@ def test_classifier_config2_shape_matches_oracle_rows():
     l1, lg1 = clf.classify(ids[3:4].numpy())
     assert l1[0] == labels[3] and np.max(np.abs(lg1[0] - logits[3])) < 0.1
     clf.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# persistent cluster decode kernel (decode_mega.cu) vs the multi-kernel graph path and the oracle
+# ---------------------------------------------------------------------------------------------------
+def _engine_with_env(geo_name, seed, env, **kw):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        geo = mg.GEOMETRIES[geo_name]
+        return mg.Generator(checkpoint(geo_name, seed)["model"], n_head=geo.n_head, dtype="bf16", **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("geo_name,B", [("train_large", 5), ("train_large", 40), ("train_large", 100), ("train_mini", 3)])
+def test_persistent_kernel_logits_match_multikernel_path_and_oracle(geo_name, B):
+    """Same teacher-forced logits from the one-launch cluster kernel (1, 2 and 4 sequences per cluster; head_dim 32
+    and 64) and from the step-graph path; both within the bf16 tolerance of the fp64 reference run."""
+    geo = mg.GEOMETRIES[geo_name]
+    ck = checkpoint(geo_name, 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], B, seed=9)]
+    n = 5
+    forced = np.random.default_rng(1).integers(0, geo.vocab_size, (B, n)).astype(np.int32)
+    mega = _engine_with_env(geo_name, 0, {}, max_batch=128, max_seq=320)
+    multi = _engine_with_env(geo_name, 0, {"MG_NO_MEGA": "1"}, max_batch=128, max_seq=320)
+    l0 = mega.stats()["kernel_launches"]
+    a = mega.step_logits(prompts, forced, n)
+    assert mega.stats()["kernel_launches"] - l0 < 120          # prefill kernels + ONE decode launch
+    l1 = multi.stats()["kernel_launches"]
+    b = multi.step_logits(prompts, forced, n)
+    assert multi.stats()["kernel_launches"] - l1 > 10 * n       # 17 (2 layers) .. 31 (4 layers) kernels per decode step
+    assert np.max(np.abs(a - b)) < 4e-2
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head, torch.float64)
+    for row in (0, B // 2, B - 1):
+        want = gpt_kv.teacher_forced_logits(ora, prompts[row], forced[row].tolist(), n).numpy()
+        assert np.max(np.abs(a[:, row, :] - want)) < 6e-2, row
+    mega.close()
+    multi.close()
+
+
+def test_persistent_kernel_ragged_max_new_eos_and_fallbacks():
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 10, seed=4)]
+    e = engine("train_large", 0, "bf16", max_batch=64, max_seq=1088)
+    max_new = [3, 0, 17, 40, 1, 40, 25, 8, 40, 33]
+    out = e.generate(prompts, max_new, 1.0, 40, seed=2)
+    assert [len(o) - len(p) for o, p in zip(out, prompts)] == max_new
+    full = e.generate(prompts, 40, 1.0, 40, seed=2)
+    assert all(o == f[:len(o)] for o, f in zip(out, full))        # a shorter budget is a prefix of the longer run
+    # top_k above the in-kernel sampler's limit and top_k=None go through the step-graph path
+    for k in (100, None):
+        o = e.generate(prompts, 12, 1.0, k, seed=3)
+        assert all(len(x) == len(p) + 12 for x, p in zip(o, prompts))
+        assert o == e.generate(prompts, 12, 1.0, k, seed=3)
+    # greedy through the persistent kernel == greedy through the step graph for the first tokens of most rows
+    g = e.generate(prompts, 8, 1.0, 1)
+    multi = _engine_with_env("train_large", 0, {"MG_NO_MEGA": "1"}, max_batch=64, max_seq=320)
+    gm = multi.generate(prompts, 8, 1.0, 1)
+    same = sum(a == b for a, b in zip(g, gm))
+    assert same >= 8, same                                        # bf16 rounding may flip a near-tie, not the bulk
+    multi.close()
+
+
+def test_persistent_kernel_sampler_distribution_chi_square():
+    """The in-kernel sampler (local top-k -> owner merge -> Philox) draws from the reference's top-k softmax:
+    one decode step from identical prompts, 4096 rows x 16 seeds, against the oracle's distribution."""
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompt = mg.encode(ck["vocab"], mg.synthetic_prompts(ck["vocab"], 1, seed=0)[0])
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head, torch.float64)
+    e = engine("train_large", 0, "bf16", max_batch=64, max_seq=1088)
+    lg = e.step_logits([prompt], None, 1)[0, 0]                   # the engine's own bf16 logits of that step
+    probs = gpt_kv.topk_probs(torch.from_numpy(lg.astype(np.float64)), 1.0, 40).numpy()
+    want_fp64 = gpt_kv.topk_probs(gpt_kv.teacher_forced_logits(ora, prompt, [], 1)[0], 1.0, 40).numpy()
+    assert np.abs(probs - want_fp64).max() < 2e-2                 # bf16 logits give (nearly) the reference distribution
+    counts = np.zeros(geo.vocab_size, np.int64)
+    for it in range(160):
+        out = e.generate([prompt] * 64, 1, 1.0, 40, seed=1000 + it)
+        counts += np.bincount([o[-1] for o in out], minlength=geo.vocab_size)
+    assert _chi_square_p(counts, probs / probs.sum()) > 1e-3
