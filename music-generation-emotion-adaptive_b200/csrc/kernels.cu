@@ -11,6 +11,8 @@
 
 #include <math.h>
 
+#include <type_traits>
+
 #include "mg_engine.h"
 
 namespace mg {
@@ -605,6 +607,173 @@ encoder_attn_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ seq_s
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Tensor-core variant for bf16 (classifier, bf16 prefill / recompute): one CTA = (sequence, head, 64
+// queries), 4 warps x 16 queries, keys in tiles of 64; S = Q K^T and O += P V are mma.sync m16n8k16
+// (K via ldmatrix, V via ldmatrix.trans), online softmax in the log2 domain on the accumulator
+// fragments, P re-used from registers as the A operand of the second product.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+encoder_attn_tc_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
+                       const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int d, int H, float scale_log2) {
+  constexpr int P = HD + 8;                          // padded pitch: ldmatrix rows land in distinct banks
+  constexpr int CPR = HD / 8;                        // 16-byte chunks per row
+  __shared__ __align__(16) bf16 Qs[64 * P];
+  __shared__ __align__(16) bf16 Ks[64 * P];
+  __shared__ __align__(16) bf16 Vs[64 * P];
+  __shared__ float Kbias[64];
+
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int len = seq_len[b];
+  const int q0 = blockIdx.y * 64;
+  if (q0 >= len) return;
+  const int start = seq_start[b];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t ld = static_cast<size_t>(3) * d;
+  const bf16* base = qkv + static_cast<size_t>(start) * ld + h * HD;
+
+  for (int i = threadIdx.x; i < 64 * CPR; i += 128) {
+    const int r = i / CPR, c = i - r * CPR;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + r < len) v = *reinterpret_cast<const uint4*>(base + (q0 + r) * ld + c * 8);
+    *reinterpret_cast<uint4*>(Qs + r * P + c * 8) = v;
+  }
+  __syncthreads();
+  const int mi = lane >> 3;
+  uint32_t qf[HD / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks)
+    ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Qs + (warp * 16 + (lane & 7) + (mi & 1) * 8) * P + ks * 16 + (mi >> 1) * 8)), qf[ks]);
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int t = 0; t < HD / 8; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[t][e] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};   // rows lane/4 and lane/4 + 8 (per-thread partial sums)
+
+  for (int k0 = 0; k0 < len; k0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * CPR; i += 128) {
+      const int r = i / CPR, c = i - r * CPR;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (k0 + r < len) {
+        const bf16* pk = base + (k0 + r) * ld + c * 8;
+        kv = *reinterpret_cast<const uint4*>(pk + d);
+        vv = *reinterpret_cast<const uint4*>(pk + 2 * d);
+      }
+      *reinterpret_cast<uint4*>(Ks + r * P + c * 8) = kv;
+      *reinterpret_cast<uint4*>(Vs + r * P + c * 8) = vv;
+    }
+    if (threadIdx.x < 64) {
+      const int kr = k0 + threadIdx.x;
+      Kbias[threadIdx.x] = (kr < len && (key_mask == nullptr || key_mask[start + kr] != 0)) ? 0.f : -INFINITY;
+    }
+    __syncthreads();
+
+    float s[8][4];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[t][e] = 0.f;
+#pragma unroll
+    for (int nt2 = 0; nt2 < 4; ++nt2) {
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        uint32_t kf[4];
+        ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Ks + (nt2 * 16 + (lane & 7) + (mi >> 1) * 8) * P + ks * 16 + (mi & 1) * 8)), kf);
+        mma_16816(s[2 * nt2], qf[ks], kf[0], kf[1]);
+        mma_16816(s[2 * nt2 + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float b0 = Kbias[t * 8 + (lane & 3) * 2], b1 = Kbias[t * 8 + (lane & 3) * 2 + 1];
+      s[t][0] = s[t][0] * scale_log2 + b0;
+      s[t][1] = s[t][1] * scale_log2 + b1;
+      s[t][2] = s[t][2] * scale_log2 + b0;
+      s[t][3] = s[t][3] * scale_log2 + b1;
+      mx[0] = fmaxf(mx[0], fmaxf(s[t][0], s[t][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[t][2], s[t][3]));
+    }
+    float corr[2], msafe[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      msafe[r] = (m_new == -INFINITY) ? 0.f : m_new;       // every key so far masked: keep everything at zero
+      corr[r] = exp2f(m_run[r] - msafe[r]);
+      m_run[r] = m_new;
+      l_run[r] *= corr[r];
+    }
+#pragma unroll
+    for (int t = 0; t < HD / 8; ++t) {
+      o[t][0] *= corr[0]; o[t][1] *= corr[0];
+      o[t][2] *= corr[1]; o[t][3] *= corr[1];
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      s[t][0] = exp2f(s[t][0] - msafe[0]); s[t][1] = exp2f(s[t][1] - msafe[0]);
+      s[t][2] = exp2f(s[t][2] - msafe[1]); s[t][3] = exp2f(s[t][3] - msafe[1]);
+      l_run[0] += s[t][0] + s[t][1];
+      l_run[1] += s[t][2] + s[t][3];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack2_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack2_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack2_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack2_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dn2 = 0; dn2 < HD / 16; ++dn2) {
+        uint32_t vf[4];
+        ldsm_x4_trans(static_cast<uint32_t>(__cvta_generic_to_shared(Vs + (kk * 16 + (lane & 7) + (mi & 1) * 8) * P + dn2 * 16 + (mi >> 1) * 8)), vf);
+        mma_16816(o[2 * dn2], pa, vf[0], vf[1]);
+        mma_16816(o[2 * dn2 + 1], pa, vf[2], vf[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qrow = q0 + warp * 16 + (lane >> 2) + r * 8;
+    if (qrow < len) {
+      const float inv = 1.0f / l_run[r];
+      bf16* op = out + static_cast<size_t>(start + qrow) * d + h * HD + (lane & 3) * 2;
+#pragma unroll
+      for (int t = 0; t < HD / 8; ++t)
+        *reinterpret_cast<uint32_t*>(op + t * 8) = pack2_bf16(o[t][2 * r] * inv, o[t][2 * r + 1] * inv);
+    }
+  }
+}
+
 // =================================================================================================
 // Sampler: /temperature -> top-k (radix select) -> softmax over the kept set -> Philox multinomial
 // =================================================================================================
@@ -1040,6 +1209,15 @@ int launch_encoder_attn(cudaStream_t s, const T* qkv, const int32_t* seq_start, 
   const int hd = d / H;
   if (hd > kEncMaxHd) return bad_shape("head_dim > 64");
   const float scale_log2 = kLog2e / sqrtf(static_cast<float>(hd));
+  if (std::is_same<T, bf16>::value && (hd == 32 || hd == 64) && d % 8 == 0) {
+    dim3 grid_tc(B * H, ceil_div(max_len, 64));
+    const bf16* q16 = reinterpret_cast<const bf16*>(qkv);
+    bf16* o16 = reinterpret_cast<bf16*>(out);
+    if (hd == 64) encoder_attn_tc_kernel<64><<<grid_tc, 128, 0, s>>>(q16, seq_start, seq_len, key_mask, o16, d, H, scale_log2);
+    else encoder_attn_tc_kernel<32><<<grid_tc, 128, 0, s>>>(q16, seq_start, seq_len, key_mask, o16, d, H, scale_log2);
+    MG_LAUNCH_CHECK();
+    return MG_OK;
+  }
   dim3 grid(B * H, ceil_div(max_len, kEncQT));
   encoder_attn_kernel<T><<<grid, kEncWarps * 32, 0, s>>>(qkv, seq_start, seq_len, key_mask, out, d, H, scale_log2);
   MG_LAUNCH_CHECK();
