@@ -45,7 +45,8 @@ constexpr int CL = kMegaCluster;       // CTAs per cluster
 constexpr int FS = 64;                 // features per CTA slice
 constexpr int D = 256;                 // d_model
 constexpr int HS = 256;                // hidden units per CTA (d_ff / CL)
-constexpr int NCW = 8;                 // compute warps
+constexpr int NCW = 8;                 // compute warps (all of them stream K/V in the attention phase; 12 measured no faster)
+constexpr int GW = 8;                  // ... of which the first 8 run the GEMMs, epilogues and the sampler
 constexpr int NCT = NCW * 32;          // compute threads
 constexpr int NTHREADS = (1 + NCW) * 32;
 constexpr int XP = 264;                // activation row pitch (bf16 elements): K = 256 + 8 pad, bank-conflict free
@@ -77,8 +78,8 @@ struct Smem {
   static constexpr int kCand = kPart + SMAX * NCW * 68 * 4;          // [CL][KMAX] (value, index) at the owner
   static constexpr int kLocal = kCand + CL * KMAX * 8;               // [SMAX][KMAX] local candidates + [KMAX] sorted list
   static constexpr int kHist = kLocal + (SMAX + 1) * KMAX * 8;       // [SMAX][256] u32 radix histograms
-  static constexpr int kParams = kHist + SMAX * 1024;                // per-layer LN / bias slices + head bias slice (fp32)
-  static constexpr int kMisc = kParams + (kMegaMaxLayersSmem * kLayerParamFloats + kMegaMaxNL) * 4;   // small scalars
+  static constexpr int kParams = kHist + SMAX * 1024;                // per-layer LN / bias slices (fp32)
+  static constexpr int kMisc = kParams + kMegaMaxLayersSmem * kLayerParamFloats * 4;                  // small scalars
   static constexpr int kBars = kMisc + 512;
   static constexpr int kTotal = kBars + 512;
 };
@@ -215,8 +216,10 @@ template <int SMAX, int NSTAGE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHREADS, 1)
 decode_mega_kernel(const MegaParams p) {
   using L = Smem<SMAX, NSTAGE>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment by pointer arithmetic on the shared array itself: a round trip through uintptr_t makes the
+  // compiler lose the shared address space and turn every LDS / STS into a generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars& bars = *reinterpret_cast<Bars*>(smem + L::kBars);
   MiscSmem& misc = *reinterpret_cast<MiscSmem*>(smem + L::kMisc);
   float* xs = reinterpret_cast<float*>(smem + L::kX);
@@ -259,12 +262,9 @@ decode_mega_kernel(const MegaParams p) {
         if (i < 192) pl[P_BQKV + i] = lw.b_in[(i >> 6) * D + r0 * FS + (i & 63)];
       }
     }
-    float* hbs = prm + kMegaMaxLayersSmem * kLayerParamFloats;      // head bias of this CTA's vocabulary slice
-    const int v_lo = r0 * p.VS, v_hi = min(p.V, (r0 + 1) * p.VS);
-    for (int i = threadIdx.x; i < NL; i += NTHREADS) hbs[i] = (v_lo + i < v_hi) ? p.head_b[v_lo + i] : 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars.full[s], 1); ptx::mbar_init(&bars.empty[s], NCW); }
+    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars.full[s], 1); ptx::mbar_init(&bars.empty[s], GW); }
     ptx::mbar_init(&bars.xchg[0], 1);
     ptx::mbar_init(&bars.xchg[1], 1);
     ptx::mbar_init(&bars.cand, 1);
@@ -381,20 +381,22 @@ decode_mega_kernel(const MegaParams p) {
         ptx::mbar_wait(&bars.xchg[buf], (xuse >> 1) & 1);
         bar_compute();                                        // local slot writes visible, everyone past the wait
         if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.xchg[buf], (CL - 1) * D * SMAX * 4);   // re-arm for use + 2
-        const int f = ct;
-        const float bv = bias[f];
-        float acc[SMAX];
+        if (ct < D) {
+          const int f = ct;
+          const float bv = bias[f];
+          float acc[SMAX];
 #pragma unroll
-        for (int s = 0; s < SMAX; ++s) acc[s] = 0.f;
+          for (int s = 0; s < SMAX; ++s) acc[s] = 0.f;
 #pragma unroll
-        for (int src = 0; src < CL; ++src) {
-          const float* sl = slots + ((buf * CL + src) * D + f) * SMAX;
+          for (int src = 0; src < CL; ++src) {
+            const float* sl = slots + ((buf * CL + src) * D + f) * SMAX;
 #pragma unroll
-          for (int s = 0; s < SMAX; ++s) acc[s] += sl[s];
+            for (int s = 0; s < SMAX; ++s) acc[s] += sl[s];
+          }
+#pragma unroll
+          for (int s = 0; s < SMAX; ++s)
+            if (s < S) xs[s * D + f] += acc[s] + bv;
         }
-#pragma unroll
-        for (int s = 0; s < SMAX; ++s)
-          if (s < S) xs[s * D + f] += acc[s] + bv;
         ++xuse;
         bar_compute();
       };
@@ -407,7 +409,7 @@ decode_mega_kernel(const MegaParams p) {
 
       for (int step = 0; step < n_steps; ++step) {
         // ---- embedding: x = tok_emb[tok] + pos_emb[0]   (api_cache.py:99 with T == 1) ----
-        {
+        if (ct < D) {
           const int f = ct;
           const float pe = __bfloat162float(p.pos_emb[f]);
           for (int s = 0; s < S; ++s) xs[s * D + f] = __bfloat162float(p.tok_emb[static_cast<size_t>(misc.tok[s]) * D + f]) + pe;
@@ -419,7 +421,7 @@ decode_mega_kernel(const MegaParams p) {
           const float* pl = reinterpret_cast<const float*>(smem + L::kParams) + l * kLayerParamFloats;
           // ---- LN1 -> QKV: stage rows 0..63 = q slice, 64..127 = k slice, 128..191 = v slice ----
           stage_x(pl + P_LN1W, pl + P_LN1B);
-          {
+          if (cw < GW) {
             float acc[2][4];
             gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, cw < 6, acc);
             if (cw < 6 && fs < S) {
@@ -486,26 +488,37 @@ decode_mega_kernel(const MegaParams p) {
               for (int u = 0; u < U; ++u) {
                 const int row = base + u * 4 + rr;
                 if (row < len) {
-                  kr[u] = ptx::ld_global_stream16(kc + static_cast<size_t>(row) * FS + c * 8);
-                  vr[u] = ptx::ld_global_stream16(vc + static_cast<size_t>(row) * FS + c * 8);
+                  const int arow = p.dbg_attn_hot ? (row & 31) : row;
+                  kr[u] = ptx::ld_global_stream16(kc + static_cast<size_t>(arow) * FS + c * 8);
+                  vr[u] = ptx::ld_global_stream16(vc + static_cast<size_t>(arow) * FS + c * 8);
                 } else {
                   kr[u] = make_uint4(0, 0, 0, 0);
                   vr[u] = make_uint4(0, 0, 0, 0);
                 }
               }
+              // phase-ordered (all dots, then all shuffles) so the U independent chains interleave; no branches
               float sc[U];
-              float m_new = m_run;
 #pragma unroll
               for (int u = 0; u < U; ++u) {
                 float kf[8];
                 unpack8(kr[u], kf);
-                float d = 0.f;
+                const float d0 = fmaf(q[0], kf[0], fmaf(q[2], kf[2], fmaf(q[4], kf[4], q[6] * kf[6])));
+                const float d1 = fmaf(q[1], kf[1], fmaf(q[3], kf[3], fmaf(q[5], kf[5], q[7] * kf[7])));
+                sc[u] = d0 + d1;
+              }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) d = fmaf(q[e], kf[e], d);
-                d += __shfl_xor_sync(0xffffffffu, d, 1);
-                d += __shfl_xor_sync(0xffffffffu, d, 2);
-                if (cph == 8) d += __shfl_xor_sync(0xffffffffu, d, 4);
-                sc[u] = (base + u * 4 + rr < len) ? d : -INFINITY;
+              for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 1);
+#pragma unroll
+              for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 2);
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const float t4 = __shfl_xor_sync(0xffffffffu, sc[u], 4);
+                sc[u] += (cph == 8) ? t4 : 0.f;
+              }
+              float m_new = m_run;
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                sc[u] = (base + u * 4 + rr < len) ? sc[u] : -INFINITY;
                 m_new = fmaxf(m_new, sc[u]);
               }
               if (m_new > -INFINITY) {
@@ -574,7 +587,7 @@ decode_mega_kernel(const MegaParams p) {
           bar_compute();
           stamp(step);                                                      // +2: attention done
           // ---- out_proj (row-parallel over this CTA's 64 attention features) -> exchange -> x += attn ----
-          {
+          if (cw < GW) {
             float acc[2][4];
             gemm_pair<1, NSTAGE>(ring, bars.full, bars.empty, rp, attb, AP, cw, lane, true, acc);
             exchange_send(acc);
@@ -583,7 +596,7 @@ decode_mega_kernel(const MegaParams p) {
           stamp(step);                                                      // +3: out_proj + exchange done
           // ---- LN2 -> MLP1 (+GELU, this CTA's 256 hidden units) -> MLP2 (row-parallel) -> exchange ----
           stage_x(pl + P_LN2W, pl + P_LN2B);
-          {
+          if (cw < GW) {
             float acc[2][4];
             gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc);
             if (fs < S) {
@@ -601,7 +614,7 @@ decode_mega_kernel(const MegaParams p) {
           }
           bar_compute();
           stamp(step);                                                      // +4: MLP1 done
-          {
+          if (cw < GW) {
             float acc[2][4];
             gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, hb, XP, cw, lane, true, acc);
             exchange_send(acc);
@@ -613,9 +626,15 @@ decode_mega_kernel(const MegaParams p) {
         stage_x(nullptr, nullptr);
         {
           const int v_lo = r * p.VS, v_hi = min(p.V, (r + 1) * p.VS);
-          const float* hbs = reinterpret_cast<const float*>(smem + L::kParams) + kMegaMaxLayersSmem * kLayerParamFloats;
-          const float inv_t_dummy = 0.f; (void)inv_t_dummy;
-          for (int pr = 0; pr < p.NP; ++pr) {
+          for (int pr = 0; pr < p.NP && cw < GW; ++pr) {
+            float hbv[2][2];                                   // head bias of this thread's 4 rows, loaded ahead of the MMAs
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                const int vr = v_lo + pr * 256 + cw * 32 + t * 16 + frow + h8 * 8;
+                hbv[t][h8] = vr < v_hi ? __ldg(p.head_b + vr) : 0.f;
+              }
             float acc[2][4];
             gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc);
             if (fs < S) {
@@ -626,12 +645,11 @@ decode_mega_kernel(const MegaParams p) {
                   const int lr = pr * 256 + cw * 32 + t * 16 + frow + h8 * 8;   // row inside the slice
                   const int vr = v_lo + lr;
                   const bool ok = vr < v_hi;
-                  const float hbias = hbs[lr];
 #pragma unroll
                   for (int e = 0; e < 2; ++e) {
                     const int s = fs + e;
                     if (s < S) {
-                      const float lg = acc[t][h8 * 2 + e] + hbias;
+                      const float lg = acc[t][h8 * 2 + e] + hbv[t][h8];
                       logits[s * NL + lr] = ok ? lg / sp.temperature : -INFINITY;
                       if (p.dbg_logits && ok) p.dbg_logits[(static_cast<size_t>(step) * p.B + b0 + s) * p.V + vr] = lg;
                     }
@@ -647,8 +665,8 @@ decode_mega_kernel(const MegaParams p) {
         // The compute warps are dealt to the sequences (warp cw -> sequence cw % S); each group radix-selects
         // the k largest logits of this CTA's vocabulary slice with warp-aggregated histogram updates.
         const int k = sp.top_k;
-        {
-          const int s = cw % S, wi = cw / S, nws = (NCW - s + S - 1) / S;
+        if (cw < GW) {
+          const int s = cw % S, wi = cw / S, nws = (GW - s + S - 1) / S;
           const int gt = wi * 32 + lane, gn = nws * 32;       // thread index / count inside the group
           const uint32_t gbar = 3 + s;                        // named barrier of the group
           float* z = logits + s * NL;

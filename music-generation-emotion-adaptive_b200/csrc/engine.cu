@@ -403,6 +403,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int* rc, float* dbg_logits, const 
   p.dbg_logits = dbg_logits; p.forced = forced; p.forced_stride = forced_stride;
   p.prof = nullptr; p.prof_step = -1;
   p.dbg_skip_loads = std::getenv("MG_MEGA_SKIP_LOADS") ? 1 : 0;
+  p.dbg_attn_hot = std::getenv("MG_MEGA_ATTN_HOT") ? 1 : 0;
   if (const char* ps = std::getenv("MG_MEGA_PROF_STEP")) {       // debug: phase timeline of one decode step -> stderr
     if (!e->d_prof) { if (e->dmalloc(&e->d_prof, 128 * sizeof(unsigned long long)) != MG_OK) e->d_prof = nullptr; }
     if (e->d_prof) {
@@ -419,7 +420,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int* rc, float* dbg_logits, const 
     for (int i = 0; i < 64 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
     fprintf(stderr, "\n[mega prof] MMA thread, layer 0 (wait-B, B-ready, committed per GEMM):");
     for (int i = 64; i < 128 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[0]));
-    fprintf(stderr, "\n");
+    fprintf(stderr, "\n[mega prof] attention layer 0 warp 0: load-wait cycles %llu, compute cycles %llu, batches %llu\n", h[100], h[101], h[102]);
   }
   e->t_steps = e->cur_steps;
   return true;

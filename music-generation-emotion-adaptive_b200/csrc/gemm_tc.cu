@@ -18,6 +18,8 @@
 #include "mg_engine.h"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace mg {
 
 namespace {
@@ -188,6 +190,198 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Persistent variant for large M (classifier, long prefill): one CTA per SM loops over 128 x BN output
+// tiles; TWO TMEM accumulator buffers so the epilogue of tile i (8 warps: TMEM -> registers -> fused
+// bias / GELU / residual -> global) overlaps the TMA + tcgen05.mma main loop of tile i + 1.
+//   warp 0: TMA producer | warp 1: TMEM allocator + MMA issuer | warps 2..9: epilogue (two per TMEM
+//   lane quarter, each half of the tile's columns)
+// Tile order: consecutive CTAs take consecutive M tiles of the same N tile, so a weight tile is read
+// from HBM once and then served by L2.
+// -------------------------------------------------------------------------------------------------
+constexpr int kPThreads = 320;
+
+template <int BN> struct PTileCfg {
+  static constexpr int kABytes = kGemmBM * kGemmBK * 2;
+  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;                          // two accumulator buffers
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                               int M, int N, int K, GemmEpilogue epi) {
+  using Cfg = PTileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;                  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + kGemmBM - 1) / kGemmBM, n_tiles = (N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 8); }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t % m_tiles) * kGemmBM, n0 = (t / m_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          ptx::tma_load_2d(a_dst, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          ptx::tma_load_2d(a_dst + Cfg::kABytes, &tmap_w, &full_bar[stage], kb * kGemmBK, n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kGemmBM, BN);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        ptx::mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator buffer
+        ptx::tc_fence_after_sync();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr);
+          const uint64_t db = ptx::make_kmajor_sw128_desc(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k)
+            ptx::umma_bf16_ss(tmem_base + buf * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;                                   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                               // which half of the tile's columns
+    const size_t ld = static_cast<size_t>(epi.ld_out);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int m0 = (t % m_tiles) * kGemmBM, n0 = (t / m_tiles) * BN;
+      const uint32_t buf = it & 1;
+      ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c * 32, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const size_t off = static_cast<size_t>(row) * ld + col0;
+        if (col0 + 32 <= N && (ld % 8 == 0) && (col0 % 8 == 0)) {
+          if (epi.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (epi.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], epi.act);
+          }
+          if (epi.resid_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 x4 = *reinterpret_cast<const float4*>(epi.resid_f32 + off + j);
+              v[j] += x4.x; v[j + 1] += x4.y; v[j + 2] += x4.z; v[j + 3] += x4.w;
+            }
+          }
+          if (epi.resid_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
+              Chunk16<bf16>::unpack(*reinterpret_cast<const uint4*>(epi.resid_bf16 + off + j), f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[j + q] += f[q];
+            }
+          }
+          if (epi.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(epi.out_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (epi.out_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(epi.out_bf16 + off + j) = Chunk16<bf16>::pack(v + j);
+          }
+        } else {
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col >= N) break;
+            float x = v[j] + (epi.bias ? __ldg(epi.bias + col) : 0.0f);
+            x = apply_act(x, epi.act);
+            if (epi.resid_f32) x += epi.resid_f32[off + j];
+            if (epi.resid_bf16) x += __bfloat162float(epi.resid_bf16[off + j]);
+            if (epi.out_f32) epi.out_f32[off + j] = x;
+            if (epi.out_bf16) epi.out_bf16[off + j] = __float2bfloat16_rn(x);
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int BN>
+int launch_persistent_bn(cudaStream_t stream, const CUtensorMap* ta, const CUtensorMap* tw, int M, int N, int K,
+                         const GemmEpilogue& epi) {
+  const int total = ceil_div(M, kGemmBM) * ceil_div(N, BN);
+  gemm_bf16_tc_persistent_kernel<BN><<<std::min(total, 148), kPThreads, PTileCfg<BN>::kSmemBytes, stream>>>(*ta, *tw, M, N, K, epi);
+  MG_LAUNCH_CHECK();
+  return MG_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -255,10 +449,17 @@ int gemm_tc_init() {
   MG_TRY(init_bn<64>());
   MG_TRY(init_bn<128>());
   MG_TRY(init_bn<256>());
+  MG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_persistent_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  PTileCfg<128>::kSmemBytes));
+  MG_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_persistent_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  PTileCfg<256>::kSmemBytes));
   return MG_OK;
 }
 
+bool gemm_use_persistent(int M, int N) { return ceil_div(M, 128) * ceil_div(N, 128) >= 2 * 148; }
+
 int pick_gemm_bn(int M, int N) {
+  if (gemm_use_persistent(M, N)) return (N % 256 == 0 || N >= 1024) ? 256 : 128;
   // Few row tiles (batched decode): small BN spreads the weight stream over many SMs.
   const int m_tiles = ceil_div(M, kGemmBM);
   if (m_tiles * ceil_div(N, 128) >= 148) return 128;
@@ -272,6 +473,9 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap* ta, const CUtensorMap
     set_last_error("launch_gemm_tc: bad shape");
     return MG_E_SHAPE;
   }
+  if (gemm_use_persistent(M, N) && (bn == 128 || bn == 256))
+    return bn == 256 ? launch_persistent_bn<256>(stream, ta, tw, M, N, K, epi)
+                     : launch_persistent_bn<128>(stream, ta, tw, M, N, K, epi);
   switch (bn) {
     case 32: return launch_bn<32>(stream, ta, tw, M, N, K, epi);
     case 64: return launch_bn<64>(stream, ta, tw, M, N, K, epi);
