@@ -102,6 +102,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes (read + write) per launch of the persistent decode kernel from the committed `ncu --set full`
+    capture of this same workload (profiles/r1b_decode_mega_full_raw.csv); None when the file is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1b_decode_mega_full_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(rows[2][i].replace(",", "")) * scale[units[i]]
+        return tot
+    except Exception:
+        return None
+
+
 def host_threads():
     """Host cores this process may actually use (cgroup / affinity aware), capped at 32 for the small GEMMs."""
     try:
@@ -271,7 +289,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": ncu_traffic_bytes(), "traffic_note": "DRAM read+write bytes per launch (= per job), ncu --set full, profiles/r1b_decode_mega_full_raw.csv",
+                     "peak_source": peak_src,
                      "kernel": ("decode_mega_kernel: ONE persistent cluster launch per job runs all 1024 decode steps "
                                 "(embedding, 4 blocks, head, top-k sampler); achieved = algorithmic bytes of the decode "
                                 "steps / that launch's duration (CUDA events on the engine stream)"),
@@ -283,6 +302,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras:
         line["batch1"] = batch1_latency(mg)
         line["classifier"] = classifier_throughput(mg, tf_peak, peak_src)
+        line["long_context"] = long_context(mg, hbm_peak)
+        line["pipeline"] = pipeline_512(mg)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         n_new = 1024
@@ -331,6 +352,52 @@ def batch1_latency(mg):
                       "note": "median over runs of (decode-loop device time / tokens); greedy (top_k=1)"}
         eng.close()
     return out
+
+
+def long_context(mg, hbm_peak):
+    """BASELINE config 4: 256-token prompt prefill + 4096 new tokens, batch 16 (train_large blocks, 512-row position table)."""
+    geo = mg.GEOMETRIES["train_large_pos512"]
+    ck = mg.make_checkpoint(geo, 0)
+    rng = np.random.default_rng(0)
+    prompts = [rng.integers(0, geo.vocab_size, 256).tolist() for _ in range(16)]
+    eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=16, max_seq=4352)
+    best = None
+    for i in range(2):
+        eng.upload(prompts, 4096)
+        eng.run(1.0, 40, eos_id=-1, seed=i)
+        eng.synchronize()
+        t = eng.last_timing()
+        best = t if best is None or t["total_ms"] < best["total_ms"] else best
+    alg, _, _ = algorithmic_bytes(geo, [256] * 16, 4096)
+    eng.close()
+    return {"workload": "config4: 256-token prompt + 4096 new tokens, batch 16, bf16", "tokens_per_s": 16 * 4096 / (best["total_ms"] * 1e-3),
+            "prefill_ms": best["prefill_ms"], "decode_us_per_step": 1e3 * best["decode_ms"] / 4096,
+            "hbm_gbs": alg / (best["decode_ms"] * 1e-3) / 1e9, "frac_of_measured_hbm": alg / (best["decode_ms"] * 1e-3) / 1e9 / hbm_peak,
+            "note": "16 sequences -> 16 clusters x 4 CTAs = 64 of 148 SMs busy (one sequence per cluster)"}
+
+
+def pipeline_512(mg):
+    """BASELINE config 5 on ONE replica: 512 requests, classify -> prompt -> generate (1024 tokens total each, top-k 40)."""
+    geo = mg.GEOMETRIES["train_large_pos512"]
+    ck = mg.make_checkpoint(geo, 0)
+    vocab = {t: i for t, i in ck["vocab"].items() if t != "[END_SEQUENCE]"}       # EOS disabled: every request runs to max_len
+    vocab["[EOS_DISABLED]"] = ck["vocab"]["[END_SEQUENCE]"]
+    gen = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=128, max_seq=1088)
+    clf = mg.Classifier(mg.make_bert_state_dict(mg.DISTILBERT_BASE, 0), n_heads=12, max_tokens=16384)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(1000, 30000, (512, 64), generator=g)
+    ids[:, 0], ids[:, 63] = 101, 102
+    mg.classify_prompt_generate(clf, gen, vocab, ids.numpy()[:128], max_len=64, top_k=40)      # warm-up
+    t0 = time.perf_counter()
+    out = mg.classify_prompt_generate(clf, gen, vocab, ids.numpy(), max_len=1024, temperature=1.0, top_k=40, batch=128)
+    dt = time.perf_counter() - t0
+    assert len(out) == 512 and all(len(o) == 1024 for o in out)
+    n_new = sum(len(o) for o in out) - sum(3 for _ in out)
+    gen.close()
+    clf.close()
+    return {"workload": "config5 on one replica: 512 requests classify -> prompt -> generate to 1024 tokens, top-k 40, batches of 128",
+            "wall_s": dt, "requests_per_s": 512 / dt, "tokens_per_s": n_new / dt,
+            "note": "host wall clock incl. tokenised-text H2D, synthetic emotion -> music mapping, prompt building, D2H of tokens"}
 
 
 def classifier_throughput(mg, tf_peak, peak_src):

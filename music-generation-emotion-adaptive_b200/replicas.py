@@ -52,19 +52,20 @@ def gather_token_lists(local: Sequence[Sequence[int]], n_total: int, group=None,
     t = torch.tensor([my_max], dtype=torch.int32, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     max_len = int(t.item())
-    buf = torch.full((max_local, 1 + max_len), -1, dtype=torch.int32)
+    import numpy as np
+    nbuf = np.full((max_local, 1 + max_len), -1, dtype=np.int32)
     for i, x in enumerate(local):
-        buf[i, 0] = len(x)
+        nbuf[i, 0] = len(x)
         if len(x):
-            buf[i, 1:1 + len(x)] = torch.tensor(list(x), dtype=torch.int32)
+            nbuf[i, 1:1 + len(x)] = np.asarray(x, dtype=np.int32)
+    buf = torch.from_numpy(nbuf)
     buf = buf.to(dev)
     outs = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf, group=group)
     result: List[List[int]] = []
     for r, o in enumerate(outs):
-        o = o.cpu()
+        o = o.cpu().numpy()
         rlo, rhi = shard_range(n_total, r, world)
         for i in range(rhi - rlo):
-            n = int(o[i, 0])
-            result.append(o[i, 1:1 + n].tolist())
+            result.append(o[i, 1:1 + int(o[i, 0])].tolist())
     return result

@@ -105,3 +105,12 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("test oracle", ""), f
+
+
+def test_pipeline_prompt_building_uses_the_service_order():
+    v = mg.build_synthetic_vocab(8324)
+    prm = mg.synthetic_music_params("joy")
+    assert set(prm) == {"emotion", "bpm", "key", "scale_type", "inst_family", "all_families"}     # EATS.py:29-37
+    p = mg.build_prompt(v, prm["bpm"], prm["key"], prm["all_families"])
+    assert p[0] == "[START_SEQUENCE]" and p[1].startswith("[BPM]") and p[2].startswith("[KEY_SIGNATURE]")
+    assert all(t in v for t in p) and 3 <= len(p) <= 6
