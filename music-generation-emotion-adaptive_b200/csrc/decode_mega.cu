@@ -95,6 +95,7 @@ struct MiscSmem {
   int nnew[8];
   int fin[8];
   int maxnew[8];
+  int go;
   int sel[4][4];                      // per sequence: remaining, gathered count, radix prefix, exact flag
 };
 
@@ -104,6 +105,7 @@ struct Bars {
   uint64_t xchg[2];
   uint64_t cand;
   uint64_t tok;
+  uint64_t step_go;                   // compute warps -> producer: the next step will run (early-exit mode)
 };
 
 __device__ __forceinline__ uint32_t float_key(float f) {
@@ -269,6 +271,7 @@ decode_mega_kernel(const MegaParams p) {
     ptx::mbar_init(&bars.xchg[1], 1);
     ptx::mbar_init(&bars.cand, 1);
     ptx::mbar_init(&bars.tok, 1);
+    ptx::mbar_init(&bars.step_go, 1);
     ptx::fence_mbar_init();
     for (int s = 0; s < 8; ++s) {
       const bool live = s < S;
@@ -293,6 +296,10 @@ decode_mega_kernel(const MegaParams p) {
         const int stages_per_step = n_layer * kMegaStagesPerLayer + 4 * p.NP;
         const uint8_t* src0 = p.packed + static_cast<size_t>(rank) * stages_per_step * STAGE_BYTES;
         for (int step = 0; step < n_steps; ++step) {
+          if (p.early_exit && step > 0) {                     // do not stream weights for a step that will not run
+            ptx::mbar_wait(&bars.step_go, (step - 1) & 1);
+            if (*reinterpret_cast<volatile int*>(&misc.go) == 0) break;
+          }
           const uint8_t* src = src0;
           for (int i = 0; i < stages_per_step; ++i, src += STAGE_BYTES) {
             ptx::mbar_wait(&bars.empty[rp.stage], rp.phase ^ 1);
@@ -929,6 +936,16 @@ decode_mega_kernel(const MegaParams p) {
           }
           bar_compute();
           stamp(step);                                                      // token published, state advanced
+        }
+        if (p.early_exit) {
+          bool all_fin = true;
+          for (int s = 0; s < S; ++s) all_fin = all_fin && misc.fin[s] != 0;
+          if (ct == 0 && step + 1 < n_steps) {
+            *reinterpret_cast<volatile int*>(&misc.go) = all_fin ? 0 : 1;
+            __threadfence_block();
+            ptx::mbar_arrive(&bars.step_go);
+          }
+          if (all_fin) break;                                 // identical decision in all four CTAs (replicated state)
         }
       }
       // write the decode state back (the host-side step graph / download read it)

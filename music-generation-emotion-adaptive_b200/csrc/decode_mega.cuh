@@ -37,6 +37,7 @@ struct MegaParams {
   DecodeState st;
   int n_layer, head_dim, V, VS, NP;   // VS = ceil(V / 4) vocabulary rows per CTA, NP = ceil(VS / 256) tile pairs
   int B, S, Tmax, n_steps;            // S = sequences per cluster
+  int early_exit;                     // EOS enabled: a cluster stops as soon as all of its sequences have finished
   // parity/debug (mg_step_logits): raw logits [n_steps][B][V] and teacher-forced next tokens [B][forced_stride]
   float* dbg_logits;
   const int32_t* forced;

@@ -129,8 +129,8 @@ struct mg_engine {
 
 namespace {
 
-bool run_decode_mega(mg_engine* e, int top_k, int* rc, float* dbg_logits = nullptr, const int32_t* forced = nullptr,
-                     int forced_stride = 0);
+bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits = nullptr,
+                     const int32_t* forced = nullptr, int forced_stride = 0);
 int setup_mega(mg_engine* e);
 
 int decode_nsplit(const mg_engine* e, int B) {
@@ -307,7 +307,7 @@ int run_impl(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t se
   MG_TRY(prefill<T>(e));
   MG_CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
   int mrc = MG_OK;
-  e->last_run_mega = std::is_same<T, bf16>::value && run_decode_mega(e, top_k, &mrc);
+  e->last_run_mega = std::is_same<T, bf16>::value && run_decode_mega(e, top_k, eos_id, &mrc);
   MG_TRY(mrc);
   if (!e->last_run_mega) MG_TRY(run_decode_loop<T>(e, eos_id));
   MG_CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
@@ -381,7 +381,7 @@ int setup_mega(mg_engine* e) {
 }
 
 // Returns true (and launches) when the persistent kernel can serve this call.
-bool run_decode_mega(mg_engine* e, int top_k, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride) {
+bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride) {
   *rc = MG_OK;
   if (!e->mega_ok || top_k < 1 || top_k > mega::kMegaMaxTopK || e->cur_steps <= 0) return false;
   const int B = e->cur_B;
@@ -401,6 +401,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int* rc, float* dbg_logits, const 
   p.VS = ceil_div(g.vocab_size, mega::kMegaCluster); p.NP = ceil_div(p.VS, 256);
   p.B = B; p.S = S; p.Tmax = e->max_seq; p.n_steps = e->cur_steps;
   p.dbg_logits = dbg_logits; p.forced = forced; p.forced_stride = forced_stride;
+  p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
   p.prof = nullptr; p.prof_step = -1;
   p.dbg_skip_loads = std::getenv("MG_MEGA_SKIP_LOADS") ? 1 : 0;
   p.dbg_attn_hot = std::getenv("MG_MEGA_ATTN_HOT") ? 1 : 0;
@@ -892,7 +893,7 @@ int mg_step_logits(mg_engine* e, const int32_t* ids, const int32_t* offs, int B,
     *e->h_sp = SampleParams{1.0f, 1, -1, 0, 0, 0};
     int rc = cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream) == cudaSuccess ? MG_OK : MG_E_CUDA;
     int mrc = MG_OK;
-    if (rc == MG_OK && run_decode_mega(e, 1, &mrc, d_lg, n_steps > 1 ? e->d_forced : nullptr, n_steps)) {
+    if (rc == MG_OK && run_decode_mega(e, 1, -1, &mrc, d_lg, n_steps > 1 ? e->d_forced : nullptr, n_steps)) {
       rc = mrc;
       if (rc == MG_OK && cudaMemcpyAsync(logits_out, d_lg, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = MG_E_CUDA;
       if (rc == MG_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(MG_E_CUDA, std::string("persistent decode kernel: ") + cudaGetErrorString(cudaGetLastError()));
