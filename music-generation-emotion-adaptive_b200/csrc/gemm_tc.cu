@@ -171,15 +171,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             *reinterpret_cast<uint4*>(epi.out_bf16 + off + j) = Chunk16<bf16>::pack(v + j);
         }
       } else {
+        // ragged / unaligned tail: fully unrolled with predicates so that v[] keeps static indices (a dynamic index
+        // would push the whole accumulator array of BOTH paths into local memory)
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
-          if (col >= N) break;
-          float x = v[j] + (epi.bias ? __ldg(epi.bias + col) : 0.0f);
-          x = apply_act(x, epi.act);
-          if (epi.resid_f32) x += epi.resid_f32[off + j];
-          if (epi.resid_bf16) x += __bfloat162float(epi.resid_bf16[off + j]);
-          if (epi.out_f32) epi.out_f32[off + j] = x;
-          if (epi.out_bf16) epi.out_bf16[off + j] = __float2bfloat16_rn(x);
+          if (col < N) {
+            float x = v[j] + (epi.bias ? __ldg(epi.bias + col) : 0.0f);
+            x = apply_act(x, epi.act);
+            if (epi.resid_f32) x += epi.resid_f32[off + j];
+            if (epi.resid_bf16) x += __bfloat162float(epi.resid_bf16[off + j]);
+            if (epi.out_f32) epi.out_f32[off + j] = x;
+            if (epi.out_bf16) epi.out_bf16[off + j] = __float2bfloat16_rn(x);
+          }
         }
       }
     }
@@ -350,15 +354,17 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
               *reinterpret_cast<uint4*>(epi.out_bf16 + off + j) = Chunk16<bf16>::pack(v + j);
           }
         } else {
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
-            if (col >= N) break;
-            float x = v[j] + (epi.bias ? __ldg(epi.bias + col) : 0.0f);
-            x = apply_act(x, epi.act);
-            if (epi.resid_f32) x += epi.resid_f32[off + j];
-            if (epi.resid_bf16) x += __bfloat162float(epi.resid_bf16[off + j]);
-            if (epi.out_f32) epi.out_f32[off + j] = x;
-            if (epi.out_bf16) epi.out_bf16[off + j] = __float2bfloat16_rn(x);
+            if (col < N) {
+              float x = v[j] + (epi.bias ? __ldg(epi.bias + col) : 0.0f);
+              x = apply_act(x, epi.act);
+              if (epi.resid_f32) x += epi.resid_f32[off + j];
+              if (epi.resid_bf16) x += __bfloat162float(epi.resid_bf16[off + j]);
+              if (epi.out_f32) epi.out_f32[off + j] = x;
+              if (epi.out_bf16) epi.out_bf16[off + j] = __float2bfloat16_rn(x);
+            }
           }
         }
       }

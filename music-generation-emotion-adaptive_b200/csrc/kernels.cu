@@ -135,6 +135,47 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ w, const fl
                          x_out ? x_out + static_cast<size_t>(row) * d : nullptr);
 }
 
+
+// bf16 -> bf16 LayerNorm with 16-byte accesses: lane owns chunks lane, lane + 32, ... of 8 elements (d = 256 * NCH).
+template <int NCH>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_bf16_vec_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                          bf16* __restrict__ y, int M, float eps) {
+  constexpr int d = 256 * NCH;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
+  float v[NCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    Chunk16<bf16>::unpack(xr[lane + 32 * j], v[j]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[j][e];
+  }
+  const float mean = warp_sum(s) * (1.0f / d);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float c = v[j][e] - mean; q += c * c; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / d) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c0)), w1 = __ldg(reinterpret_cast<const float4*>(w + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(b + c0 + 4));
+    float o[8];
+    o[0] = (v[j][0] - mean) * rstd * w0.x + b0.x; o[1] = (v[j][1] - mean) * rstd * w0.y + b0.y;
+    o[2] = (v[j][2] - mean) * rstd * w0.z + b0.z; o[3] = (v[j][3] - mean) * rstd * w0.w + b0.w;
+    o[4] = (v[j][4] - mean) * rstd * w1.x + b1.x; o[5] = (v[j][5] - mean) * rstd * w1.y + b1.y;
+    o[6] = (v[j][6] - mean) * rstd * w1.z + b1.z; o[7] = (v[j][7] - mean) * rstd * w1.w + b1.w;
+    yr[lane + 32 * j] = Chunk16<bf16>::pack(o);
+  }
+}
+
 // =================================================================================================
 // SIMT GEMM (64x64x16 tiles, 4x4 per thread, fp32 FMA in k order) and small-M GEMV
 // =================================================================================================
@@ -1129,6 +1170,19 @@ int launch_layernorm(cudaStream_t s, const TI* x, const float* w, const float* b
                      float eps) {
   if (M <= 0) return MG_OK;
   if (d > 32 * kLnMaxPerLane) return bad_shape("d_model > 1024");
+  if (std::is_same<TI, bf16>::value && std::is_same<TO, bf16>::value && x_out == nullptr && d % 256 == 0) {
+    const bf16* xi = reinterpret_cast<const bf16*>(x);
+    bf16* yo = reinterpret_cast<bf16*>(y);
+    const int blocks = ceil_div(M, kLnWarps);
+    switch (d / 256) {
+      case 1: layernorm_bf16_vec_kernel<1><<<blocks, kLnWarps * 32, 0, s>>>(xi, w, b, yo, M, eps); break;
+      case 2: layernorm_bf16_vec_kernel<2><<<blocks, kLnWarps * 32, 0, s>>>(xi, w, b, yo, M, eps); break;
+      case 3: layernorm_bf16_vec_kernel<3><<<blocks, kLnWarps * 32, 0, s>>>(xi, w, b, yo, M, eps); break;
+      default: layernorm_bf16_vec_kernel<4><<<blocks, kLnWarps * 32, 0, s>>>(xi, w, b, yo, M, eps); break;
+    }
+    MG_LAUNCH_CHECK();
+    return MG_OK;
+  }
   layernorm_kernel<TI, TO><<<ceil_div(M, kLnWarps), kLnWarps * 32, 0, s>>>(x, w, b, y, x_out, M, d, eps);
   MG_LAUNCH_CHECK();
   return MG_OK;
