@@ -36,6 +36,13 @@
 #include "mg_engine.h"
 #include "ptx.cuh"
 
+// -DMG_MEGA_TRACE: clock64 trace of one layer of the profiled step (costs registers; off in the product build)
+#ifdef MG_MEGA_TRACE
+#define MG_TR(tr) do { if (tr) *tr++ = clock64(); } while (0)
+#else
+#define MG_TR(tr) do { } while (0)
+#endif
+
 namespace mg {
 namespace mega {
 
@@ -48,7 +55,8 @@ constexpr int HS = 256;                // hidden units per CTA (d_ff / CL)
 constexpr int NCW = 8;                 // compute warps (all of them stream K/V in the attention phase; 12 measured no faster)
 constexpr int GW = 8;                  // ... of which the first 8 run the GEMMs, epilogues and the sampler
 constexpr int NCT = NCW * 32;          // compute threads
-constexpr int NTHREADS = (1 + NCW) * 32;
+constexpr int NPW = 4;                 // producer warpgroup: warp 0 lane 0 streams the weights, warps 1..3 idle (setmaxnreg is per warpgroup)
+constexpr int NTHREADS = (NPW + NCW) * 32;
 constexpr int XP = 264;                // activation row pitch (bf16 elements): K = 256 + 8 pad, bank-conflict free
 constexpr int AP = 72;                 // attention-output row pitch: K = 64 + 8 pad
 constexpr int STAGE_BYTES = kMegaStageBytes;   // one stage: two weight tiles [128 rows x 64 K] bf16 (rows 0..255)
@@ -97,6 +105,7 @@ struct MiscSmem {
   int maxnew[8];
   int go;
   int sel[4][4];                      // per sequence: remaining, gathered count, radix prefix, exact flag
+  bf16* kvp[kMegaMaxLayersSmem][2];   // K / V cache base of every layer (the MegaLayer table lives in global memory)
 };
 
 struct Bars {
@@ -168,7 +177,8 @@ struct RingPos {
 //   acc   : [2][4] fp32, thread holds rows (lane/4, lane/4 + 8) x sequences ((lane%4)*2, +1) of each tile
 template <int NKB, int NSTAGE>
 __device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_t* empty, RingPos& rp, const bf16* act,
-                                          int pitch, int cw, int lane, bool active, float (&acc)[2][4]) {
+                                          int pitch, int cw, int lane, bool active, float (&acc)[2][4],
+                                          unsigned long long*& tr) {
   uint32_t breg[NKB * 4][2];
   {
     const bf16* bp = act + (lane >> 2) * pitch + (lane & 3) * 2;
@@ -189,6 +199,7 @@ __device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_
 #pragma unroll
   for (int kb = 0; kb < NKB; ++kb) {
     ptx::mbar_wait(&full[rp.stage], rp.phase);
+    MG_TR(tr);
     if (active) {
       const uint32_t sbase = ptx::smem_u32(ring + rp.stage * STAGE_BYTES);
 #pragma unroll
@@ -212,6 +223,7 @@ __device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_
   for (int t = 0; t < 2; ++t)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[t][e] += acc2[t][e];
+  MG_TR(tr);
 }
 
 template <int SMAX, int NSTAGE>
@@ -267,11 +279,11 @@ decode_mega_kernel(const MegaParams p) {
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars.full[s], 1); ptx::mbar_init(&bars.empty[s], GW); }
+    ptx::mbar_init(&bars.step_go, 1);
     ptx::mbar_init(&bars.xchg[0], 1);
     ptx::mbar_init(&bars.xchg[1], 1);
     ptx::mbar_init(&bars.cand, 1);
     ptx::mbar_init(&bars.tok, 1);
-    ptx::mbar_init(&bars.step_go, 1);
     ptx::fence_mbar_init();
     for (int s = 0; s < 8; ++s) {
       const bool live = s < S;
@@ -281,6 +293,7 @@ decode_mega_kernel(const MegaParams p) {
       misc.maxnew[s] = live ? p.st.max_new[b0 + s] : 0;
       misc.fin[s] = live ? static_cast<int>(p.st.finished[b0 + s]) : 1;
     }
+    for (int l = 0; l < n_layer; ++l) { misc.kvp[l][0] = p.layers[l].kc; misc.kvp[l][1] = p.layers[l].vc; }
   }
   __syncthreads();
   // every CTA of the cluster must have initialised its barriers before any remote st.async lands
@@ -289,9 +302,10 @@ decode_mega_kernel(const MegaParams p) {
   const int n_steps = p.n_steps;
 
   if (S > 0) {
-    if (warp == 0) {
-      // =========================== bulk-copy producer ===========================
-      if (lane == 0) {
+    if (warp < NPW) {
+      // =========================== bulk-copy producer warpgroup ===========================
+      ptx::setmaxnreg_dec<40>();
+      if (warp == 0 && lane == 0) {
         RingPos rp;
         const int stages_per_step = n_layer * kMegaStagesPerLayer + 4 * p.NP;
         const uint8_t* src0 = p.packed + static_cast<size_t>(rank) * stages_per_step * STAGE_BYTES;
@@ -315,14 +329,21 @@ decode_mega_kernel(const MegaParams p) {
       }
       __syncwarp();
     } else {
-      // =========================== compute warps ===========================
-      const int cw = warp - 1;                               // 0..7
-      const int ct = threadIdx.x - 32;                       // 0..255
+      // =========================== compute warps (two warpgroups) ===========================
+      ptx::setmaxnreg_inc<232>();
+      const int cw = warp - NPW;                             // 0..7
+      const int ct = threadIdx.x - NPW * 32;                 // 0..255
       uint32_t xuse = 0;
       RingPos rp;
       const SampleParams sp = *p.sp;
       const float scale_log2 = kLog2e / sqrtf(static_cast<float>(hd));
       const int cph = hd / 8;                                // 16-byte chunks per head (4 or 8)
+      const int hd_shift = hd == 64 ? 6 : 5;
+      // work assignment without run-time integer divisions (S <= 4): warp cw serves sequence cw % S as its (cw / S)-th
+      // worker; a sequence has NCW / S workers (3, 3, 2 when S == 3)
+      auto seq_of = [&](int w) { return S == 3 ? w % 3 : (w & (S - 1)); };
+      auto worker_of = [&](int w) { return S == 3 ? w / 3 : (S == 1 ? w : (S == 2 ? w >> 1 : w >> 2)); };
+      auto workers = [&](int sq) { return S == 1 ? 8 : (S == 2 ? 4 : (S == 4 ? 2 : (sq < 2 ? 3 : 2))); };
       const int r = static_cast<int>(rank);
       uint8_t* ring = smem + L::kRing;
       // accumulator fragment coordinates: rows frow / frow + 8 of tile t (weight row 32 cw + 16 t + ...), sequences fs, fs + 1
@@ -334,28 +355,56 @@ decode_mega_kernel(const MegaParams p) {
       auto stamp = [&](int step_now) {
         if (prof_on && step_now == p.prof_step && stamp_id < 64) p.prof[stamp_id++] = ptx::global_timer_ns();
       };
-      // LayerNorm of x[s] (or plain cast when w == nullptr) into xb (bf16 [8][XP]), warp s < S
-      auto stage_x = [&](const float* __restrict__ w, const float* __restrict__ b) {
+      // fine-grained trace (clock64) of layer 1 of the profiled step: p.prof[64..127]
+      unsigned long long* tr = nullptr;
+      auto fst = [&]() { MG_TR(tr); };
+      // Row-wise epilogue of warp s < S over v[8] = features {64 j + 2 lane, +1}: keep the fp32 residual row, LayerNorm it
+      // (one-pass mean / E[x^2], fp32; plain cast when w == nullptr) and stage the bf16 GEMM operand.
+      auto ln_store = [&](int s, float (&v)[8], const float* __restrict__ w, const float* __restrict__ b) {
+        float wv[8], bv[8];                                    // every load ahead of the first store
+        if (w) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float2 w2 = *reinterpret_cast<const float2*>(w + 64 * j4 + 2 * lane);
+            const float2 b2 = *reinterpret_cast<const float2*>(b + 64 * j4 + 2 * lane);
+            wv[2 * j4] = w2.x; wv[2 * j4 + 1] = w2.y; bv[2 * j4] = b2.x; bv[2 * j4 + 1] = b2.y;
+          }
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          *reinterpret_cast<float2*>(xs + s * D + 64 * j4 + 2 * lane) = make_float2(v[2 * j4], v[2 * j4 + 1]);
+        if (w) {
+          float sum = 0.f, sq = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sum += v[e]; sq = fmaf(v[e], v[e], sq); }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+          const float mean = sum * (1.0f / D);
+          const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd * wv[e] + bv[e];
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          *reinterpret_cast<uint32_t*>(xb + s * XP + 64 * j4 + 2 * lane) = pack_bf16(v[2 * j4], v[2 * j4 + 1]);
+      };
+      // embedding x = tok_emb[tok] + pos_emb[0] (api_cache.py:99 with T == 1) fused with the first LayerNorm
+      auto embed_ln = [&](const float* __restrict__ w, const float* __restrict__ b) {
         if (cw < S) {
           const int s = cw;
+          const bf16* te = p.tok_emb + static_cast<size_t>(misc.tok[s]) * D;
           float v[8];
-          const float4 a = *reinterpret_cast<const float4*>(xs + s * D + lane * 8);
-          const float4 c = *reinterpret_cast<const float4*>(xs + s * D + lane * 8 + 4);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-          if (w) {
-            float sum = 0.f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sum += v[e];
-            const float mean = warp_sum(sum) * (1.0f / D);
-            float sq = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { const float dlt = v[e] - mean; sq += dlt * dlt; }
-            const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / D) + 1e-5f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd * w[lane * 8 + e] + b[lane * 8 + e];
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const __nv_bfloat162 t2 = *reinterpret_cast<const __nv_bfloat162*>(te + 64 * j4 + 2 * lane);
+            const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(p.pos_emb + 64 * j4 + 2 * lane);
+            v[2 * j4] = __bfloat162float(t2.x) + __bfloat162float(p2.x);
+            v[2 * j4 + 1] = __bfloat162float(t2.y) + __bfloat162float(p2.y);
           }
-          const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          *reinterpret_cast<uint4*>(xb + s * XP + lane * 8) = o;
+          ln_store(s, v, w, b);
         }
         bar_compute();
       };
@@ -383,26 +432,33 @@ decode_mega_kernel(const MegaParams p) {
             }
         }
       };
-      auto exchange_finish = [&](const float* __restrict__ bias) {
+      // receive the peers' partial sums, x += sum + bias (fixed order: identical in every CTA of the cluster), then the
+      // NEXT LayerNorm (or the plain cast in front of the head) by the same warp: one pass, two barriers
+      auto exchange_finish_ln = [&](const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ b) {
         const int buf = xuse & 1;
         ptx::mbar_wait(&bars.xchg[buf], (xuse >> 1) & 1);
+        fst();                                                // peers' partial sums have landed
         bar_compute();                                        // local slot writes visible, everyone past the wait
         if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.xchg[buf], (CL - 1) * D * SMAX * 4);   // re-arm for use + 2
-        if (ct < D) {
-          const int f = ct;
-          const float bv = bias[f];
-          float acc[SMAX];
+        if (cw < S) {
+          const int s = cw;
+          float v[8];
 #pragma unroll
-          for (int s = 0; s < SMAX; ++s) acc[s] = 0.f;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int f0 = 64 * j4 + 2 * lane;
+            const float2 xv = *reinterpret_cast<const float2*>(xs + s * D + f0);
+            const float2 bv = *reinterpret_cast<const float2*>(bias + f0);
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-          for (int src = 0; src < CL; ++src) {
-            const float* sl = slots + ((buf * CL + src) * D + f) * SMAX;
-#pragma unroll
-            for (int s = 0; s < SMAX; ++s) acc[s] += sl[s];
+            for (int src = 0; src < CL; ++src) {
+              const float* sl = slots + ((buf * CL + src) * D + f0) * SMAX;
+              a0 += sl[s];
+              a1 += sl[SMAX + s];
+            }
+            v[2 * j4] = xv.x + (a0 + bv.x);
+            v[2 * j4 + 1] = xv.y + (a1 + bv.y);
           }
-#pragma unroll
-          for (int s = 0; s < SMAX; ++s)
-            if (s < S) xs[s * D + f] += acc[s] + bv;
+          ln_store(s, v, w, b);
         }
         ++xuse;
         bar_compute();
@@ -415,30 +471,33 @@ decode_mega_kernel(const MegaParams p) {
       uint32_t cand_use = 0, tok_use = 0;
 
       for (int step = 0; step < n_steps; ++step) {
-        // ---- embedding: x = tok_emb[tok] + pos_emb[0]   (api_cache.py:99 with T == 1) ----
-        if (ct < D) {
-          const int f = ct;
-          const float pe = __bfloat162float(p.pos_emb[f]);
-          for (int s = 0; s < S; ++s) xs[s * D + f] = __bfloat162float(p.tok_emb[static_cast<size_t>(misc.tok[s]) * D + f]) + pe;
-        }
-        bar_compute();
+        // ---- embedding + LayerNorm 1 of the first block ----
+        embed_ln(reinterpret_cast<const float*>(smem + L::kParams) + P_LN1W, reinterpret_cast<const float*>(smem + L::kParams) + P_LN1B);
         stamp(step);                                                        // 0: embedding done
         for (int l = 0; l < n_layer; ++l) {
-          const MegaLayer& lw = p.layers[l];
           const float* pl = reinterpret_cast<const float*>(smem + L::kParams) + l * kLayerParamFloats;
-          // ---- LN1 -> QKV: stage rows 0..63 = q slice, 64..127 = k slice, 128..191 = v slice ----
-          stage_x(pl + P_LN1W, pl + P_LN1B);
+#ifdef MG_MEGA_TRACE
+          tr = (prof_on && step == p.prof_step && l == 1) ? p.prof + 64 : nullptr;
+#endif
+          fst();                                                            // t0: layer start
+          // ---- QKV (LN1 was applied by the previous epilogue): stage rows 0..63 = q, 64..127 = k, 128..191 = v slice ----
           if (cw < GW) {
+            const int part_id = cw >> 1;                      // 0 = q, 1 = k, 2 = v
+            float qb[2][2];                                   // biases ahead of the MMAs (no load behind a store in the epilogue)
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8)
+                qb[t][h8] = cw < 6 ? pl[P_BQKV + part_id * FS + (cw & 1) * 32 + t * 16 + frow + h8 * 8] : 0.f;
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, cw < 6, acc);
+            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, cw < 6, acc, tr);
             if (cw < 6 && fs < S) {
-              const int part_id = cw >> 1;                    // 0 = q, 1 = k, 2 = v
 #pragma unroll
               for (int t = 0; t < 2; ++t)
 #pragma unroll
                 for (int h8 = 0; h8 < 2; ++h8) {
                   const int f = (cw & 1) * 32 + t * 16 + frow + h8 * 8;      // feature inside the 64-wide slice
-                  const float bias = pl[P_BQKV + part_id * FS + f];
+                  const float bias = qb[t][h8];
 #pragma unroll
                   for (int e = 0; e < 2; ++e) {
                     const int s = fs + e;
@@ -452,13 +511,17 @@ decode_mega_kernel(const MegaParams p) {
                 }
             }
           }
+          fst();                                                            // QKV epilogue
           bar_compute();
           stamp(step);                                                      // +1: QKV done
           // ---- append the new K/V rows (api_cache.py:66-67) + flash-decoding over this CTA's slice ----
+          const size_t kv_seq = static_cast<size_t>(CL) * p.Tmax * FS;       // cache elements per sequence
+          const size_t kv_cta = (static_cast<size_t>(b0) * CL + r) * p.Tmax * FS;
+          bf16* const kbase = misc.kvp[l][0] + kv_cta;
+          bf16* const vbase = misc.kvp[l][1] + kv_cta;
           if (cw < S && lane < 16 && !misc.fin[cw]) {
             const int s = cw, which = lane >> 3, c = lane & 7;
-            bf16* dst = (which ? lw.vc : lw.kc) +
-                        ((static_cast<size_t>(b0 + s) * CL + r) * p.Tmax + misc.len[s]) * FS + c * 8;
+            bf16* dst = (which ? vbase : kbase) + s * kv_seq + static_cast<size_t>(misc.len[s]) * FS + c * 8;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>((which ? vnew : knew) + s * FS + c * 8);
           }
           // L2 prefetch of the NEXT layer's K/V streams of this CTA (next step's layer 0 after the last layer):
@@ -468,17 +531,17 @@ decode_mega_kernel(const MegaParams p) {
             const int ln = (l + 1 < n_layer) ? l + 1 : 0;
             const int rows = misc.len[s] + (ln == 0 ? 1 : 0);
             if (!misc.fin[s] && rows > 0) {
-              const MegaLayer& nx = p.layers[ln];
-              const bf16* src = (which ? nx.vc : nx.kc) + (static_cast<size_t>(b0 + s) * CL + r) * p.Tmax * FS;
+              const bf16* src = misc.kvp[ln][which] + kv_cta + s * kv_seq;
               ptx::prefetch_l2_bulk(src, static_cast<uint32_t>(rows) * FS * 2);
             }
           }
+          fst();                                                            // append + prefetch issued
           {
             // warps are dealt round-robin to the sequences: warp cw serves sequence cw % S as its (cw / S)-th worker
-            const int s = cw % S, wi = cw / S, nws = (NCW - s + S - 1) / S;
+            const int s = seq_of(cw), wi = worker_of(cw), nws = workers(s);
             const int len = misc.fin[s] ? 0 : misc.len[s];
-            const bf16* kc = lw.kc + (static_cast<size_t>(b0 + s) * CL + r) * p.Tmax * FS;
-            const bf16* vc = lw.vc + (static_cast<size_t>(b0 + s) * CL + r) * p.Tmax * FS;
+            const bf16* kc = kbase + s * kv_seq;
+            const bf16* vc = vbase + s * kv_seq;
             const int rr = lane >> 3, c = lane & 7;           // row inside a 4-row group, 16-byte chunk
             float q[8];
 #pragma unroll
@@ -546,6 +609,31 @@ decode_mega_kernel(const MegaParams p) {
                 m_run = m_new;
               }
             }
+            // the new token's own row (api_cache.py:66-68: the cache already contains it): every warp computes its score
+            // with the same shuffle pattern, the first worker of the sequence folds it in as one more row
+            {
+              const uint4 kn = *reinterpret_cast<const uint4*>(knew + s * FS + c * 8);
+              float kf[8];
+              unpack8(kn, kf);
+              float sn = 0.f;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) sn = fmaf(q[e], kf[e], sn);
+              sn += __shfl_xor_sync(0xffffffffu, sn, 1);
+              sn += __shfl_xor_sync(0xffffffffu, sn, 2);
+              const float t4 = __shfl_xor_sync(0xffffffffu, sn, 4);
+              sn += (cph == 8) ? t4 : 0.f;
+              if (wi == 0 && rr == 0) {
+                const uint4 vn = *reinterpret_cast<const uint4*>(vnew + s * FS + c * 8);
+                float vf[8];
+                unpack8(vn, vf);
+                const float m_new = fmaxf(m_run, sn);
+                const float corr = exp2f(m_run - m_new), pw = exp2f(sn - m_new);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(pw, vf[e], acc[e] * corr);
+                l_run = l_run * corr + pw;
+                m_run = m_new;
+              }
+            }
             // merge the four row residues of the warp (lanes xor 8, 16)
 #pragma unroll
             for (int o = 8; o <= 16; o <<= 1) {
@@ -564,73 +652,102 @@ decode_mega_kernel(const MegaParams p) {
             }
             if (lane < 8) {
               float* pp = part + (s * NCW + wi) * 68;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pp[c * 8 + e] = acc[e];
-              if ((c % cph) == 0) { pp[64 + (c / cph) * 2] = m_run; pp[64 + (c / cph) * 2 + 1] = l_run; }
+              *reinterpret_cast<float4*>(pp + c * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+              *reinterpret_cast<float4*>(pp + c * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+              if ((c & (cph - 1)) == 0) { pp[64 + (c >> (hd_shift - 3)) * 2] = m_run; pp[64 + (c >> (hd_shift - 3)) * 2 + 1] = l_run; }
             }
           }
+          fst();                                                            // attention stream done (this warp)
           bar_compute();
-          // final merge over the warps + the new token's own row; writes the out_proj operand
+          fst();
+          // final merge over the workers of the sequence (worker 0 always holds the new token: its maximum is finite)
           if (ct < S * FS) {
-            const int s = ct / FS, f = ct - s * FS, hh = f / hd;
-            float snew = 0.f;
-            for (int e = 0; e < hd; ++e) snew = fmaf(qs[s * FS + hh * hd + e], __bfloat162float(knew[s * FS + hh * hd + e]), snew);
-            const int nws = (NCW - s + S - 1) / S;
-            float M = snew;
-            for (int w = 0; w < nws; ++w) M = fmaxf(M, part[(s * NCW + w) * 68 + 64 + hh * 2]);
-            const float pn = exp2f(snew - M);
-            float Lsum = pn, o = pn * __bfloat162float(vnew[s * FS + f]);
-            for (int w = 0; w < nws; ++w) {
-              const float* pp = part + (s * NCW + w) * 68;
-              const float mw = pp[64 + hh * 2];
-              if (mw > -INFINITY) {
-                const float fw = exp2f(mw - M);
-                Lsum = fmaf(pp[64 + hh * 2 + 1], fw, Lsum);
-                o = fmaf(pp[f], fw, o);
-              }
+            const int mg_s = ct >> 6, mg_f = ct & 63, mg_hh = mg_f >> hd_shift, mg_nws = workers(mg_s);
+            const float* pp0 = part + mg_s * NCW * 68;
+            float mw[NCW], lw_[NCW], ow[NCW];
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) {                                   // all loads first, then the arithmetic
+              const bool on = w < mg_nws;
+              mw[w] = on ? pp0[w * 68 + 64 + mg_hh * 2] : -INFINITY;
+              lw_[w] = on ? pp0[w * 68 + 64 + mg_hh * 2 + 1] : 0.f;
+              ow[w] = on ? pp0[w * 68 + mg_f] : 0.f;
             }
-            attb[s * AP + f] = __float2bfloat16_rn(o / Lsum);
+            float M = mw[0];
+#pragma unroll
+            for (int w = 1; w < NCW; ++w) M = fmaxf(M, mw[w]);
+            float Lsum = 0.f, o = 0.f;
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) {
+              const float fw = exp2f(mw[w] - M);                            // exp2(-inf) = 0 for an idle worker
+              Lsum = fmaf(lw_[w], fw, Lsum);
+              o = fmaf(ow[w], fw, o);
+            }
+            attb[mg_s * AP + mg_f] = __float2bfloat16_rn(__fdividef(o, Lsum));
           }
+          fst();                                                            // merge done
           bar_compute();
           stamp(step);                                                      // +2: attention done
           // ---- out_proj (row-parallel over this CTA's 64 attention features) -> exchange -> x += attn ----
           if (cw < GW) {
             float acc[2][4];
-            gemm_pair<1, NSTAGE>(ring, bars.full, bars.empty, rp, attb, AP, cw, lane, true, acc);
+            gemm_pair<1, NSTAGE>(ring, bars.full, bars.empty, rp, attb, AP, cw, lane, true, acc, tr);
             exchange_send(acc);
           }
-          exchange_finish(pl + P_BOUT);
-          stamp(step);                                                      // +3: out_proj + exchange done
-          // ---- LN2 -> MLP1 (+GELU, this CTA's 256 hidden units) -> MLP2 (row-parallel) -> exchange ----
-          stage_x(pl + P_LN2W, pl + P_LN2B);
+          fst();                                                            // out_proj sent
+          exchange_finish_ln(pl + P_BOUT, pl + P_LN2W, pl + P_LN2B);
+          fst();
+          stamp(step);                                                      // +3: out_proj + exchange + LN2 done
+          // ---- MLP1 (+GELU, this CTA's 256 hidden units) -> MLP2 (row-parallel) -> exchange ----
           if (cw < GW) {
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc);
-            if (fs < S) {
+            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc, tr);
+            // bias + exact-erf GELU: the valid accumulators sit in quad lanes 0 .. SMAX/2-1 (two sequences each); spread
+            // them over the four lanes of the quad so that every lane evaluates erff for 2 (SMAX = 2) or 4 values
+            {
+              constexpr int NSRC = SMAX / 2, PER = 2 * NSRC;
+              const int ql = lane & 3, qbase = lane & ~3;
+              float mine[PER], b1v[PER];
 #pragma unroll
-              for (int t = 0; t < 2; ++t)
+              for (int idx = 0; idx < PER; ++idx) {
+                const int i = (ql * PER + idx) & 7;
+                b1v[idx] = pl[P_B1 + cw * 32 + (i >> 2) * 16 + frow + ((i >> 1) & 1) * 8];
+              }
 #pragma unroll
-                for (int h8 = 0; h8 < 2; ++h8) {
-                  const int j = cw * 32 + t * 16 + frow + h8 * 8;            // hidden unit inside this CTA's slice
-                  const float b1 = pl[P_B1 + j];
+              for (int src = 0; src < NSRC; ++src)
 #pragma unroll
-                  for (int e = 0; e < 2; ++e)
-                    if (fs + e < S) hb[(fs + e) * XP + j] = __float2bfloat16_rn(gelu_erf_f(acc[t][h8 * 2 + e] + b1));
+                for (int i = 0; i < 8; ++i) {
+                  const float got = __shfl_sync(0xffffffffu, acc[i >> 2][i & 3], qbase + src);
+                  const int v = src * 8 + i;                               // value id inside the quad: owner lane v / PER
+                  if (v / PER == ql) mine[v % PER] = got;
                 }
+#pragma unroll
+              for (int idx = 0; idx < PER; ++idx) {
+                const int v = ql * PER + idx, src = v >> 3, i = v & 7;
+                const int t = i >> 2, h8 = (i >> 1) & 1, sq = 2 * src + (i & 1);
+                const int j = cw * 32 + t * 16 + frow + h8 * 8;            // hidden unit inside this CTA's slice
+                if (sq < S) hb[sq * XP + j] = __float2bfloat16_rn(gelu_erf_f(mine[idx] + b1v[idx]));
+              }
             }
           }
+          fst();                                                            // GELU epilogue
           bar_compute();
           stamp(step);                                                      // +4: MLP1 done
           if (cw < GW) {
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, hb, XP, cw, lane, true, acc);
+            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, hb, XP, cw, lane, true, acc, tr);
             exchange_send(acc);
           }
-          exchange_finish(pl + P_B2);
+          fst();                                                            // mlp.2 sent
+          {
+            // ... + LayerNorm 1 of the next block, or the plain cast in front of the head (no final LayerNorm, api_cache.py:105)
+            const float* pn = pl + kLayerParamFloats;
+            const bool more = l + 1 < n_layer;
+            exchange_finish_ln(pl + P_B2, more ? pn + P_LN1W : nullptr, more ? pn + P_LN1B : nullptr);
+          }
+          fst();
           stamp(step);                                                      // +5: MLP2 + exchange done
         }
-        // ---- head: logits of this CTA's vocabulary slice (no final LayerNorm, api_cache.py:105) ----
-        stage_x(nullptr, nullptr);
+        // ---- head: logits of this CTA's vocabulary slice ----
         {
           const int v_lo = r * p.VS, v_hi = min(p.V, (r + 1) * p.VS);
           for (int pr = 0; pr < p.NP && cw < GW; ++pr) {
@@ -643,7 +760,7 @@ decode_mega_kernel(const MegaParams p) {
                 hbv[t][h8] = vr < v_hi ? __ldg(p.head_b + vr) : 0.f;
               }
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc);
+            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc, tr);
             if (fs < S) {
 #pragma unroll
               for (int t = 0; t < 2; ++t)
@@ -673,7 +790,7 @@ decode_mega_kernel(const MegaParams p) {
         // the k largest logits of this CTA's vocabulary slice with warp-aggregated histogram updates.
         const int k = sp.top_k;
         if (cw < GW) {
-          const int s = cw % S, wi = cw / S, nws = (GW - s + S - 1) / S;
+          const int s = seq_of(cw), wi = worker_of(cw), nws = workers(s);        // GW == NCW
           const int gt = wi * 32 + lane, gn = nws * 32;       // thread index / count inside the group
           const uint32_t gbar = 3 + s;                        // named barrier of the group
           float* z = logits + s * NL;

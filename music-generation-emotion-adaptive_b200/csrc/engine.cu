@@ -419,9 +419,9 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
     cudaMemcpy(h, e->d_prof, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[mega prof] step %d (ns since first stamp):", p.prof_step);
     for (int i = 0; i < 64 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
-    fprintf(stderr, "\n[mega prof] MMA thread, layer 0 (wait-B, B-ready, committed per GEMM):");
-    for (int i = 64; i < 128 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[0]));
-    fprintf(stderr, "\n[mega prof] attention layer 0 warp 0: load-wait cycles %llu, compute cycles %llu, batches %llu\n", h[100], h[101], h[102]);
+    fprintf(stderr, "\n[mega prof] layer 1 fine trace (SM cycles since layer start, warp 1 lane 0):");
+    for (int i = 64; i < 128 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[64]));
+    fprintf(stderr, "\n");
   }
   e->t_steps = e->cur_steps;
   return true;
