@@ -226,7 +226,168 @@ __device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_
   MG_TR(tr);
 }
 
-template <int SMAX, int NSTAGE>
+
+__device__ __forceinline__ uint4 ldg_stream16(const bf16* p) { return ptx::ld_global_stream16(p); }
+
+// Tensor-core flash-decoding of ONE (sequence, head) by ONE warp straight from global memory (no shared-memory staging):
+// this worker takes the 32-key blocks wi, wi + nws, ... of the cache.
+//   scores   S = q K^T   : A = the query (row 0 = bf16 hi part, row 8 = bf16 lo part of the fp32 query, so the product keeps
+//                          fp32-query accuracy for free), B = K rows; lane (g, t) loads 16 bytes = dims [8t, 8t+8) of key row
+//                          8 j + g for the j-th MMA of the block: eight consecutive rows of the head-major K cache, one
+//                          contiguous 512-byte request (head_dim 32); lane t of row 0 receives the scores of keys 8j + 2t + {0,1};
+//   output   O = P V     : A = the probabilities (row 0), B = V^T: lane (g, t) loads 16 bytes = key positions [8t, 8t+8) of dim
+//                          8 n + g.  The V cache of this kernel is stored per 32-key block as [dim][32 positions] with key
+//                          8j + 2t + e at position 8t + 2j + e, i.e. exactly in the order the score MMAs leave the
+//                          probabilities in lane t -- no shuffles, and again one contiguous 512-byte request per load.
+// The contraction index of an MMA may be permuted freely as long as A and B agree, which is what makes 16-byte loads work.
+// Only row 0 (lanes 0..3) carries data; the other 15 rows of the m16 tile are idle -- the tensor pipe has nothing else to do.
+// kh: K rows of this (sequence, head) [T][HD], vt: V blocks of this (sequence, head) [T / 32][HD][32], q: fp32, log2-scaled.
+template <int HD>
+__device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int wi, int nws,
+                                        int lane, const float* __restrict__ q, const bf16* __restrict__ knew,
+                                        const bf16* __restrict__ vnew, bool fold_new, float* __restrict__ out) {
+  constexpr int KS = HD / 16;              // k-steps of the score MMAs
+  constexpr int NT = HD / 8;               // n-tiles (8 dims) of the output MMAs
+  constexpr int KL = HD / 32;              // 16-byte K loads per lane per key row
+  const int g = lane >> 2, t = lane & 3;
+  // query fragments: k-step ks covers dims 32 (ks / 2) + 8 t + 4 (ks % 2) + {0..3} of this lane
+  uint32_t qh[KS][2], ql[KS][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const float4 qv = *reinterpret_cast<const float4*>(q + 32 * (ks >> 1) + 8 * t + 4 * (ks & 1));
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(qv.x, qv.y), h1 = __floats2bfloat162_rn(qv.z, qv.w);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(qv.x - __bfloat162float(h0.x), qv.y - __bfloat162float(h0.y));
+    const __nv_bfloat162 l1 = __floats2bfloat162_rn(qv.z - __bfloat162float(h1.x), qv.w - __bfloat162float(h1.y));
+    const bool row0 = g == 0;
+    qh[ks][0] = row0 ? *reinterpret_cast<const uint32_t*>(&h0) : 0u;
+    qh[ks][1] = row0 ? *reinterpret_cast<const uint32_t*>(&h1) : 0u;
+    ql[ks][0] = row0 ? *reinterpret_cast<const uint32_t*>(&l0) : 0u;
+    ql[ks][1] = row0 ? *reinterpret_cast<const uint32_t*>(&l1) : 0u;
+  }
+  float oacc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[n][e] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;   // l_run: this lane's share of the denominator (summed over the quad at the end)
+
+  const int nblk = (len + 31) >> 5;
+  const bf16* kl = kh + 8 * t;
+  const bf16* vl = vt + g * 32 + 8 * t;                         // + block * HD * 32 + n * 256
+  auto load_block = [&](int b, uint4 (&kq)[4][KL], uint4 (&vq)[NT]) {
+    const int key0 = b << 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = min(key0 + 8 * j + g, len - 1);          // rows past the end are masked below; never read them
+#pragma unroll
+      for (int c = 0; c < KL; ++c) kq[j][c] = ldg_stream16(kl + static_cast<size_t>(row) * HD + 32 * c);
+    }
+    const bf16* vb = vl + static_cast<size_t>(b) * (HD * 32);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) vq[n] = ldg_stream16(vb + n * 256);
+  };
+  auto compute_block = [&](int b, const uint4 (&kq)[4][KL], const uint4 (&vq)[NT]) {
+    const int key0 = b << 5;
+    float sc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float c4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < KL; ++c) {
+        const uint32_t a0[4] = {qh[2 * c][0], ql[2 * c][0], qh[2 * c][1], ql[2 * c][1]};
+        const uint32_t a1[4] = {qh[2 * c + 1][0], ql[2 * c + 1][0], qh[2 * c + 1][1], ql[2 * c + 1][1]};
+        mma_bf16_16816(c4, a0, kq[j][c].x, kq[j][c].y);
+        mma_bf16_16816(c4, a1, kq[j][c].z, kq[j][c].w);
+      }
+      const int key = key0 + 8 * j + 2 * t;
+      sc[j][0] = key < len ? c4[0] + c4[2] : -INFINITY;          // row 0 (hi) + row 8 (lo)
+      sc[j][1] = key + 1 < len ? c4[1] + c4[3] : -INFINITY;
+    }
+    float mb = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1])),
+                     fmaxf(fmaxf(sc[2][0], sc[2][1]), fmaxf(sc[3][0], sc[3][1])));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    const float m_new = fmaxf(m_run, mb);                        // finite: key0 < len, so the quad holds a valid key
+    const float corr = exp2f(m_run - m_new);
+    float psum = 0.f;
+    uint32_t pa[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const float p0 = exp2f(sc[2 * u + w][0] - m_new), p1 = exp2f(sc[2 * u + w][1] - m_new);
+        psum += p0 + p1;
+        pa[u][w] = pack_bf16(p0, p1);
+      }
+    l_run = fmaf(l_run, corr, psum);
+    m_run = m_new;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      oacc[n][0] *= corr;
+      oacc[n][1] *= corr;
+      const uint32_t a0[4] = {pa[0][0], 0u, pa[0][1], 0u};
+      const uint32_t a1[4] = {pa[1][0], 0u, pa[1][1], 0u};
+      mma_bf16_16816(oacc[n], a0, vq[n].x, vq[n].y);
+      mma_bf16_16816(oacc[n], a1, vq[n].z, vq[n].w);
+    }
+  };
+  if (HD == 32) {
+    // two register sets: the loads of the next block are in flight while this one is computed
+    uint4 kqa[4][KL], vqa[NT], kqb[4][KL], vqb[NT];
+    int b = wi;
+    if (b < nblk) load_block(b, kqa, vqa);
+    while (b < nblk) {
+      const int b1 = b + nws;
+      if (b1 < nblk) load_block(b1, kqb, vqb);
+      compute_block(b, kqa, vqa);
+      if (b1 >= nblk) break;
+      const int b2 = b1 + nws;
+      if (b2 < nblk) load_block(b2, kqa, vqa);
+      compute_block(b1, kqb, vqb);
+      b = b2;
+    }
+  } else {
+    uint4 kqa[4][KL], vqa[NT];
+    for (int b = wi; b < nblk; b += nws) {
+      load_block(b, kqa, vqa);
+      compute_block(b, kqa, vqa);
+    }
+  }
+  // the new token's own row (the reference's cache already contains it, api_cache.py:66-68): first worker only
+  if (fold_new) {
+    float sn = 0.f;
+#pragma unroll
+    for (int c = 0; c < KL; ++c) {
+      const uint4 kn = *reinterpret_cast<const uint4*>(knew + 32 * c + 8 * t);
+      float kf[8];
+      unpack8(kn, kf);
+      const float4 q0 = *reinterpret_cast<const float4*>(q + 32 * c + 8 * t), q1 = *reinterpret_cast<const float4*>(q + 32 * c + 8 * t + 4);
+      sn = fmaf(q0.x, kf[0], fmaf(q0.y, kf[1], fmaf(q0.z, kf[2], fmaf(q0.w, kf[3], sn))));
+      sn = fmaf(q1.x, kf[4], fmaf(q1.y, kf[5], fmaf(q1.z, kf[6], fmaf(q1.w, kf[7], sn))));
+    }
+    sn += __shfl_xor_sync(0xffffffffu, sn, 1);
+    sn += __shfl_xor_sync(0xffffffffu, sn, 2);
+    const float m_new = fmaxf(m_run, sn);
+    const float corr = exp2f(m_run - m_new), pw = exp2f(sn - m_new);
+    l_run = fmaf(l_run, corr, t == 0 ? pw : 0.f);
+    m_run = m_new;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vnew + 8 * n + 2 * t);
+      oacc[n][0] = fmaf(pw, __bfloat162float(v2.x), oacc[n][0] * corr);
+      oacc[n][1] = fmaf(pw, __bfloat162float(v2.y), oacc[n][1] * corr);
+    }
+  }
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (g == 0) {                                                   // out: [HD] numerators | m | l
+#pragma unroll
+    for (int n = 0; n < NT; ++n) *reinterpret_cast<float2*>(out + 8 * n + 2 * t) = make_float2(oacc[n][0], oacc[n][1]);
+    if (t == 0) { out[64] = m_run; out[65] = l_run; }
+  }
+}
+
+template <int SMAX, int NSTAGE, int HD>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHREADS, 1)
 decode_mega_kernel(const MegaParams p) {
   using L = Smem<SMAX, NSTAGE>;
@@ -256,7 +417,7 @@ decode_mega_kernel(const MegaParams p) {
   const int S = min(p.S, p.B - cluster * p.S);             // sequences of this cluster (may be <= 0)
   const int b0 = cluster * p.S;                            // first global sequence index
   const int n_layer = p.n_layer, NL = 2 * p.NP * 128;      // head rows per CTA, padded to tile pairs
-  const int hd = p.head_dim;
+  constexpr int hd = HD;
 
   // ---------------- one-time setup ----------------
   for (int i = threadIdx.x; i < (L::kSlots - L::kBx) / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(smem + L::kBx)[i] = 0u;
@@ -293,7 +454,7 @@ decode_mega_kernel(const MegaParams p) {
       misc.maxnew[s] = live ? p.st.max_new[b0 + s] : 0;
       misc.fin[s] = live ? static_cast<int>(p.st.finished[b0 + s]) : 1;
     }
-    for (int l = 0; l < n_layer; ++l) { misc.kvp[l][0] = p.layers[l].kc; misc.kvp[l][1] = p.layers[l].vc; }
+    for (int l = 0; l < n_layer; ++l) { misc.kvp[l][0] = p.layers[l].kh; misc.kvp[l][1] = p.layers[l].vt; }
   }
   __syncthreads();
   // every CTA of the cluster must have initialised its barriers before any remote st.async lands
@@ -337,8 +498,14 @@ decode_mega_kernel(const MegaParams p) {
       RingPos rp;
       const SampleParams sp = *p.sp;
       const float scale_log2 = kLog2e / sqrtf(static_cast<float>(hd));
+      const float inv_temp = 1.0f / sp.temperature;          // logits / temperature (api_cache.py:169) as one multiply
       const int cph = hd / 8;                                // 16-byte chunks per head (4 or 8)
-      const int hd_shift = hd == 64 ? 6 : 5;
+      constexpr int hd_shift = HD == 64 ? 6 : 5, nh_shift = 6 - hd_shift;   // heads per 64-wide slice: 1 << nh_shift
+      // attention work assignment: (sequence, head) pairs dealt round-robin to the warps
+      const int n_pairs = S << nh_shift;
+      int att_pair = cw, att_wi = 0;
+      while (att_pair >= n_pairs) { att_pair -= n_pairs; ++att_wi; }
+      const int att_nws = (NCW - att_pair + n_pairs - 1) / n_pairs;
       // work assignment without run-time integer divisions (S <= 4): warp cw serves sequence cw % S as its (cw / S)-th
       // worker; a sequence has NCW / S workers (3, 3, 2 when S == 3)
       auto seq_of = [&](int w) { return S == 3 ? w % 3 : (w & (S - 1)); };
@@ -514,173 +681,61 @@ decode_mega_kernel(const MegaParams p) {
           fst();                                                            // QKV epilogue
           bar_compute();
           stamp(step);                                                      // +1: QKV done
-          // ---- append the new K/V rows (api_cache.py:66-67) + flash-decoding over this CTA's slice ----
-          const size_t kv_seq = static_cast<size_t>(CL) * p.Tmax * FS;       // cache elements per sequence
-          const size_t kv_cta = (static_cast<size_t>(b0) * CL + r) * p.Tmax * FS;
-          bf16* const kbase = misc.kvp[l][0] + kv_cta;
-          bf16* const vbase = misc.kvp[l][1] + kv_cta;
-          if (cw < S && lane < 16 && !misc.fin[cw]) {
-            const int s = cw, which = lane >> 3, c = lane & 7;
-            bf16* dst = (which ? vbase : kbase) + s * kv_seq + static_cast<size_t>(misc.len[s]) * FS + c * 8;
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>((which ? vnew : knew) + s * FS + c * 8);
+          // ---- append the new K row / V^T column (api_cache.py:66-67) + flash-decoding over this CTA's slice ----
+          const size_t kv_seq = static_cast<size_t>(CL) * p.Tmax * FS;       // K cache elements per sequence
+          const size_t vt_seq = static_cast<size_t>(CL) * p.Tvt * FS;        // V cache elements per sequence
+          bf16* const kbase = misc.kvp[l][0] + (static_cast<size_t>(b0) * CL + r) * p.Tmax * FS;   // [head][T][hd]
+          bf16* const vbase = misc.kvp[l][1] + (static_cast<size_t>(b0) * CL + r) * p.Tvt * FS;    // [head][T / 32][hd][32]
+          if (cw < S && lane < 8 && !misc.fin[cw]) {
+            const int s = cw, c = lane, h = (8 * c) >> hd_shift, d0 = (8 * c) & (hd - 1);
+            bf16* dst = kbase + s * kv_seq + (static_cast<size_t>(h) * p.Tmax + misc.len[s]) * hd + d0;
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(knew + s * FS + c * 8);
           }
-          // L2 prefetch of the NEXT layer's K/V streams of this CTA (next step's layer 0 after the last layer):
-          // HBM keeps streaming while the GEMM / exchange / sampler phases run; four bulk prefetches per layer
-          if (cw == NCW - 1 && lane < 2 * S) {
-            const int s = lane >> 1, which = lane & 1;
-            const int ln = (l + 1 < n_layer) ? l + 1 : 0;
-            const int rows = misc.len[s] + (ln == 0 ? 1 : 0);
-            if (!misc.fin[s] && rows > 0) {
-              const bf16* src = misc.kvp[ln][which] + kv_cta + s * kv_seq;
-              ptx::prefetch_l2_bulk(src, static_cast<uint32_t>(rows) * FS * 2);
+          if (ct < S * FS) {
+            const int s = ct >> 6, f = ct & 63, h = f >> hd_shift, d = f & (hd - 1);
+            if (!misc.fin[s]) {
+              const int key = misc.len[s], ki = key & 31;
+              const int pos = 8 * ((ki >> 1) & 3) + 2 * (ki >> 3) + (ki & 1);          // see attn_tc
+              vbase[s * vt_seq + (static_cast<size_t>(h) * (p.Tvt >> 5) + (key >> 5)) * (hd * 32) + d * 32 + pos] = vnew[s * FS + f];
             }
           }
           fst();                                                            // append + prefetch issued
           {
-            // warps are dealt round-robin to the sequences: warp cw serves sequence cw % S as its (cw / S)-th worker
-            const int s = seq_of(cw), wi = worker_of(cw), nws = workers(s);
+            // warp cw is the att_wi-th worker of (sequence, head) pair att_pair
+            const int s = att_pair >> nh_shift, h = att_pair & ((1 << nh_shift) - 1);
             const int len = misc.fin[s] ? 0 : misc.len[s];
-            const bf16* kc = kbase + s * kv_seq;
-            const bf16* vc = vbase + s * kv_seq;
-            const int rr = lane >> 3, c = lane & 7;           // row inside a 4-row group, 16-byte chunk
-            float q[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) q[e] = qs[s * FS + c * 8 + e];
-            float m_run = -INFINITY, l_run = 0.f, acc[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-            // Batches of U four-row groups: all 2 x U 16-byte loads of a batch are issued before the first use
-            // (the scoreboard tracks loads per batch, so finer-grained register pipelining serialises them).
-            constexpr int U = 8;
-            for (int base = wi * 4 * U; base < len; base += nws * 4 * U) {
-              uint4 kr[U], vr[U];
-#pragma unroll
-              for (int u = 0; u < U; ++u) {
-                const int row = base + u * 4 + rr;
-                if (row < len) {
-                  const int arow = p.dbg_attn_hot ? (row & 31) : row;
-                  kr[u] = ptx::ld_global_stream16(kc + static_cast<size_t>(arow) * FS + c * 8);
-                  vr[u] = ptx::ld_global_stream16(vc + static_cast<size_t>(arow) * FS + c * 8);
-                } else {
-                  kr[u] = make_uint4(0, 0, 0, 0);
-                  vr[u] = make_uint4(0, 0, 0, 0);
-                }
-              }
-              // phase-ordered (all dots, then all shuffles) so the U independent chains interleave; no branches
-              float sc[U];
-#pragma unroll
-              for (int u = 0; u < U; ++u) {
-                float kf[8];
-                unpack8(kr[u], kf);
-                const float d0 = fmaf(q[0], kf[0], fmaf(q[2], kf[2], fmaf(q[4], kf[4], q[6] * kf[6])));
-                const float d1 = fmaf(q[1], kf[1], fmaf(q[3], kf[3], fmaf(q[5], kf[5], q[7] * kf[7])));
-                sc[u] = d0 + d1;
-              }
-#pragma unroll
-              for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 1);
-#pragma unroll
-              for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], 2);
-#pragma unroll
-              for (int u = 0; u < U; ++u) {
-                const float t4 = __shfl_xor_sync(0xffffffffu, sc[u], 4);
-                sc[u] += (cph == 8) ? t4 : 0.f;
-              }
-              float m_new = m_run;
-#pragma unroll
-              for (int u = 0; u < U; ++u) {
-                sc[u] = (base + u * 4 + rr < len) ? sc[u] : -INFINITY;
-                m_new = fmaxf(m_new, sc[u]);
-              }
-              if (m_new > -INFINITY) {
-                const float corr = exp2f(m_run - m_new);
-                float psum = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] *= corr;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                  const float pw = exp2f(sc[u] - m_new);
-                  psum += pw;
-                  float vf[8];
-                  unpack8(vr[u], vf);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) acc[e] = fmaf(pw, vf[e], acc[e]);
-                }
-                l_run = l_run * corr + psum;
-                m_run = m_new;
-              }
-            }
-            // the new token's own row (api_cache.py:66-68: the cache already contains it): every warp computes its score
-            // with the same shuffle pattern, the first worker of the sequence folds it in as one more row
-            {
-              const uint4 kn = *reinterpret_cast<const uint4*>(knew + s * FS + c * 8);
-              float kf[8];
-              unpack8(kn, kf);
-              float sn = 0.f;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) sn = fmaf(q[e], kf[e], sn);
-              sn += __shfl_xor_sync(0xffffffffu, sn, 1);
-              sn += __shfl_xor_sync(0xffffffffu, sn, 2);
-              const float t4 = __shfl_xor_sync(0xffffffffu, sn, 4);
-              sn += (cph == 8) ? t4 : 0.f;
-              if (wi == 0 && rr == 0) {
-                const uint4 vn = *reinterpret_cast<const uint4*>(vnew + s * FS + c * 8);
-                float vf[8];
-                unpack8(vn, vf);
-                const float m_new = fmaxf(m_run, sn);
-                const float corr = exp2f(m_run - m_new), pw = exp2f(sn - m_new);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(pw, vf[e], acc[e] * corr);
-                l_run = l_run * corr + pw;
-                m_run = m_new;
-              }
-            }
-            // merge the four row residues of the warp (lanes xor 8, 16)
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              const float m_o = __shfl_xor_sync(0xffffffffu, m_run, o);
-              const float l_o = __shfl_xor_sync(0xffffffffu, l_run, o);
-              const float m_n = fmaxf(m_run, m_o);
-              const float fa = (m_run > -INFINITY) ? exp2f(m_run - m_n) : 0.f;
-              const float fb = (m_o > -INFINITY) ? exp2f(m_o - m_n) : 0.f;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float a_o = __shfl_xor_sync(0xffffffffu, acc[e], o);
-                acc[e] = acc[e] * fa + a_o * fb;
-              }
-              l_run = l_run * fa + l_o * fb;
-              m_run = m_n;
-            }
-            if (lane < 8) {
-              float* pp = part + (s * NCW + wi) * 68;
-              *reinterpret_cast<float4*>(pp + c * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-              *reinterpret_cast<float4*>(pp + c * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-              if ((c & (cph - 1)) == 0) { pp[64 + (c >> (hd_shift - 3)) * 2] = m_run; pp[64 + (c >> (hd_shift - 3)) * 2 + 1] = l_run; }
-            }
+            const bf16* kh = kbase + s * kv_seq + static_cast<size_t>(h) * p.Tmax * hd;
+            const bf16* vt = vbase + s * vt_seq + static_cast<size_t>(h) * p.Tvt * hd;
+            float* out = part + cw * 68;
+            attn_tc<HD>(kh, vt, len, att_wi, att_nws, lane, qs + s * FS + h * HD, knew + s * FS + h * HD, vnew + s * FS + h * HD,
+                        att_wi == 0, out);
           }
           fst();                                                            // attention stream done (this warp)
           bar_compute();
           fst();
-          // final merge over the workers of the sequence (worker 0 always holds the new token: its maximum is finite)
+          // final merge over the workers of the (sequence, head) pair (worker 0 always holds the new token: finite maximum)
           if (ct < S * FS) {
-            const int mg_s = ct >> 6, mg_f = ct & 63, mg_hh = mg_f >> hd_shift, mg_nws = workers(mg_s);
-            const float* pp0 = part + mg_s * NCW * 68;
+            const int mg_s = ct >> 6, mg_f = ct & 63, mg_h = mg_f >> hd_shift, mg_d = mg_f & (hd - 1);
+            const int pair = (mg_s << nh_shift) + mg_h;
             float mw[NCW], lw_[NCW], ow[NCW];
 #pragma unroll
-            for (int w = 0; w < NCW; ++w) {                                   // all loads first, then the arithmetic
-              const bool on = w < mg_nws;
-              mw[w] = on ? pp0[w * 68 + 64 + mg_hh * 2] : -INFINITY;
-              lw_[w] = on ? pp0[w * 68 + 64 + mg_hh * 2 + 1] : 0.f;
-              ow[w] = on ? pp0[w * 68 + mg_f] : 0.f;
+            for (int k = 0; k < NCW; ++k) {                                   // all loads first, then the arithmetic
+              const int w = pair + k * n_pairs;
+              const bool on = w < NCW;
+              const float* pp = part + (on ? w : 0) * 68;
+              mw[k] = on ? pp[64] : -INFINITY;
+              lw_[k] = on ? pp[65] : 0.f;
+              ow[k] = on ? pp[mg_d] : 0.f;
             }
             float M = mw[0];
 #pragma unroll
-            for (int w = 1; w < NCW; ++w) M = fmaxf(M, mw[w]);
+            for (int k = 1; k < NCW; ++k) M = fmaxf(M, mw[k]);
             float Lsum = 0.f, o = 0.f;
 #pragma unroll
-            for (int w = 0; w < NCW; ++w) {
-              const float fw = exp2f(mw[w] - M);                            // exp2(-inf) = 0 for an idle worker
-              Lsum = fmaf(lw_[w], fw, Lsum);
-              o = fmaf(ow[w], fw, o);
+            for (int k = 0; k < NCW; ++k) {
+              const float fw = exp2f(mw[k] - M);                            // exp2(-inf) = 0 for an idle worker
+              Lsum = fmaf(lw_[k], fw, Lsum);
+              o = fmaf(ow[k], fw, o);
             }
             attb[mg_s * AP + mg_f] = __float2bfloat16_rn(__fdividef(o, Lsum));
           }
@@ -762,23 +817,28 @@ decode_mega_kernel(const MegaParams p) {
             float acc[2][4];
             gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc, tr);
             if (fs < S) {
+              const int lr0 = pr * 256 + cw * 32 + frow;                     // row inside the slice: lr0 + 16 t + 8 h8
 #pragma unroll
               for (int t = 0; t < 2; ++t)
 #pragma unroll
                 for (int h8 = 0; h8 < 2; ++h8) {
-                  const int lr = pr * 256 + cw * 32 + t * 16 + frow + h8 * 8;   // row inside the slice
-                  const int vr = v_lo + lr;
-                  const bool ok = vr < v_hi;
+                  const int lr = lr0 + t * 16 + h8 * 8;
+                  const bool ok = v_lo + lr < v_hi;
 #pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-                    const int s = fs + e;
-                    if (s < S) {
-                      const float lg = acc[t][h8 * 2 + e] + hbv[t][h8];
-                      logits[s * NL + lr] = ok ? lg / sp.temperature : -INFINITY;
-                      if (p.dbg_logits && ok) p.dbg_logits[(static_cast<size_t>(step) * p.B + b0 + s) * p.V + vr] = lg;
-                    }
-                  }
+                  for (int e = 0; e < 2; ++e)
+                    if (fs + e < S) logits[(fs + e) * NL + lr] = ok ? (acc[t][h8 * 2 + e] + hbv[t][h8]) * inv_temp : -INFINITY;
                 }
+              if (p.dbg_logits) {                                            // parity / debug path only (mg_step_logits)
+                float* dl = p.dbg_logits + (static_cast<size_t>(step) * p.B + b0 + fs) * p.V + v_lo + lr0;
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                  for (int h8 = 0; h8 < 2; ++h8)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                      if (fs + e < S && v_lo + lr0 + t * 16 + h8 * 8 < v_hi)
+                        dl[static_cast<size_t>(e) * p.V + t * 16 + h8 * 8] = acc[t][h8 * 2 + e] + hbv[t][h8];
+              }
             }
           }
         }
@@ -1134,7 +1194,31 @@ __global__ void mega_pack_kernel(PackSrc src, uint4* __restrict__ dst, int n_lay
   }
 }
 
+// K / V cache rows written by the prefill ([B][4][Tmax][64]) -> the caches of the persistent kernel:
+//   kh [B][4][head][Tmax][hd]            (head-major rows)
+//   vt [B][4][head][Tvt / 32][hd][32]    (per 32-key block transposed, key 8j + 2t + e at position 8t + 2j + e)
+__global__ void mega_relayout_kv_kernel(const MegaLayer* __restrict__ layers, const int32_t* __restrict__ lens, int Tmax, int Tvt, int hd) {
+  const int bs = blockIdx.x, l = blockIdx.y;                 // (sequence, slice), layer
+  const int len = lens[bs / CL];
+  const bf16* ksrc = layers[l].kc + static_cast<size_t>(bs) * Tmax * FS;
+  const bf16* vsrc = layers[l].vc + static_cast<size_t>(bs) * Tmax * FS;
+  bf16* kdst = layers[l].kh + static_cast<size_t>(bs) * Tmax * FS;
+  bf16* vdst = layers[l].vt + static_cast<size_t>(bs) * Tvt * FS;
+  for (int i = threadIdx.x; i < len * FS; i += blockDim.x) {
+    const int t = i >> 6, f = i & 63, h = f / hd, d = f - h * hd, ki = t & 31;
+    const int pos = 8 * ((ki >> 1) & 3) + 2 * (ki >> 3) + (ki & 1);
+    kdst[(static_cast<size_t>(h) * Tmax + t) * hd + d] = ksrc[i];
+    vdst[(static_cast<size_t>(h) * (Tvt >> 5) + (t >> 5)) * (hd * 32) + d * 32 + pos] = vsrc[i];
+  }
+}
+
 }  // namespace
+
+int mega_relayout_kv(cudaStream_t stream, const MegaLayer* layers, const int32_t* lens, int B, int n_layer, int Tmax, int Tvt, int hd) {
+  mega_relayout_kv_kernel<<<dim3(B * CL, n_layer), 256, 0, stream>>>(layers, lens, Tmax, Tvt, hd);
+  MG_LAUNCH_CHECK();
+  return MG_OK;
+}
 
 int mega_smem_bytes(int smax) {
   return (smax <= 2 ? Smem<2, kMegaStages2>::kTotal : Smem<4, kMegaStages4>::kTotal) + 1024;
@@ -1155,11 +1239,20 @@ int mega_pack_weights(cudaStream_t stream, const bf16* const* w_in, const bf16* 
   return MG_OK;
 }
 
+template <typename F>
+static auto mega_dispatch(int smax, int hd, F&& f) {
+  if (smax <= 2) return hd == 32 ? f(decode_mega_kernel<2, kMegaStages2, 32>) : f(decode_mega_kernel<2, kMegaStages2, 64>);
+  return hd == 32 ? f(decode_mega_kernel<4, kMegaStages4, 32>) : f(decode_mega_kernel<4, kMegaStages4, 64>);
+}
+
 int mega_init() {
-  MG_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<2, kMegaStages2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  mega_smem_bytes(2)));
-  MG_CUDA_OK(cudaFuncSetAttribute(decode_mega_kernel<4, kMegaStages4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  mega_smem_bytes(4)));
+  for (int smax : {2, 4})
+    for (int hd : {32, 64}) {
+      const cudaError_t e = mega_dispatch(smax, hd, [&](auto* k) {
+        return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, mega_smem_bytes(smax));
+      });
+      MG_CUDA_OK(e);
+    }
   return MG_OK;
 }
 
@@ -1174,17 +1267,19 @@ int mega_max_clusters(int smax) {
   cfg.attrs = &at;
   cfg.numAttrs = 1;
   int n = 0;
-  cudaError_t e = smax <= 2 ? cudaOccupancyMaxActiveClusters(&n, decode_mega_kernel<2, kMegaStages2>, &cfg)
-                            : cudaOccupancyMaxActiveClusters(&n, decode_mega_kernel<4, kMegaStages4>, &cfg);
+  const cudaError_t e = mega_dispatch(smax, 32, [&](auto* k) { return cudaOccupancyMaxActiveClusters(&n, k, &cfg); });
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 
 int launch_decode_mega(cudaStream_t stream, const MegaParams& p, int n_clusters) {
   const int smax = p.S <= 2 ? 2 : 4;
+  if (p.head_dim != 32 && p.head_dim != 64) return MG_E_SHAPE;
   dim3 grid(n_clusters * CL);
-  if (smax == 2) decode_mega_kernel<2, kMegaStages2><<<grid, NTHREADS, mega_smem_bytes(2), stream>>>(p);
-  else decode_mega_kernel<4, kMegaStages4><<<grid, NTHREADS, mega_smem_bytes(4), stream>>>(p);
+  mega_dispatch(smax, p.head_dim, [&](auto* k) {
+    k<<<grid, NTHREADS, mega_smem_bytes(smax), stream>>>(p);
+    return cudaSuccess;
+  });
   MG_LAUNCH_CHECK();
   return MG_OK;
 }

@@ -24,7 +24,9 @@ constexpr int kMegaMaxSeqPerCluster = 4;
 
 struct MegaLayer {
   const float *b_in, *b_out, *b1, *b2, *ln1w, *ln1b, *ln2w, *ln2b;
-  bf16 *kc, *vc;                      // cache slices [B][4][Tmax][64]
+  bf16 *kc, *vc;                      // cache slices [B][4][Tmax][64], written by the prefill
+  bf16 *kh, *vt;                      // caches of the persistent kernel: K head-major [B][4][head][Tmax][hd],
+                                      // V per 32-key block transposed [B][4][head][Tvt / 32][hd][32] (see attn_tc)
 };
 
 struct MegaParams {
@@ -37,6 +39,7 @@ struct MegaParams {
   DecodeState st;
   int n_layer, head_dim, V, VS, NP;   // VS = ceil(V / 4) vocabulary rows per CTA, NP = ceil(VS / 256) tile pairs
   int B, S, Tmax, n_steps;            // S = sequences per cluster
+  int Tvt;                            // keys per (sequence, head) of the V cache: Tmax rounded up to 32
   int early_exit;                     // EOS enabled: a cluster stops as soon as all of its sequences have finished
   // parity/debug (mg_step_logits): raw logits [n_steps][B][V] and teacher-forced next tokens [B][forced_stride]
   float* dbg_logits;
@@ -53,6 +56,7 @@ int mega_init();
 size_t mega_packed_bytes(int n_layer, int NP);
 int mega_pack_weights(cudaStream_t stream, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1,
                       const bf16* const* w2, const bf16* head, int n_layer, int V, int VS, int NP, void* dst);
+int mega_relayout_kv(cudaStream_t stream, const MegaLayer* layers, const int32_t* lens, int B, int n_layer, int Tmax, int Tvt, int hd);
 int mega_max_clusters(int smax);      // co-resident clusters (0 when the query fails)
 int launch_decode_mega(cudaStream_t stream, const MegaParams& p, int n_clusters);
 

@@ -46,6 +46,7 @@ struct LayerW {
   float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
   WMaps m_in, m_out, m_w1, m_w2;
   void *kc = nullptr, *vc = nullptr;
+  void *kh = nullptr, *vt = nullptr;                   // head-major K / block-transposed V caches (persistent decode kernel only)
 };
 
 struct mg_engine {
@@ -344,6 +345,8 @@ int forward_nocache(mg_engine* e, int B, int Tcap, int max_len_now) {
 }
 
 // ---- persistent cluster decode kernel: eligibility, tables, launch ------------------------------
+static int mega_tvt(int max_seq) { return (max_seq + 31) / 32 * 32; }
+
 int setup_mega(mg_engine* e) {
   const mg_geometry& g = e->geo;
   e->mega_ok = false;
@@ -365,8 +368,16 @@ int setup_mega(mg_engine* e) {
     LayerW& w = e->layers[l];
     w_in[l] = reinterpret_cast<const bf16*>(w.w_in); w_out[l] = reinterpret_cast<const bf16*>(w.w_out);
     w1[l] = reinterpret_cast<const bf16*>(w.w1); w2[l] = reinterpret_cast<const bf16*>(w.w2);
+    if (!w.vt) {
+      // zero-filled once so that V entries beyond a sequence's length are always finite (they meet probability 0)
+      const size_t vt_bytes = sizeof(bf16) * static_cast<size_t>(e->max_batch) * g.d_model * mega_tvt(e->max_seq);
+      MG_TRY(e->dmalloc(&w.vt, vt_bytes));
+      MG_CUDA_OK(cudaMemsetAsync(w.vt, 0, vt_bytes, e->stream));
+      MG_TRY(e->dmalloc(&w.kh, sizeof(bf16) * static_cast<size_t>(e->max_batch) * g.d_model * e->max_seq));
+    }
     lay[l] = mega::MegaLayer{w.b_in, w.b_out, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
-                             reinterpret_cast<bf16*>(w.kc), reinterpret_cast<bf16*>(w.vc)};
+                             reinterpret_cast<bf16*>(w.kc), reinterpret_cast<bf16*>(w.vc), reinterpret_cast<bf16*>(w.kh),
+                             reinterpret_cast<bf16*>(w.vt)};
   }
   if (!e->d_mega_packed) {
     MG_TRY(e->dmalloc(&e->d_mega_packed, mega::mega_packed_bytes(L, NP)));
@@ -399,7 +410,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   p.head_b = e->head_b; p.sp = e->d_sp; p.st = e->st;
   p.n_layer = g.n_layer; p.head_dim = g.d_model / g.n_head; p.V = g.vocab_size;
   p.VS = ceil_div(g.vocab_size, mega::kMegaCluster); p.NP = ceil_div(p.VS, 256);
-  p.B = B; p.S = S; p.Tmax = e->max_seq; p.n_steps = e->cur_steps;
+  p.B = B; p.S = S; p.Tmax = e->max_seq; p.n_steps = e->cur_steps; p.Tvt = mega_tvt(e->max_seq);
   p.dbg_logits = dbg_logits; p.forced = forced; p.forced_stride = forced_stride;
   p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
   p.prof = nullptr; p.prof_step = -1;
@@ -412,7 +423,8 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
       p.prof = e->d_prof; p.prof_step = std::atoi(ps);
     }
   }
-  *rc = mega::launch_decode_mega(e->stream, p, n_clusters);
+  *rc = mega::mega_relayout_kv(e->stream, e->d_mega_layers, e->st.lens, B, g.n_layer, e->max_seq, p.Tvt, p.head_dim);
+  if (*rc == MG_OK) *rc = mega::launch_decode_mega(e->stream, p, n_clusters);
   if (p.prof && *rc == MG_OK) {
     unsigned long long h[128];
     cudaStreamSynchronize(e->stream);
