@@ -64,7 +64,7 @@ constexpr int KMAX = kMegaMaxTopK;     // top_k limit of the in-kernel sampler
 constexpr int kCandCap = 128;          // per-sequence superset capacity of the sampler's fast path
 constexpr float kLog2e = 1.4426950408889634f;
 
-enum { BAR_COMPUTE = 1, BAR_EPI = 2 };
+enum { BAR_COMPUTE = 1, BAR_EPI = 2, BAR_STAGE_FREE = 8 };   // BAR_STAGE_FREE + ring stage: "every compute warp has read it"
 // per-layer parameter block kept in shared memory for the whole generation (floats):
 //   ln1w 256 | ln1b 256 | ln2w 256 | ln2b 256 | b_q 64 | b_k 64 | b_v 64 | b_out 256 | b1 slice 256 | b2 256
 constexpr int kLayerParamFloats = 4 * 256 + 3 * 64 + 3 * 256;
@@ -106,7 +106,10 @@ struct MiscSmem {
   int go;
   int sel[4][4];                      // per sequence: remaining, gathered count, radix prefix, exact flag
   bf16* kvp[kMegaMaxLayersSmem][2];   // K / V cache base of every layer (the MegaLayer table lives in global memory)
+  int wtot[4][8];                     // sampler: per-warp candidate counts of a sequence's group
 };
+
+static_assert(sizeof(MiscSmem) <= 512, "MiscSmem outgrew its shared-memory slot");
 
 struct Bars {
   uint64_t full[16];
@@ -171,61 +174,101 @@ struct RingPos {
   }
 };
 
+// A-operand (weight) fragments of one stage for this warp: 2 m16 tiles x 4 k-steps, double-buffered across stages.
+struct WFrag {
+  uint32_t a[2][2][4][4];
+  uint32_t off[2][4];             // fragment offsets inside a stage (the same for every stage)
+  RingPos ld;                     // next stage to load (runs ahead of the release position)
+  int dbg;                        // timing experiments: 1 = skip ldmatrix, 2 = skip the MMAs (results are garbage)
+};
+__device__ __forceinline__ void wfrag_init(WFrag& wf, int cw, int lane) {
+  // ldmatrix row address of this lane: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, k chunk (m >> 1)
+  const int lrow = ((lane >> 3) & 1) * 8 + (lane & 7), lchunk = lane >> 4;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = cw * 32 + t * 16 + lrow;                     // stage row 0..255
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      wf.off[t][ks] = (i >> 7) * (STAGE_BYTES / 2) + (i & 127) * 128 + (((ks * 2 + lchunk) ^ (i & 7)) << 4);
+  }
+}
+template <int NSTAGE>
+__device__ __forceinline__ void wfrag_load(WFrag& wf, int buf, uint32_t ring_addr, uint64_t* full, bool active) {
+  ptx::mbar_wait(&full[wf.ld.stage], wf.ld.phase);
+  if (active && !(wf.dbg & 1)) {
+    const uint32_t sbase = ring_addr + wf.ld.stage * STAGE_BYTES;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(sbase + wf.off[t][ks], wf.a[buf][t][ks]);
+  }
+  wf.ld.template advance<NSTAGE>();
+}
+
 // One GEMM "pair": NKB stages of [256 weight rows x 64 K]; this warp owns weight rows [32 cw, 32 cw + 32)
 // (two m16 tiles) and accumulates D[16 rows x 8 sequences] per tile over the stages.
 //   act   : activations bf16 [8][pitch] (row = sequence), K contiguous
 //   acc   : [2][4] fp32, thread holds rows (lane/4, lane/4 + 8) x sequences ((lane%4)*2, +1) of each tile
-template <int NKB, int NSTAGE>
-__device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_t* empty, RingPos& rp, const bf16* act,
-                                          int pitch, int cw, int lane, bool active, float (&acc)[2][4],
-                                          unsigned long long*& tr) {
-  uint32_t breg[NKB * 4][2];
-  {
-    const bf16* bp = act + (lane >> 2) * pitch + (lane & 3) * 2;
+// Explicit software pipeline: the eight ldmatrix of stage kb + 1 are issued BEFORE the eight MMAs of stage kb, so the
+// shared-memory pipe (256 cycles per 32 KB stage for the whole CTA) and the tensor pipe overlap even though the mbarrier
+// waits / arrives pin the instruction order (measured: 275 instead of 390-510 cycles per stage, tools/microbench/mb3.cu).
+// PRE: buffer 0 already holds the first stage (loaded by the previous call); preload_next: the first stage of the NEXT GEMM
+// is loaded into buffer 0 during the last stage (NKB even) -- the head chains its tile pairs this way.
+template <int NKB, int NSTAGE, bool PRE = false>
+__device__ __forceinline__ void gemm_pair(uint8_t* ring, uint64_t* full, uint64_t* empty, RingPos& rp, WFrag& wf, const bf16* act,
+                                          int pitch, int lane, bool active, bool preload_next, bool next_active,
+                                          float (&acc)[2][4], unsigned long long*& tr) {
+  const uint32_t ring_addr = ptx::smem_u32(ring);
+  const bf16* bp = act + (lane >> 2) * pitch + (lane & 3) * 2;   // B fragments: sequence lane / 4, k = (lane % 4) * 2 + {0, 1, 8, 9}
+  uint32_t bq[2][4][2];
+  auto load_b = [&](int buf, int kb) {
 #pragma unroll
-    for (int ks = 0; ks < NKB * 4; ++ks) {
-      breg[ks][0] = *reinterpret_cast<const uint32_t*>(bp + ks * 16);
-      breg[ks][1] = *reinterpret_cast<const uint32_t*>(bp + ks * 16 + 8);
+    for (int ks = 0; ks < 4; ++ks) {
+      bq[buf][ks][0] = *reinterpret_cast<const uint32_t*>(bp + (kb * 4 + ks) * 16);
+      bq[buf][ks][1] = *reinterpret_cast<const uint32_t*>(bp + (kb * 4 + ks) * 16 + 8);
     }
-  }
+  };
   float acc2[2][4];                                        // odd k-steps: halves the dependent MMA chains
 #pragma unroll
   for (int t = 0; t < 2; ++t)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { acc[t][e] = 0.f; acc2[t][e] = 0.f; }
-  // ldmatrix row address of this lane: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, k chunk (m >> 1)
-  const int lrow = ((lane >> 3) & 1) * 8 + (lane & 7);
-  const int lchunk = lane >> 4;
+  load_b(0, 0);
+  if (!PRE) { wf.ld = rp; wfrag_load<NSTAGE>(wf, 0, ring_addr, full, active); }
+  MG_TR(tr);
 #pragma unroll
   for (int kb = 0; kb < NKB; ++kb) {
-    ptx::mbar_wait(&full[rp.stage], rp.phase);
-    MG_TR(tr);
-    if (active) {
-      const uint32_t sbase = ptx::smem_u32(ring + rp.stage * STAGE_BYTES);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int i = cw * 32 + t * 16 + lrow;                 // stage row 0..255
-        const uint32_t rbase = sbase + (i >> 7) * (STAGE_BYTES / 2) + (i & 127) * 128;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t a[4];
-          ldmatrix_x4(rbase + (((ks * 2 + lchunk) ^ (i & 7)) << 4), a);
-          if (ks & 1) mma_bf16_16816(acc2[t], a, breg[kb * 4 + ks][0], breg[kb * 4 + ks][1]);
-          else mma_bf16_16816(acc[t], a, breg[kb * 4 + ks][0], breg[kb * 4 + ks][1]);
-        }
-      }
+    if (kb + 1 < NKB) {
+      load_b((kb + 1) & 1, kb + 1);
+      wfrag_load<NSTAGE>(wf, (kb + 1) & 1, ring_addr, full, active);
+    } else if (preload_next) {
+      wfrag_load<NSTAGE>(wf, (kb + 1) & 1, ring_addr, full, next_active);
     }
+    if (active && !(wf.dbg & 2)) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (ks & 1) mma_bf16_16816(acc2[t], wf.a[kb & 1][t][ks], bq[kb & 1][ks][0], bq[kb & 1][ks][1]);
+          else mma_bf16_16816(acc[t], wf.a[kb & 1][t][ks], bq[kb & 1][ks][0], bq[kb & 1][ks][1]);
+        }
+    }
+    // stage kb is free: its ldmatrix have returned (the MMAs above were issued).  A named barrier is the cheap way to tell the
+    // producer warp (92 vs 235 cycles per hand-off for an 8-arrival mbarrier, tools/microbench/mb5.cu)
+#ifndef MG_MEGA_MBAR_RELEASE
+    ptx::named_bar_arrive(BAR_STAGE_FREE + rp.stage, NCT + 32);
+#else
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&empty[rp.stage]);
+#endif
     rp.template advance<NSTAGE>();
+    MG_TR(tr);
   }
 #pragma unroll
   for (int t = 0; t < 2; ++t)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[t][e] += acc2[t][e];
-  MG_TR(tr);
 }
-
 
 __device__ __forceinline__ uint4 ldg_stream16(const bf16* p) { return ptx::ld_global_stream16(p); }
 
@@ -242,10 +285,29 @@ __device__ __forceinline__ uint4 ldg_stream16(const bf16* p) { return ptx::ld_gl
 // The contraction index of an MMA may be permuted freely as long as A and B agree, which is what makes 16-byte loads work.
 // Only row 0 (lanes 0..3) carries data; the other 15 rows of the m16 tile are idle -- the tensor pipe has nothing else to do.
 // kh: K rows of this (sequence, head) [T][HD], vt: V blocks of this (sequence, head) [T / 32][HD][32], q: fp32, log2-scaled.
+// 16-byte loads of one 32-key block (see attn_tc): K rows 8 j + g, V^T rows 8 n + g
 template <int HD>
+__device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int b, int lane,
+                                                uint4 (&kq)[4][HD / 32], uint4 (&vq)[HD / 8]) {
+  const int g = lane >> 2, t = lane & 3, key0 = b << 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = min(key0 + 8 * j + g, len - 1);            // rows past the end are masked in attn_tc; never read them
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) kq[j][c] = ldg_stream16(kh + static_cast<size_t>(row) * HD + 32 * c + 8 * t);
+  }
+  const bf16* vb = vt + static_cast<size_t>(b) * (HD * 32) + g * 32 + 8 * t;
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) vq[n] = ldg_stream16(vb + n * 256);
+}
+
+// kq0 / vq0: block `wi` of this worker, loaded by the caller ahead of time (before the QKV GEMM, whose result the loads do not
+// depend on) when PRE is set.
+template <int HD, bool PRE>
 __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int wi, int nws,
                                         int lane, const float* __restrict__ q, const bf16* __restrict__ knew,
-                                        const bf16* __restrict__ vnew, bool fold_new, float* __restrict__ out) {
+                                        const bf16* __restrict__ vnew, bool fold_new, float* __restrict__ out,
+                                        uint4 (&kq0)[4][HD / 32], uint4 (&vq0)[HD / 8]) {
   constexpr int KS = HD / 16;              // k-steps of the score MMAs
   constexpr int NT = HD / 8;               // n-tiles (8 dims) of the output MMAs
   constexpr int KL = HD / 32;              // 16-byte K loads per lane per key row
@@ -272,20 +334,7 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
   float m_run = -INFINITY, l_run = 0.f;   // l_run: this lane's share of the denominator (summed over the quad at the end)
 
   const int nblk = (len + 31) >> 5;
-  const bf16* kl = kh + 8 * t;
-  const bf16* vl = vt + g * 32 + 8 * t;                         // + block * HD * 32 + n * 256
-  auto load_block = [&](int b, uint4 (&kq)[4][KL], uint4 (&vq)[NT]) {
-    const int key0 = b << 5;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int row = min(key0 + 8 * j + g, len - 1);          // rows past the end are masked below; never read them
-#pragma unroll
-      for (int c = 0; c < KL; ++c) kq[j][c] = ldg_stream16(kl + static_cast<size_t>(row) * HD + 32 * c);
-    }
-    const bf16* vb = vl + static_cast<size_t>(b) * (HD * 32);
-#pragma unroll
-    for (int n = 0; n < NT; ++n) vq[n] = ldg_stream16(vb + n * 256);
-  };
+  auto load_block = [&](int b, uint4 (&kq)[4][KL], uint4 (&vq)[NT]) { attn_load_block<HD>(kh, vt, len, b, lane, kq, vq); };
   auto compute_block = [&](int b, const uint4 (&kq)[4][KL], const uint4 (&vq)[NT]) {
     const int key0 = b << 5;
     float sc[4][2];
@@ -333,24 +382,23 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
   };
   if (HD == 32) {
     // two register sets: the loads of the next block are in flight while this one is computed
-    uint4 kqa[4][KL], vqa[NT], kqb[4][KL], vqb[NT];
+    uint4 kqb[4][KL], vqb[NT];
     int b = wi;
-    if (b < nblk) load_block(b, kqa, vqa);
+    if (!PRE && b < nblk) load_block(b, kq0, vq0);
     while (b < nblk) {
       const int b1 = b + nws;
       if (b1 < nblk) load_block(b1, kqb, vqb);
-      compute_block(b, kqa, vqa);
+      compute_block(b, kq0, vq0);
       if (b1 >= nblk) break;
       const int b2 = b1 + nws;
-      if (b2 < nblk) load_block(b2, kqa, vqa);
+      if (b2 < nblk) load_block(b2, kq0, vq0);
       compute_block(b1, kqb, vqb);
       b = b2;
     }
   } else {
-    uint4 kqa[4][KL], vqa[NT];
     for (int b = wi; b < nblk; b += nws) {
-      load_block(b, kqa, vqa);
-      compute_block(b, kqa, vqa);
+      if (!(PRE && b == wi)) load_block(b, kq0, vq0);
+      compute_block(b, kq0, vq0);
     }
   }
   // the new token's own row (the reference's cache already contains it, api_cache.py:66-68): first worker only
@@ -466,26 +514,42 @@ decode_mega_kernel(const MegaParams p) {
     if (warp < NPW) {
       // =========================== bulk-copy producer warpgroup ===========================
       ptx::setmaxnreg_dec<40>();
-      if (warp == 0 && lane == 0) {
+      if (warp == 0) {
+        // warp 0: all lanes take part in the named-barrier waits, lane 0 issues the copies
         RingPos rp;
         const int stages_per_step = n_layer * kMegaStagesPerLayer + 4 * p.NP;
         const uint8_t* src0 = p.packed + static_cast<size_t>(rank) * stages_per_step * STAGE_BYTES;
+        int issued = 0;
         for (int step = 0; step < n_steps; ++step) {
           if (p.early_exit && step > 0) {                     // do not stream weights for a step that will not run
             ptx::mbar_wait(&bars.step_go, (step - 1) & 1);
             if (*reinterpret_cast<volatile int*>(&misc.go) == 0) break;
           }
           const uint8_t* src = src0;
-          for (int i = 0; i < stages_per_step; ++i, src += STAGE_BYTES) {
+          for (int i = 0; i < stages_per_step; ++i, src += STAGE_BYTES, ++issued) {
+#ifndef MG_MEGA_MBAR_RELEASE
+            if (issued >= NSTAGE) ptx::named_bar_sync(BAR_STAGE_FREE + rp.stage, NCT + 32);
+#else
             ptx::mbar_wait(&bars.empty[rp.stage], rp.phase ^ 1);
-            if (p.dbg_skip_loads) {
-              ptx::mbar_arrive(&bars.full[rp.stage]);
-            } else {
-              ptx::mbar_arrive_expect_tx(&bars.full[rp.stage], STAGE_BYTES);
-              ptx::bulk_load_1d(smem + L::kRing + rp.stage * STAGE_BYTES, src, STAGE_BYTES, &bars.full[rp.stage]);
+#endif
+            if (lane == 0) {
+              if (p.dbg_skip_loads) {
+                ptx::mbar_arrive(&bars.full[rp.stage]);
+              } else {
+                ptx::mbar_arrive_expect_tx(&bars.full[rp.stage], STAGE_BYTES);
+                ptx::bulk_load_1d(smem + L::kRing + rp.stage * STAGE_BYTES, src, STAGE_BYTES, &bars.full[rp.stage]);
+              }
             }
             rp.template advance<NSTAGE>();
           }
+        }
+        // match the compute warps' arrivals for the last stages (no refill follows)
+#ifdef MG_MEGA_MBAR_RELEASE
+        issued = 0;
+#endif
+        for (int i = 0; i < NSTAGE && i < issued; ++i) {
+          ptx::named_bar_sync(BAR_STAGE_FREE + rp.stage, NCT + 32);
+          rp.template advance<NSTAGE>();
         }
       }
       __syncwarp();
@@ -496,6 +560,10 @@ decode_mega_kernel(const MegaParams p) {
       const int ct = threadIdx.x - NPW * 32;                 // 0..255
       uint32_t xuse = 0;
       RingPos rp;
+      WFrag wf;
+      wfrag_init(wf, cw, lane);
+      wf.dbg = p.dbg_attn_hot;
+      if (wf.dbg) for (int i = 0; i < 64; ++i) (&wf.a[0][0][0][0])[i] = 0u;
       const SampleParams sp = *p.sp;
       const float scale_log2 = kLog2e / sqrtf(static_cast<float>(hd));
       const float inv_temp = 1.0f / sp.temperature;          // logits / temperature (api_cache.py:169) as one multiply
@@ -647,6 +715,22 @@ decode_mega_kernel(const MegaParams p) {
           tr = (prof_on && step == p.prof_step && l == 1) ? p.prof + 64 : nullptr;
 #endif
           fst();                                                            // t0: layer start
+          // ---- attention prefetch: this warp's first 32-key block does not depend on this step's q / k / v ----
+#ifdef MG_MEGA_NO_ATTN_PRE
+          constexpr bool kAttnPre = false;
+#else
+          constexpr bool kAttnPre = HD == 32;
+#endif
+          uint4 kq0[4][HD / 32], vq0[HD / 8];
+          const size_t kv_seq = static_cast<size_t>(CL) * p.Tmax * FS;       // K cache elements per sequence
+          const size_t vt_seq = static_cast<size_t>(CL) * p.Tvt * FS;        // V cache elements per sequence
+          bf16* const kbase = misc.kvp[l][0] + (static_cast<size_t>(b0) * CL + r) * p.Tmax * FS;   // [head][T][hd]
+          bf16* const vbase = misc.kvp[l][1] + (static_cast<size_t>(b0) * CL + r) * p.Tvt * FS;    // [head][T / 32][hd][32]
+          const int at_s = att_pair >> nh_shift, at_h = att_pair & ((1 << nh_shift) - 1);
+          const int at_len = misc.fin[at_s] ? 0 : misc.len[at_s];
+          const bf16* at_kh = kbase + at_s * kv_seq + static_cast<size_t>(at_h) * p.Tmax * hd;
+          const bf16* at_vt = vbase + at_s * vt_seq + static_cast<size_t>(at_h) * p.Tvt * hd;
+          if (kAttnPre && (att_wi << 5) < at_len) attn_load_block<HD>(at_kh, at_vt, at_len, att_wi, lane, kq0, vq0);
           // ---- QKV (LN1 was applied by the previous epilogue): stage rows 0..63 = q, 64..127 = k, 128..191 = v slice ----
           if (cw < GW) {
             const int part_id = cw >> 1;                      // 0 = q, 1 = k, 2 = v
@@ -657,7 +741,7 @@ decode_mega_kernel(const MegaParams p) {
               for (int h8 = 0; h8 < 2; ++h8)
                 qb[t][h8] = cw < 6 ? pl[P_BQKV + part_id * FS + (cw & 1) * 32 + t * 16 + frow + h8 * 8] : 0.f;
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, cw < 6, acc, tr);
+            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, cw < 6, false, false, acc, tr);
             if (cw < 6 && fs < S) {
 #pragma unroll
               for (int t = 0; t < 2; ++t)
@@ -682,10 +766,6 @@ decode_mega_kernel(const MegaParams p) {
           bar_compute();
           stamp(step);                                                      // +1: QKV done
           // ---- append the new K row / V^T column (api_cache.py:66-67) + flash-decoding over this CTA's slice ----
-          const size_t kv_seq = static_cast<size_t>(CL) * p.Tmax * FS;       // K cache elements per sequence
-          const size_t vt_seq = static_cast<size_t>(CL) * p.Tvt * FS;        // V cache elements per sequence
-          bf16* const kbase = misc.kvp[l][0] + (static_cast<size_t>(b0) * CL + r) * p.Tmax * FS;   // [head][T][hd]
-          bf16* const vbase = misc.kvp[l][1] + (static_cast<size_t>(b0) * CL + r) * p.Tvt * FS;    // [head][T / 32][hd][32]
           if (cw < S && lane < 8 && !misc.fin[cw]) {
             const int s = cw, c = lane, h = (8 * c) >> hd_shift, d0 = (8 * c) & (hd - 1);
             bf16* dst = kbase + s * kv_seq + (static_cast<size_t>(h) * p.Tmax + misc.len[s]) * hd + d0;
@@ -702,13 +782,9 @@ decode_mega_kernel(const MegaParams p) {
           fst();                                                            // append + prefetch issued
           {
             // warp cw is the att_wi-th worker of (sequence, head) pair att_pair
-            const int s = att_pair >> nh_shift, h = att_pair & ((1 << nh_shift) - 1);
-            const int len = misc.fin[s] ? 0 : misc.len[s];
-            const bf16* kh = kbase + s * kv_seq + static_cast<size_t>(h) * p.Tmax * hd;
-            const bf16* vt = vbase + s * vt_seq + static_cast<size_t>(h) * p.Tvt * hd;
-            float* out = part + cw * 68;
-            attn_tc<HD>(kh, vt, len, att_wi, att_nws, lane, qs + s * FS + h * HD, knew + s * FS + h * HD, vnew + s * FS + h * HD,
-                        att_wi == 0, out);
+            const int s = at_s, h = at_h;
+            attn_tc<HD, kAttnPre>(at_kh, at_vt, at_len, att_wi, att_nws, lane, qs + s * FS + h * HD, knew + s * FS + h * HD,
+                                  vnew + s * FS + h * HD, att_wi == 0, part + cw * 68, kq0, vq0);
           }
           fst();                                                            // attention stream done (this warp)
           bar_compute();
@@ -745,7 +821,7 @@ decode_mega_kernel(const MegaParams p) {
           // ---- out_proj (row-parallel over this CTA's 64 attention features) -> exchange -> x += attn ----
           if (cw < GW) {
             float acc[2][4];
-            gemm_pair<1, NSTAGE>(ring, bars.full, bars.empty, rp, attb, AP, cw, lane, true, acc, tr);
+            gemm_pair<1, NSTAGE>(ring, bars.full, bars.empty, rp, wf, attb, AP, lane, true, false, false, acc, tr);
             exchange_send(acc);
           }
           fst();                                                            // out_proj sent
@@ -755,7 +831,7 @@ decode_mega_kernel(const MegaParams p) {
           // ---- MLP1 (+GELU, this CTA's 256 hidden units) -> MLP2 (row-parallel) -> exchange ----
           if (cw < GW) {
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc, tr);
+            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, true, false, false, acc, tr);
             // bias + exact-erf GELU: the valid accumulators sit in quad lanes 0 .. SMAX/2-1 (two sequences each); spread
             // them over the four lanes of the quad so that every lane evaluates erff for 2 (SMAX = 2) or 4 values
             {
@@ -789,7 +865,7 @@ decode_mega_kernel(const MegaParams p) {
           stamp(step);                                                      // +4: MLP1 done
           if (cw < GW) {
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, hb, XP, cw, lane, true, acc, tr);
+            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, wf, hb, XP, lane, true, false, false, acc, tr);
             exchange_send(acc);
           }
           fst();                                                            // mlp.2 sent
@@ -805,7 +881,7 @@ decode_mega_kernel(const MegaParams p) {
         // ---- head: logits of this CTA's vocabulary slice ----
         {
           const int v_lo = r * p.VS, v_hi = min(p.V, (r + 1) * p.VS);
-          for (int pr = 0; pr < p.NP && cw < GW; ++pr) {
+          auto head_pair = [&](int pr, bool first) {
             float hbv[2][2];                                   // head bias of this thread's 4 rows, loaded ahead of the MMAs
 #pragma unroll
             for (int t = 0; t < 2; ++t)
@@ -815,7 +891,8 @@ decode_mega_kernel(const MegaParams p) {
                 hbv[t][h8] = vr < v_hi ? __ldg(p.head_b + vr) : 0.f;
               }
             float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, xb, XP, cw, lane, true, acc, tr);
+            if (first) gemm_pair<4, NSTAGE, false>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, true, pr + 1 < p.NP, true, acc, tr);
+            else gemm_pair<4, NSTAGE, true>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, true, pr + 1 < p.NP, true, acc, tr);
             if (fs < S) {
               const int lr0 = pr * 256 + cw * 32 + frow;                     // row inside the slice: lr0 + 16 t + 8 h8
 #pragma unroll
@@ -840,6 +917,10 @@ decode_mega_kernel(const MegaParams p) {
                         dl[static_cast<size_t>(e) * p.V + t * 16 + h8 * 8] = acc[t][h8 * 2 + e] + hbv[t][h8];
               }
             }
+          };
+          if (cw < GW) {
+            head_pair(0, true);
+            for (int pr = 1; pr < p.NP; ++pr) head_pair(pr, false);
           }
         }
         bar_compute();
@@ -870,28 +951,44 @@ decode_mega_kernel(const MegaParams p) {
             float m_t = -INFINITY;
             for (int i = gt; i < NL; i += gn) m_t = fmaxf(m_t, z[i]);
             maxima[gt] = m_t;
-            if (gt == 0) { *g_cnt = 0; *g_exact = 0; }
+            if (gt == 0) *g_exact = 0;
             ptx::named_bar_sync(gbar, gn);
             int rk = 0;
-#pragma unroll 4
-            for (int u = 0; u < gn; ++u) {
-              const float mu = maxima[u];
-              rk += (mu > m_t) || (mu == m_t && u < gt);
+            for (int u = 0; u < gn; u += 4) {
+              const float4 mu = *reinterpret_cast<const float4*>(maxima + u);
+              rk += (mu.x > m_t) || (mu.x == m_t && u < gt);
+              rk += (mu.y > m_t) || (mu.y == m_t && u + 1 < gt);
+              rk += (mu.z > m_t) || (mu.z == m_t && u + 2 < gt);
+              rk += (mu.w > m_t) || (mu.w == m_t && u + 3 < gt);
             }
             if (rk == k - 1) *reinterpret_cast<volatile float*>(g_pre) = m_t;
             ptx::named_bar_sync(gbar, gn);
             const float tau = *reinterpret_cast<volatile float*>(g_pre);
-            for (int i0 = 0; i0 < NL; i0 += gn) {
-              const int i = i0 + gt;
-              const float zi = i < NL ? z[i] : -INFINITY;
-              const bool take = i < NL && zi >= tau;
-              const unsigned bal = __ballot_sync(0xffffffffu, take);
-              int base_pos = 0;
-              if (lane == 0 && bal) base_pos = atomicAdd(const_cast<int*>(g_cnt), __popc(bal));
-              base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
-              const int pos = base_pos + __popc(bal & ((1u << lane) - 1));
-              if (take && pos < kCandCap) clist[pos] = make_uint2(__float_as_uint(zi), static_cast<uint32_t>(r * p.VS + i));
+            // gather everything >= tau without atomics: per-thread count, warp scan, warp totals through shared memory
+            int cnt = 0;
+            for (int i = gt; i < NL; i += gn) cnt += z[i] >= tau ? 1 : 0;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int up = __shfl_up_sync(0xffffffffu, inc, o);
+              if (lane >= o) inc += up;
             }
+            if (lane == 31) misc.wtot[s][wi] = inc;
+            ptx::named_bar_sync(gbar, gn);
+            int pos = inc - cnt, total = 0;
+            for (int w = 0; w < nws; ++w) {
+              const int wt = misc.wtot[s][w];
+              pos += w < wi ? wt : 0;
+              total += wt;
+            }
+            for (int i = gt; i < NL; i += gn) {
+              const float zi = z[i];
+              if (zi >= tau) {
+                if (pos < kCandCap) clist[pos] = make_uint2(__float_as_uint(zi), static_cast<uint32_t>(r * p.VS + i));
+                ++pos;
+              }
+            }
+            if (gt == 0) *g_cnt = total;
             ptx::named_bar_sync(gbar, gn);
             const int c = *g_cnt;
             overflow = c > kCandCap || c < k;

@@ -190,6 +190,67 @@ __global__ void __launch_bounds__(288) stage_kernel(long long* out, float* sink,
           if (ks & 1) mma(acc2[t], a, b0, b1); else mma(acc[t], a, b0, b1);
         }
     }
+  } else if (mode == 3 || mode == 4) {   // mode 0 + the kernel's per-stage synchronisation (try_wait on a completed phase, syncwarp, arrive)
+    __shared__ uint64_t fullb[4], emptyb[4];
+    if (threadIdx.x == 0) for (int i = 0; i < 4; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&fullb[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&emptyb[i])));
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullb[i])) : "memory");
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    t0 = clock64();
+    const int per = mode == 3 ? 1 : 4;          // stages per synchronisation
+#pragma unroll 1
+    for (int st0 = 0; st0 < 16; st0 += per) {
+      for (int q = 0; q < per; ++q) while (!try_wait(&fullb[(st0 + q) & 3], 0)) {}
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q >= per) break;
+        const uint32_t sb = base + ((st0 + q) & 3) * 32768;
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[4];
+            ldsm(sb + foff[t][ks], a);
+            if (ks & 1) mma(acc2[t], a, b0, b1); else mma(acc[t], a, b0, b1);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) for (int q = 0; q < per; ++q) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&emptyb[(st0 + q) & 3])) : "memory");
+    }
+  } else if (mode == 5) {   // explicit software pipeline: ldmatrix of stage i + 1 before the MMAs of stage i, per-stage sync kept
+    __shared__ uint64_t fullb[4], emptyb[4];
+    if (threadIdx.x == 0) for (int i = 0; i < 4; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&fullb[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&emptyb[i])));
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullb[i])) : "memory");
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    t0 = clock64();
+    uint32_t fa[2][2][4][4];
+    while (!try_wait(&fullb[0], 0)) {}
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm(base + foff[t][ks], fa[0][t][ks]);
+#pragma unroll
+    for (int st = 0; st < 16; ++st) {
+      if (st + 1 < 16) {
+        while (!try_wait(&fullb[(st + 1) & 3], 0)) {}
+        const uint32_t sb = base + ((st + 1) & 3) * 32768;
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ldsm(sb + foff[t][ks], fa[(st + 1) & 1][t][ks]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { if (ks & 1) mma(acc2[t], fa[st & 1][t][ks], b0, b1); else mma(acc[t], fa[st & 1][t][ks], b0, b1); }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&emptyb[st & 3])) : "memory");
+    }
   } else if (mode == 1) {   // LDSM only
     uint32_t x = 0;
 #pragma unroll 4
@@ -262,9 +323,9 @@ int main() {
   printf("LDS dependent x16: %lld -> %.1f each\n", h[9], h[9] / 16.0);
   printf("erff x8: %lld -> %.1f each; exp2f+sub x8: %lld -> %.1f each\n", h[10], h[10] / 8.0, h[11], h[11] / 8.0);
   CK(cudaFuncSetAttribute(stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768));
-  for (int rep = 0; rep < 2; ++rep) for (int mode = 0; mode < 3; ++mode) { stage_kernel<<<1, 288, 4 * 32768>>>(out, sink, mode); CK(cudaDeviceSynchronize()); }
-  CK(cudaMemcpy(h, out, 3 * 8, cudaMemcpyDeviceToHost));
-  printf("GEMM stage body, 8 warps, 16 stages: LDSM+HMMA %.1f cyc/stage, LDSM only %.1f, HMMA only %.1f\n", h[0] / 16.0, h[1] / 16.0, h[2] / 16.0);
+  for (int rep = 0; rep < 2; ++rep) for (int mode = 0; mode < 6; ++mode) { stage_kernel<<<1, 288, 4 * 32768>>>(out, sink, mode); CK(cudaDeviceSynchronize()); }
+  CK(cudaMemcpy(h, out, 6 * 8, cudaMemcpyDeviceToHost));
+  printf("GEMM stage body, 8 warps, 16 stages: LDSM+HMMA %.1f cyc/stage, LDSM only %.1f, HMMA only %.1f, with per-stage mbarrier sync %.1f, sync per 4 stages %.1f, explicit pipeline + per-stage sync %.1f\n", h[0] / 16.0, h[1] / 16.0, h[2] / 16.0, h[3] / 16.0, h[4] / 16.0, h[5] / 16.0);
   CK(cudaMemset(out, 0, 64 * 8));
   pingpong_kernel<<<4, 32>>>(out, 1000); CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost));
