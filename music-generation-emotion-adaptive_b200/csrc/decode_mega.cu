@@ -381,19 +381,29 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
     }
   };
   if (HD == 32) {
-    // two register sets: the loads of the next block are in flight while this one is computed
-    uint4 kqb[4][KL], vqb[NT];
+    // MG_ATTN_BUFS register sets: the loads of the next block(s) are in flight while this one is computed (bytes in flight per
+    // SM = warps x sets x 4 KB).  Measured on B200 (same box, config 3 / config 4): 2 sets 78.8 ms / 80.7 us per step, 3 sets
+    // 83.9 / 85.8, 4 sets 106.9 / 109.7 -- with more sets the loads of different sets end up on the same scoreboard and a
+    // wait for the oldest set waits for all of them, so two is the useful depth of a register pipeline.
+#ifndef MG_ATTN_BUFS
+#define MG_ATTN_BUFS 2
+#endif
+    constexpr int NB = MG_ATTN_BUFS;
+    uint4 kqx[NB - 1][4][KL], vqx[NB - 1][NT];
     int b = wi;
     if (!PRE && b < nblk) load_block(b, kq0, vq0);
+#pragma unroll
+    for (int i = 1; i < NB; ++i)
+      if (b + i * nws < nblk) load_block(b + i * nws, kqx[i - 1], vqx[i - 1]);
     while (b < nblk) {
-      const int b1 = b + nws;
-      if (b1 < nblk) load_block(b1, kqb, vqb);
-      compute_block(b, kq0, vq0);
-      if (b1 >= nblk) break;
-      const int b2 = b1 + nws;
-      if (b2 < nblk) load_block(b2, kq0, vq0);
-      compute_block(b1, kqb, vqb);
-      b = b2;
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        if (b >= nblk) break;
+        if (i == 0) compute_block(b, kq0, vq0); else compute_block(b, kqx[i - 1], vqx[i - 1]);
+        const int bn = b + NB * nws;                         // refill the set that was just consumed
+        if (bn < nblk) { if (i == 0) load_block(bn, kq0, vq0); else load_block(bn, kqx[i - 1], vqx[i - 1]); }
+        b += nws;
+      }
     }
   } else {
     for (int b = wi; b < nblk; b += nws) {
@@ -509,6 +519,13 @@ decode_mega_kernel(const MegaParams p) {
   ptx::cluster_arrive();
   ptx::cluster_wait();
   const int n_steps = p.n_steps;
+  // optional start offset per cluster group: de-synchronises the clusters' phases (weight streaming from L2 vs K/V streaming
+  // from HBM are different shared resources; clusters that run in lock-step hit each of them all at once)
+  if (p.stagger_groups > 1 && p.stagger_ns > 0) {
+    const uint64_t wait_ns = static_cast<uint64_t>(cluster % p.stagger_groups) * static_cast<uint64_t>(p.stagger_ns);
+    const uint64_t t_start = ptx::global_timer_ns();
+    while (ptx::global_timer_ns() - t_start < wait_ns) {}
+  }
 
   if (S > 0) {
     if (warp < NPW) {

@@ -48,6 +48,7 @@ struct MegaParams {
   // optional phase timeline of one step (globaltimer ns), written by cluster 0 / CTA 0: [64] entries
   unsigned long long* prof;
   int prof_step;
+  int stagger_groups, stagger_ns;     // start offset (cluster % groups) * ns: phase de-synchronisation of the clusters
   int dbg_attn_hot;                   // timing experiment only: attention reads the same 32 cache rows over and over
   int dbg_skip_loads;                 // timing experiment only: signal the stages without copying (results are garbage)
 };

@@ -12,7 +12,7 @@ for rep in 1 2; do
   i=0
   for flags in "$@"; do
     cp /tmp/lib_$i.so $LIB; i=$((i+1))
-    echo "[$flags] $(MG_MEGA_PROF_STEP=40 timeout 120 python tools/profile_step.py 1024 64 2>&1 | grep 'prof\] step\|profile_step' | sed 's/.mega prof. step 40 .ns since first stamp.://' | cut -c1-230)"
+    echo "[$flags] c3: $(timeout 120 python tools/profile_step.py 1024 64 2>&1 | grep 'profile_step' | cut -c20-110) | c4: $(timeout 120 python tools/profile_long.py 2048 2>&1 | grep profile_long | sed 's/.*us.step/us\/step/')"
   done
 done
 touch music-generation-emotion-adaptive_b200/csrc/decode_mega.cu
