@@ -392,6 +392,36 @@ def test_persistent_kernel_logits_match_multikernel_path_and_oracle(geo_name, B)
     multi.close()
 
 
+@pytest.mark.parametrize("geo_name,lens", [("train_large_pos512", [31, 32, 33, 64, 95, 130, 200, 256]),
+                                           ("train_large_pos512", [97, 120]),
+                                           ("train_large_pos512", [20 + (7 * i) % 230 for i in range(40)]),   # 2 per cluster
+                                           ("train_large_pos512", [20 + (11 * i) % 230 for i in range(70)]),  # 3 per cluster
+                                           ("train_large_pos512", [20 + (13 * i) % 230 for i in range(120)]), # 4 per cluster
+                                           ("train_mini", [30, 65, 127, 190]),
+                                           ("train_mini", [25 + (9 * i) % 200 for i in range(50)])])
+def test_persistent_kernel_long_caches_cross_block_boundaries(geo_name, lens):
+    """The tensor-core flash-decoding of the persistent kernel works on 32-key blocks of re-laid-out caches (head-major K,
+    block-transposed V) split over several warps: long, ragged prompts whose caches cross 32-key block boundaries during
+    40 teacher-forced steps (1, 2 and 4 sequences per cluster, head_dim 32 and 64) against the fp64 reference run."""
+    geo = mg.GEOMETRIES[geo_name]
+    ck = checkpoint(geo_name, 0)
+    rng = np.random.default_rng(7)
+    prompts = [rng.integers(0, geo.vocab_size, n).tolist() for n in lens]
+    n = 40
+    forced = rng.integers(0, geo.vocab_size, (len(lens), n)).astype(np.int32)
+    mega = _engine_with_env(geo_name, 0, {}, max_batch=128, max_seq=320)
+    l0 = mega.stats()["kernel_launches"]
+    a = mega.step_logits(prompts, forced, n)
+    assert mega.stats()["kernel_launches"] - l0 < 140          # prefill kernels + re-layout + ONE decode launch
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head, torch.float64)
+    rows = range(len(lens)) if len(lens) <= 8 else sorted({0, 1, len(lens) // 3, len(lens) // 2, len(lens) - 2, len(lens) - 1})
+    for row in rows:
+        want = gpt_kv.teacher_forced_logits(ora, prompts[row], forced[row].tolist(), n).numpy()
+        err = np.max(np.abs(a[:, row, :] - want), axis=1)
+        assert float(err.max()) < 6e-2, (row, lens[row], err)
+    mega.close()
+
+
 def test_persistent_kernel_ragged_max_new_eos_and_fallbacks():
     geo = mg.GEOMETRIES["train_large"]
     ck = checkpoint("train_large", 0)

@@ -114,3 +114,19 @@ def test_pipeline_prompt_building_uses_the_service_order():
     p = mg.build_prompt(v, prm["bpm"], prm["key"], prm["all_families"])
     assert p[0] == "[START_SEQUENCE]" and p[1].startswith("[BPM]") and p[2].startswith("[KEY_SIGNATURE]")
     assert all(t in v for t in p) and 3 <= len(p) <= 6
+
+
+def test_transposed_v_block_layout_matches_the_mma_fragments():
+    """The persistent kernel stores V per 32-key block as [dim][32 positions] with key 8j + 2t + e at position
+    8t + 2j + e (csrc/decode_mega.cu, attn_tc / mega_relayout_kv_kernel).  Restated here: the map is a bijection, lane t
+    of the score MMAs (keys 8j + 2t + {0, 1} of MMA j) ends up owning positions [8t, 8t + 8) -- the 16 bytes it loads for
+    the P.V MMAs -- and the two k-steps of that MMA pair (positions 8t + 4u + {0..3}) see keys of score MMAs 2u, 2u + 1."""
+    def pos_of(key):                      # as in the kernels
+        return 8 * ((key >> 1) & 3) + 2 * (key >> 3) + (key & 1)
+    assert sorted(pos_of(k) for k in range(32)) == list(range(32))
+    for t in range(4):
+        owned = sorted(pos_of(8 * j + 2 * t + e) for j in range(4) for e in range(2))
+        assert owned == list(range(8 * t, 8 * t + 8))
+        for u in range(2):
+            keys = [8 * j + 2 * t + e for j in (2 * u, 2 * u + 1) for e in range(2)]
+            assert sorted(pos_of(k) for k in keys) == list(range(8 * t + 4 * u, 8 * t + 4 * u + 4))
