@@ -693,11 +693,33 @@ encoder_attn_tc_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__
   const size_t ld = static_cast<size_t>(3) * d;
   const bf16* base = qkv + static_cast<size_t>(start) * ld + h * HD;
 
-  for (int i = threadIdx.x; i < 64 * CPR; i += 128) {
-    const int r = i / CPR, c = i - r * CPR;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q0 + r < len) v = *reinterpret_cast<const uint4*>(base + (q0 + r) * ld + c * 8);
-    *reinterpret_cast<uint4*>(Qs + r * P + c * 8) = v;
+  // Q tile and the first K / V tile are requested together: one global round trip instead of two (T <= 64 in the classifier,
+  // so this is the only tile and the CTA's lifetime is dominated by that latency)
+  {
+    constexpr int NI = 64 * CPR / 128;
+    uint4 qv[NI], kv[NI], vv[NI];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int i = threadIdx.x + j * 128, r = i / CPR, c = i - r * CPR;
+      qv[j] = kv[j] = vv[j] = make_uint4(0, 0, 0, 0);
+      if (q0 + r < len) qv[j] = *reinterpret_cast<const uint4*>(base + (q0 + r) * ld + c * 8);
+      if (r < len) {
+        const bf16* pk = base + r * ld + c * 8;
+        kv[j] = *reinterpret_cast<const uint4*>(pk + d);
+        vv[j] = *reinterpret_cast<const uint4*>(pk + 2 * d);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int i = threadIdx.x + j * 128, r = i / CPR, c = i - r * CPR;
+      *reinterpret_cast<uint4*>(Qs + r * P + c * 8) = qv[j];
+      *reinterpret_cast<uint4*>(Ks + r * P + c * 8) = kv[j];
+      *reinterpret_cast<uint4*>(Vs + r * P + c * 8) = vv[j];
+    }
+    if (threadIdx.x < 64) {
+      const int kr = threadIdx.x;
+      Kbias[threadIdx.x] = (kr < len && (key_mask == nullptr || key_mask[start + kr] != 0)) ? 0.f : -INFINITY;
+    }
   }
   __syncthreads();
   const int mi = lane >> 3;
@@ -714,23 +736,25 @@ encoder_attn_tc_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};   // rows lane/4 and lane/4 + 8 (per-thread partial sums)
 
   for (int k0 = 0; k0 < len; k0 += 64) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * CPR; i += 128) {
-      const int r = i / CPR, c = i - r * CPR;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (k0 + r < len) {
-        const bf16* pk = base + (k0 + r) * ld + c * 8;
-        kv = *reinterpret_cast<const uint4*>(pk + d);
-        vv = *reinterpret_cast<const uint4*>(pk + 2 * d);
+    if (k0 > 0) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 64 * CPR; i += 128) {
+        const int r = i / CPR, c = i - r * CPR;
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (k0 + r < len) {
+          const bf16* pk = base + (k0 + r) * ld + c * 8;
+          kv = *reinterpret_cast<const uint4*>(pk + d);
+          vv = *reinterpret_cast<const uint4*>(pk + 2 * d);
+        }
+        *reinterpret_cast<uint4*>(Ks + r * P + c * 8) = kv;
+        *reinterpret_cast<uint4*>(Vs + r * P + c * 8) = vv;
       }
-      *reinterpret_cast<uint4*>(Ks + r * P + c * 8) = kv;
-      *reinterpret_cast<uint4*>(Vs + r * P + c * 8) = vv;
+      if (threadIdx.x < 64) {
+        const int kr = k0 + threadIdx.x;
+        Kbias[threadIdx.x] = (kr < len && (key_mask == nullptr || key_mask[start + kr] != 0)) ? 0.f : -INFINITY;
+      }
+      __syncthreads();
     }
-    if (threadIdx.x < 64) {
-      const int kr = k0 + threadIdx.x;
-      Kbias[threadIdx.x] = (kr < len && (key_mask == nullptr || key_mask[start + kr] != 0)) ? 0.f : -INFINITY;
-    }
-    __syncthreads();
 
     float s[8][4];
 #pragma unroll
