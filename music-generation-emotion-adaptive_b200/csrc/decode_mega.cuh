@@ -18,7 +18,10 @@ constexpr int kMegaStageBytes = 32768;
 constexpr int kMegaStagesPerLayer = 13;   // in_proj 4 + out_proj 1 + mlp.0 4 + mlp.2 4 stages of 32 KB
 constexpr int kMegaMaxLayers = 8;
 constexpr int kMegaMaxLayersSmem = 4;  // layers whose LN / bias parameters are kept in shared memory
-constexpr int kMegaStages2 = 4;       // ring depth (32 KB stages) when <= 2 sequences per cluster
+#ifndef MG_MEGA_STAGES2
+#define MG_MEGA_STAGES2 4
+#endif
+constexpr int kMegaStages2 = MG_MEGA_STAGES2;       // ring depth (32 KB stages) when <= 2 sequences per cluster
 constexpr int kMegaStages4 = 2;       // ... when 3..4 sequences per cluster
 constexpr int kMegaMaxSeqPerCluster = 4;
 
