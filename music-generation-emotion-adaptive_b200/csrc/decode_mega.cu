@@ -964,7 +964,32 @@ decode_mega_kernel(const MegaParams p) {
           float* maxima = reinterpret_cast<float*>(gh);        // [gn] (the radix histogram's storage)
           uint2* clist = reinterpret_cast<uint2*>(part) + s * kCandCap;
           bool overflow = k > gn;
-          if (!overflow) {
+          if (k == 1) {
+            // greedy (the reference expresses it as top_k = 1): arg-max of the slice, value descending / index ascending
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int i = gt; i < NL; i += gn) {
+              const float zi = z[i];
+              if (zi > bv) { bv = zi; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) clist[wi] = make_uint2(__float_as_uint(bv), static_cast<uint32_t>(bi));
+            ptx::named_bar_sync(gbar, gn);
+            if (gt == 0) {
+              for (int w = 1; w < nws; ++w) {
+                const uint2 o = clist[w];
+                const float ov = __uint_as_float(o.x);
+                if (ov > bv || (ov == bv && static_cast<int>(o.y) < bi)) { bv = ov; bi = static_cast<int>(o.y); }
+              }
+              gl[0] = make_uint2(__float_as_uint(bv), static_cast<uint32_t>(r * p.VS + bi));
+            }
+            overflow = false;
+          } else if (!overflow) {
             float m_t = -INFINITY;
             for (int i = gt; i < NL; i += gn) m_t = fmaxf(m_t, z[i]);
             maxima[gt] = m_t;
@@ -1141,53 +1166,72 @@ decode_mega_kernel(const MegaParams p) {
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.cand, (CL - 1) * k * 8);
           ptx::mbar_wait(&bars.cand, cand_use & 1);
           ++cand_use;
-          bar_compute();
-          // every CTA's list arrives sorted (value descending, index ascending): the global rank of an entry is
-          // its own position plus, for each other list, the number of entries that precede it (binary search)
-          const int n = CL * k;                               // <= 256 candidates, one per thread
-          uint2 mine = make_uint2(0, 0);
-          int rk = 0;
-          if (ct < n) {
-            const int src = ct / k, j = ct - src * k;
-            mine = cand[src * KMAX + j];
-            const float mv = __uint_as_float(mine.x);
-            rk = j;
-            for (int si = 0; si < CL; ++si) {
-              if (si == src) continue;
-              const uint2* lst = cand + si * KMAX;
-              int lo = 0, hi = k;                             // first position whose entry does NOT precede `mine`
-              while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const uint2 o = lst[mid];
-                const float ov = __uint_as_float(o.x);
-                const bool before = (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && si < src)));
-                if (before) lo = mid + 1; else hi = mid;
+          int tok = 0;
+          if (k == 1) {
+            // greedy: the best of the CL slice maxima (the local one became visible at the barrier above)
+            if (cw == 0) {
+              const uint2 e = cand[(lane < CL ? lane : 0) * KMAX];
+              float bv = lane < CL ? __uint_as_float(e.x) : -INFINITY;
+              int bi = lane < CL ? static_cast<int>(e.y) : 0x7fffffff;
+#pragma unroll
+              for (int o = 2; o; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
               }
-              rk += lo;
+              tok = __shfl_sync(0xffffffffu, bi, 0);
+            }
+          } else {
+            bar_compute();
+            // every CTA's list arrives sorted (value descending, index ascending): the global rank of an entry is
+            // its own position plus, for each other list, the number of entries that precede it (binary search)
+            const int n = CL * k;                               // <= 256 candidates, one per thread
+            uint2 mine = make_uint2(0, 0);
+            int rk = 0;
+            if (ct < n) {
+              const int src = ct / k, j = ct - src * k;
+              mine = cand[src * KMAX + j];
+              const float mv = __uint_as_float(mine.x);
+              rk = j;
+              for (int si = 0; si < CL; ++si) {
+                if (si == src) continue;
+                const uint2* lst = cand + si * KMAX;
+                int lo = 0, hi = k;                             // first position whose entry does NOT precede `mine`
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  const uint2 o = lst[mid];
+                  const float ov = __uint_as_float(o.x);
+                  const bool before = (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && si < src)));
+                  if (before) lo = mid + 1; else hi = mid;
+                }
+                rk += lo;
+              }
+            }
+            uint2* sorted = local_list + SMAX * KMAX;           // [KMAX] behind the per-sequence local lists
+            if (ct < n && rk < k) sorted[rk] = mine;            // value descending, index ascending
+            bar_compute();
+            if (cw == 0) {
+              const float v0 = __uint_as_float(sorted[0].x);
+              float w0 = lane < k ? expf(__uint_as_float(sorted[lane].x) - v0) : 0.f;
+              float w1 = lane + 32 < k ? expf(__uint_as_float(sorted[lane + 32].x) - v0) : 0.f;
+              float i0 = w0, i1 = w1;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const float t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= o) { i0 += t0; i1 += t1; }
+              }
+              const float tot0 = __shfl_sync(0xffffffffu, i0, 31);
+              i1 += tot0;
+              const float total = __shfl_sync(0xffffffffu, i1, 31);
+              const float u01 = philox_uniform(sp.seed, sp.seq_base + static_cast<uint64_t>(b0 + s), static_cast<uint32_t>(misc.nnew[s]));
+              const float target = u01 * total;
+              const unsigned c0 = __ballot_sync(0xffffffffu, lane < k && i0 > target);
+              const unsigned c1 = __ballot_sync(0xffffffffu, lane + 32 < k && i1 > target);
+              const int pick = c0 ? __ffs(c0) - 1 : (c1 ? 32 + __ffs(c1) - 1 : k - 1);
+              tok = static_cast<int>(sorted[pick].y);
             }
           }
-          uint2* sorted = local_list + SMAX * KMAX;           // [KMAX] behind the per-sequence local lists
-          if (ct < n && rk < k) sorted[rk] = mine;            // value descending, index ascending
-          bar_compute();
           if (cw == 0) {
-            const float v0 = __uint_as_float(sorted[0].x);
-            float w0 = lane < k ? expf(__uint_as_float(sorted[lane].x) - v0) : 0.f;
-            float w1 = lane + 32 < k ? expf(__uint_as_float(sorted[lane + 32].x) - v0) : 0.f;
-            float i0 = w0, i1 = w1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const float t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-              if (lane >= o) { i0 += t0; i1 += t1; }
-            }
-            const float tot0 = __shfl_sync(0xffffffffu, i0, 31);
-            i1 += tot0;
-            const float total = __shfl_sync(0xffffffffu, i1, 31);
-            const float u01 = philox_uniform(sp.seed, sp.seq_base + static_cast<uint64_t>(b0 + s), static_cast<uint32_t>(misc.nnew[s]));
-            const float target = u01 * total;
-            const unsigned c0 = __ballot_sync(0xffffffffu, lane < k && i0 > target);
-            const unsigned c1 = __ballot_sync(0xffffffffu, lane + 32 < k && i1 > target);
-            const int pick = c0 ? __ffs(c0) - 1 : (c1 ? 32 + __ffs(c1) - 1 : k - 1);
-            int tok = static_cast<int>(sorted[pick].y);
             if (p.forced) tok = p.forced[static_cast<size_t>(b0 + s) * p.forced_stride + step];
             tok = min(max(tok, 0), p.V - 1);                 // never index the embedding table out of range
             if (lane == 0) {
