@@ -11,23 +11,29 @@
 //     column-parallel -> row-parallel pairs, so a layer needs two exchanges only);
 //   * the weights were re-laid out at load time (mega_pack_weights) as the exact shared-memory image of
 //     every 32 KB stage [256 weight rows x 64 K, 128B-swizzled] in consumption order, so the producer warp
-//     streams them L2 -> shared memory with ONE cp.async.bulk per stage into an mbarrier ring;
+//     streams them L2 -> shared memory with ONE cp.async.bulk per stage into a 4-stage ring ("full" = mbarrier
+//     with complete_tx, "free" = named barrier: bar.arrive by the compute warps, bar.sync by the producer warp);
 //   * the contractions are warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 -> fp32) issued by all eight
 //     compute warps straight from the ring with ldmatrix (weights = the M = 16 operand, the cluster's <= 8
-//     sequences = the N = 8 operand).  A tcgen05/TMEM formulation of the same step (swap-AB, M = 128,
+//     sequences = the N = 8 operand), software-pipelined by hand (ldmatrix of stage i + 1 before the MMAs of
+//     stage i).  A tcgen05/TMEM formulation of the same step (swap-AB, M = 128,
 //     N = 16, single issuing thread) was built and measured first: at 2-4 sequences per cluster it is bound
 //     by instruction issue (~85 cycles per tcgen05.mma, 704 per step = 31 us) and by the commit -> mbarrier
 //     -> tcgen05.ld hand-offs (profiles/r1_mega_tcgen05_timeline.txt); tcgen05 stays where the contraction
 //     is dense (prefill, batched multi-kernel decode, the classifier: gemm_tc.cu);
 //   * row-parallel partial sums are all-gathered across the cluster with st.async (distributed shared
-//     memory writes that complete_tx on the receiver's mbarrier) and summed in a fixed order;
-//   * attention is flash-decoding over the CTA's own cache slice [b][slice][t][64]: 128-byte rows,
-//     four rows per warp load, 8 x 2 x 16 B in flight per lane, warp-shuffle softmax reductions;
-//   * sampling: every CTA radix-selects the top-k of its vocabulary slice, the candidates go to the
+//     memory writes that complete_tx on the receiver's mbarrier), summed in a fixed order, and the residual
+//     add + the NEXT LayerNorm are done by the same warp in the same phase;
+//   * attention is tensor-core flash-decoding straight from global memory over re-laid-out caches (K head-major,
+//     V transposed per 32-key block; see attn_tc): one warp per (sequence, head, key range), 16-byte loads,
+//     no shuffles between the score and the output MMAs, two register sets of loads in flight;
+//   * sampling: every CTA selects the top-k of its vocabulary slice (threshold from the per-thread maxima,
+//     atomic-free gather, radix-select fallback; arg-max fast path for top_k = 1), the candidates go to the
 //     sequence's owner CTA, which ranks them, draws with Philox and broadcasts the token.
 //
-// Warp roles (288 threads): warp 0 bulk-copy producer, warps 1..8 compute (LayerNorm, MMA, attention,
-// epilogues, exchange, sampler).
+// Warp roles (384 threads): a producer warpgroup (warp 0 streams the weights; setmaxnreg.dec) and two compute
+// warpgroups (LayerNorm, MMA, attention, epilogues, exchange, sampler; setmaxnreg.inc to 232 registers).
+// Where the time of a step goes, and what was measured and rejected: profiles/r1e_mega_timeline.txt.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -64,7 +70,8 @@ constexpr int KMAX = kMegaMaxTopK;     // top_k limit of the in-kernel sampler
 constexpr int kCandCap = 128;          // per-sequence superset capacity of the sampler's fast path
 constexpr float kLog2e = 1.4426950408889634f;
 
-enum { BAR_COMPUTE = 1, BAR_EPI = 2, BAR_STAGE_FREE = 8 };   // BAR_STAGE_FREE + ring stage: "every compute warp has read it"
+// named barriers: 1 = the compute warps, 3 + sequence = a sampler group, BAR_STAGE_FREE + ring stage = "every compute warp has read it"
+enum { BAR_COMPUTE = 1, BAR_STAGE_FREE = 8 };
 // per-layer parameter block kept in shared memory for the whole generation (floats):
 //   ln1w 256 | ln1b 256 | ln2w 256 | ln2b 256 | b_q 64 | b_k 64 | b_v 64 | b_out 256 | b1 slice 256 | b2 256
 constexpr int kLayerParamFloats = 4 * 256 + 3 * 64 + 3 * 256;
@@ -579,7 +586,7 @@ decode_mega_kernel(const MegaParams p) {
       RingPos rp;
       WFrag wf;
       wfrag_init(wf, cw, lane);
-      wf.dbg = p.dbg_attn_hot;
+      wf.dbg = p.dbg_gemm;
       if (wf.dbg) for (int i = 0; i < 64; ++i) (&wf.a[0][0][0][0])[i] = 0u;
       const SampleParams sp = *p.sp;
       const float scale_log2 = kLog2e / sqrtf(static_cast<float>(hd));

@@ -52,7 +52,7 @@ struct MegaParams {
   unsigned long long* prof;
   int prof_step;
   int stagger_groups, stagger_ns;     // start offset (cluster % groups) * ns: phase de-synchronisation of the clusters
-  int dbg_attn_hot;                   // timing experiment only: attention reads the same 32 cache rows over and over
+  int dbg_gemm;                       // timing experiment only: 1 = skip ldmatrix, 2 = skip the MMAs of the weight GEMMs (garbage results)
   int dbg_skip_loads;                 // timing experiment only: signal the stages without copying (results are garbage)
 };
 

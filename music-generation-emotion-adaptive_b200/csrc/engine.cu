@@ -417,7 +417,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   p.dbg_skip_loads = std::getenv("MG_MEGA_SKIP_LOADS") ? 1 : 0;
   p.stagger_groups = std::getenv("MG_MEGA_STAGGER_GROUPS") ? std::atoi(std::getenv("MG_MEGA_STAGGER_GROUPS")) : 0;
   p.stagger_ns = std::getenv("MG_MEGA_STAGGER_NS") ? std::atoi(std::getenv("MG_MEGA_STAGGER_NS")) : 0;
-  p.dbg_attn_hot = std::getenv("MG_MEGA_GEMM_DBG") ? std::atoi(std::getenv("MG_MEGA_GEMM_DBG")) : 0;
+  p.dbg_gemm = std::getenv("MG_MEGA_GEMM_DBG") ? std::atoi(std::getenv("MG_MEGA_GEMM_DBG")) : 0;
   if (const char* ps = std::getenv("MG_MEGA_PROF_STEP")) {       // debug: phase timeline of one decode step -> stderr
     if (!e->d_prof) { if (e->dmalloc(&e->d_prof, 128 * sizeof(unsigned long long)) != MG_OK) e->d_prof = nullptr; }
     if (e->d_prof) {
