@@ -1,0 +1,125 @@
+"""Request coalescing in front of ``Generator.generate``.
+
+The reference service handles one prompt per HTTP request; the endpoint is a sync ``def``, so Starlette runs concurrent
+requests on threadpool threads that all call ``sample_kvcache`` on the module-global model (api_cache.py:186-204).  The
+engine serialises calls (one mutex per engine), which turns N concurrent requests into N batch-1 runs.  ``RequestBatcher``
+puts a queue in between: requests that arrive within ``max_wait_ms`` of each other (or until ``max_batch`` are waiting) and
+share the sampling settings are decoded in ONE batched engine call -- row b of a batched call equals a batch-1 run on
+prompt b, so nothing changes for the caller except the latency / throughput trade-off.
+
+    batcher = RequestBatcher(model.engine, max_batch=64, max_wait_ms=2.0)
+    tokens = batcher.generate(prompt_ids, max_new_tokens, temperature, top_k, eos_id)     # blocking, thread-safe
+    ...
+    batcher.close()
+
+This is coalescing, not continuous batching: a batch runs to completion (the persistent decode kernel owns its sequences for
+the whole generation; a cluster stops early when all of its sequences have hit EOS) before the next one starts.
+"""
+from __future__ import annotations
+
+import itertools
+import threading
+import time
+from concurrent.futures import Future
+from typing import Dict, List, Optional, Sequence, Tuple
+
+
+class _Request:
+    __slots__ = ("prompt", "max_new", "key", "future", "t_submit")
+
+    def __init__(self, prompt, max_new, key, future):
+        self.prompt, self.max_new, self.key, self.future = prompt, max_new, key, future
+        self.t_submit = time.perf_counter()
+
+
+class RequestBatcher:
+    """Thread-safe front end: ``submit`` returns a Future, ``generate`` blocks.  One worker thread drives the engine."""
+
+    def __init__(self, engine, max_batch: int = 64, max_wait_ms: float = 2.0, seed: int = 0):
+        if max_batch < 1:
+            raise ValueError("max_batch must be positive")
+        self.engine, self.max_batch, self.max_wait = engine, int(max_batch), float(max_wait_ms) * 1e-3
+        self._seed = seed
+        self._cv = threading.Condition()
+        self._queue: List[_Request] = []
+        self._closed = False
+        self._seq = itertools.count()            # Philox sequence index base: no two requests ever share a stream
+        self.batches: List[int] = []             # sizes of the engine calls made so far (observability / tests)
+        self._worker = threading.Thread(target=self._run, name="mgea-batcher", daemon=True)
+        self._worker.start()
+
+    # -- caller side ----------------------------------------------------------------------------------
+    def submit(self, prompt_ids: Sequence[int], max_new_tokens: int, temperature: float = 1.0, top_k: Optional[int] = 50,
+               eos_id: int = -1) -> "Future[List[int]]":
+        fut: "Future[List[int]]" = Future()
+        req = _Request(list(prompt_ids), int(max_new_tokens), (float(temperature), top_k, int(eos_id)), fut)
+        with self._cv:
+            if self._closed:
+                raise RuntimeError("RequestBatcher is closed")
+            self._queue.append(req)
+            self._cv.notify_all()
+        return fut
+
+    def generate(self, prompt_ids: Sequence[int], max_new_tokens: int, temperature: float = 1.0,
+                 top_k: Optional[int] = 50, eos_id: int = -1) -> List[int]:
+        """Blocking call with the engine's exceptions re-raised in the calling thread."""
+        return self.submit(prompt_ids, max_new_tokens, temperature, top_k, eos_id).result()
+
+    def close(self) -> None:
+        with self._cv:
+            self._closed = True
+            self._cv.notify_all()
+        self._worker.join()
+
+    # -- worker -----------------------------------------------------------------------------------------
+    def _take_batch(self) -> Optional[Tuple[Tuple, List[_Request]]]:
+        """Waits for work, then for up to ``max_wait`` (counted from the oldest request) for more of the same kind."""
+        with self._cv:
+            while not self._queue and not self._closed:
+                self._cv.wait()
+            if not self._queue:
+                return None
+            key = self._queue[0].key
+            deadline = self._queue[0].t_submit + self.max_wait
+            while not self._closed:
+                same = sum(1 for r in self._queue if r.key == key)
+                left = deadline - time.perf_counter()
+                if same >= self.max_batch or left <= 0:
+                    break
+                self._cv.wait(timeout=left)
+            batch = [r for r in self._queue if r.key == key][:self.max_batch]
+            taken = set(map(id, batch))
+            self._queue = [r for r in self._queue if id(r) not in taken]
+            return key, batch
+
+    def _run(self) -> None:
+        while True:
+            item = self._take_batch()
+            if item is None:
+                return
+            (temperature, top_k, eos_id), batch = item
+            base = next(self._seq) * self.max_batch
+            try:
+                out = self.engine.generate([r.prompt for r in batch], [r.max_new for r in batch], temperature, top_k,
+                                           eos_id=eos_id, seed=self._seed, seq_index_base=base)
+                self.batches.append(len(batch))
+                for r, o in zip(batch, out):
+                    r.future.set_result(o)
+            except BaseException as e:                     # KeyError / RuntimeError / ValueError of the engine call
+                if len(batch) == 1:
+                    batch[0].future.set_exception(e)
+                else:
+                    # one bad request (e.g. a prompt longer than the position table) must not fail its neighbours
+                    for r in batch:
+                        try:
+                            o = self.engine.generate([r.prompt], [r.max_new], temperature, top_k, eos_id=eos_id,
+                                                     seed=self._seed, seq_index_base=base)[0]
+                            r.future.set_result(o)
+                        except BaseException as e1:
+                            r.future.set_exception(e1)
+                    self.batches.extend([1] * len(batch))
+
+
+def stats(batcher: RequestBatcher) -> Dict[str, float]:
+    n = len(batcher.batches)
+    return {"engine_calls": n, "requests": sum(batcher.batches), "mean_batch": (sum(batcher.batches) / n) if n else 0.0}

@@ -307,13 +307,20 @@ class KVModel:
     globals (``tok2id`` / ``id2tok``, api_cache.py:140-141)."""
 
     def __init__(self, ckpt: dict, n_head: int = 8, dtype: str = "fp32", max_batch: int = 1, max_seq: Optional[int] = None,
-                 device: int = 0):
+                 device: int = 0, coalesce_ms: Optional[float] = None):
+        """``coalesce_ms``: when set (and ``max_batch`` > 1), concurrent ``sample_kvcache`` calls -- the reference endpoint
+        runs on a threadpool, api_cache.py:186-187 -- that arrive within that many milliseconds are decoded as one batch
+        (``batcher.RequestBatcher``)."""
         self.tok2id: Dict[str, int] = ckpt["vocab"]
         self.id2tok = {i: t for t, i in self.tok2id.items()}
         pos_rows = int(ckpt["model"]["pos"].shape[0])
         self.seq_len = pos_rows                                 # SEQ_LEN of api_cache.py:36
         self.engine = Generator(ckpt["model"], n_head=n_head, dtype=dtype, max_batch=max_batch,
                                 max_seq=max_seq or max(2 * pos_rows, 1088), device=device)
+        self.batcher = None
+        if coalesce_ms is not None and max_batch > 1:
+            from .batcher import RequestBatcher
+            self.batcher = RequestBatcher(self.engine, max_batch=max_batch, max_wait_ms=coalesce_ms)
 
     def to(self, device):            # the reference calls model.to(device).eval() (api_cache.py:161)
         return self
@@ -328,7 +335,10 @@ def sample_kvcache(model: KVModel, prompt: Sequence[str], max_len: int = 512, te
     the engine already lives on its GPU).  Returns ALL tokens including the prompt, as strings."""
     ids = [model.tok2id[t] for t in prompt]                      # KeyError on OOV, like :162
     eos = model.tok2id.get("[END_SEQUENCE]", -1)                 # :181
-    out = model.engine.generate([ids], max_len - len(ids), temperature, top_k, eos_id=eos, seed=seed)[0]
+    if getattr(model, "batcher", None) is not None:             # coalesced with the other requests in flight
+        out = model.batcher.generate(ids, max_len - len(ids), temperature, top_k, eos)
+    else:
+        out = model.engine.generate([ids], max_len - len(ids), temperature, top_k, eos_id=eos, seed=seed)[0]
     return [model.id2tok[i] for i in out]
 
 

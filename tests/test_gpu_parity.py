@@ -276,6 +276,36 @@ def test_sample_kvcache_drop_in_string_api():
     model.engine.close()
 
 
+def test_concurrent_sample_kvcache_calls_are_coalesced_and_equal_batch1_runs():
+    """The reference endpoint runs on a threadpool (api_cache.py:186-187): 24 threads call the drop-in sample_kvcache at the
+    same time on one model; the request batcher decodes them in a few batched engine calls and every caller gets exactly the
+    tokens of a batch-1 run on its prompt (fp32 greedy: bit-identical)."""
+    import threading
+    ck = checkpoint("train_large", 0)
+    vocab = {("[EOS_DISABLED]" if t == "[END_SEQUENCE]" else t): i for t, i in ck["vocab"].items()}
+    model = mg.KVModel({"model": ck["model"], "vocab": vocab}, n_head=8, dtype="fp32", max_batch=16, max_seq=128,
+                       coalesce_ms=200.0)
+    prompts = mg.synthetic_prompts(ck["vocab"], 24, seed=11)
+    got = {}
+
+    def worker(i):
+        got[i] = mg.sample_kvcache(model, prompts[i], max_len=len(prompts[i]) + 12 + i % 3, temperature=1.0, top_k=1)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(24)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    calls = list(model.batcher.batches)
+    assert sum(calls) == 24 and len(calls) <= 6 and max(calls) <= 16, calls
+    for i in (0, 5, 11, 23):
+        ids = [vocab[t] for t in prompts[i]]
+        want = model.engine.generate([ids], 12 + i % 3, 1.0, 1)[0]
+        assert [vocab[t] for t in got[i]] == want, i
+    model.batcher.close()
+    model.engine.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # recompute mode: model (A), generate_music/generate.py
 # ---------------------------------------------------------------------------------------------------

@@ -130,3 +130,69 @@ def test_transposed_v_block_layout_matches_the_mma_fragments():
         for u in range(2):
             keys = [8 * j + 2 * t + e for j in (2 * u, 2 * u + 1) for e in range(2)]
             assert sorted(pos_of(k) for k in keys) == list(range(8 * t + 4 * u, 8 * t + 4 * u + 4))
+
+
+class _FakeEngine:
+    """Stands in for Generator on the CPU: row b = prompt b followed by max_new[b] copies of (sum(prompt) % 97)."""
+
+    def __init__(self, delay=0.01):
+        import threading
+        self.calls, self.delay, self.lock = [], delay, threading.Lock()
+
+    def generate(self, prompts, max_new, temperature=1.0, top_k=50, eos_id=-1, seed=0, seq_index_base=0):
+        import time
+        for p in prompts:
+            if len(p) > 8:
+                raise RuntimeError("prompt longer than the position table")
+        time.sleep(self.delay)
+        with self.lock:
+            self.calls.append((len(prompts), temperature, top_k, seq_index_base))
+        return [list(p) + [sum(p) % 97] * n for p, n in zip(prompts, max_new)]
+
+
+def test_request_batcher_coalesces_concurrent_requests_and_routes_results():
+    import threading
+    eng = _FakeEngine()
+    b = mg.RequestBatcher(eng, max_batch=8, max_wait_ms=50.0)
+    results = {}
+
+    def worker(i):
+        results[i] = b.generate([i, i + 1, 2], 3 + i % 4, 1.0, 50 if i % 5 else 7, -1)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(20)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    b.close()
+    for i in range(20):
+        assert results[i] == [i, i + 1, 2] + [(2 * i + 3) % 97] * (3 + i % 4)          # every caller got ITS row
+    assert sum(c[0] for c in eng.calls) == 20 and len(eng.calls) < 20                  # requests were coalesced ...
+    assert all(c[0] <= 8 for c in eng.calls)                                           # ... within max_batch ...
+    assert all(len({c[2]}) == 1 for c in eng.calls)                                    # ... one sampling setting per call
+    bases = [c[3] for c in eng.calls]
+    assert len(set(bases)) == len(bases)                                               # distinct Philox stream ranges
+
+
+def test_request_batcher_isolates_a_failing_request():
+    import threading
+    eng = _FakeEngine()
+    b = mg.RequestBatcher(eng, max_batch=4, max_wait_ms=100.0)
+    out, err = {}, {}
+
+    def worker(i, prompt):
+        try:
+            out[i] = b.generate(prompt, 2)
+        except RuntimeError as e:
+            err[i] = str(e)
+
+    threads = [threading.Thread(target=worker, args=(0, [1, 2])), threading.Thread(target=worker, args=(1, list(range(9)))),
+               threading.Thread(target=worker, args=(2, [5]))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    b.close()
+    assert out == {0: [1, 2, 3, 3], 2: [5, 5, 5]} and list(err) == [1] and "position table" in err[1]
+    with pytest.raises(RuntimeError):
+        b.submit([1], 1)
