@@ -12,7 +12,7 @@ for rep in 1 2; do
   i=0
   for flags in "$@"; do
     cp /tmp/lib_$i.so $LIB; i=$((i+1))
-    echo "[$flags] c3: $(MG_MEGA_PROF_STEP=40 timeout 120 python tools/profile_step.py 1024 64 2>&1 | grep 'prof\] step\|profile_step' | sed 's/.mega prof. step 40 .ns since first stamp.://' | cut -c1-200 | tr '\n' ' ') | $(timeout 100 python tools/profile_batch1.py 2>&1 | tail -1)"
+    echo "[$flags] c3: $(MG_MEGA_PROF_STEP=40 timeout 120 python tools/profile_step.py 1024 64 2>&1 | grep 'prof\] step\|profile_step' | sed 's/.mega prof. step 40 .ns since first stamp.://' | cut -c1-200 | tr '\n' ' ') | c4 $(timeout 120 python tools/profile_long.py 1024 2>&1 | grep profile_long | sed 's/.*us.step/us\/step/')"
   done
 done
 rm -rf music-generation-emotion-adaptive_b200/csrc/build; make -C music-generation-emotion-adaptive_b200/csrc -j8 > /dev/null 2>&1
