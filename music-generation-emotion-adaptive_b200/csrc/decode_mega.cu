@@ -114,6 +114,7 @@ struct MiscSmem {
   int sel[4][4];                      // per sequence: remaining, gathered count, radix prefix, exact flag
   bf16* kvp[kMegaMaxLayersSmem][2];   // K / V cache base of every layer (the MegaLayer table lives in global memory)
   int wtot[4][8];                     // sampler: per-warp candidate counts of a sequence's group
+  int outlen[8];                      // tokens written so far per sequence (owner CTA; global copy updated at the end)
 };
 
 static_assert(sizeof(MiscSmem) <= 512, "MiscSmem outgrew its shared-memory slot");
@@ -518,6 +519,7 @@ decode_mega_kernel(const MegaParams p) {
       misc.nnew[s] = live ? p.st.n_new[b0 + s] : 0;
       misc.maxnew[s] = live ? p.st.max_new[b0 + s] : 0;
       misc.fin[s] = live ? static_cast<int>(p.st.finished[b0 + s]) : 1;
+      misc.outlen[s] = live ? p.st.out_len[b0 + s] : 0;
     }
     for (int l = 0; l < n_layer; ++l) { misc.kvp[l][0] = p.layers[l].kh; misc.kvp[l][1] = p.layers[l].vt; }
   }
@@ -954,6 +956,10 @@ decode_mega_kernel(const MegaParams p) {
         // The compute warps are dealt to the sequences (warp cw -> sequence cw % S); each group radix-selects
         // the k largest logits of this CTA's vocabulary slice with warp-aggregated histogram updates.
         const int k = sp.top_k;
+#ifdef MG_MEGA_TRACE
+        tr = (prof_on && step == p.prof_step) ? p.prof + 96 : nullptr;
+#endif
+        fst();                                                              // sampler start
         if (cw < GW) {
           const int s = seq_of(cw), wi = worker_of(cw), nws = workers(s);        // GW == NCW
           const int gt = wi * 32 + lane, gn = nws * 32;       // thread index / count inside the group
@@ -997,25 +1003,58 @@ decode_mega_kernel(const MegaParams p) {
             }
             overflow = false;
           } else if (!overflow) {
-            float m_t = -INFINITY;
-            for (int i = gt; i < NL; i += gn) m_t = fmaxf(m_t, z[i]);
+            // every pass below keeps several independent shared-memory loads in flight (these loops are pure latency)
+            float m_t;
+            {
+              float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY;
+              int i = gt;
+#pragma unroll 2
+              for (; i + 2 * gn < NL; i += 3 * gn) {
+                const float a = z[i], b = z[i + gn], c3 = z[i + 2 * gn];
+                m0 = fmaxf(m0, a); m1 = fmaxf(m1, b); m2 = fmaxf(m2, c3);
+              }
+              for (; i < NL; i += gn) m0 = fmaxf(m0, z[i]);
+              m_t = fmaxf(m0, fmaxf(m1, m2));
+            }
             maxima[gt] = m_t;
             if (gt == 0) *g_exact = 0;
+            fst();                                                          // per-thread maxima
             ptx::named_bar_sync(gbar, gn);
-            int rk = 0;
-            for (int u = 0; u < gn; u += 4) {
+            fst();
+            int rk = 0, rk2 = 0;
+#pragma unroll 4
+            for (int u = 0; u < gn; u += 8) {                               // gn is a multiple of 32
               const float4 mu = *reinterpret_cast<const float4*>(maxima + u);
+              const float4 mv = *reinterpret_cast<const float4*>(maxima + u + 4);
               rk += (mu.x > m_t) || (mu.x == m_t && u < gt);
               rk += (mu.y > m_t) || (mu.y == m_t && u + 1 < gt);
               rk += (mu.z > m_t) || (mu.z == m_t && u + 2 < gt);
               rk += (mu.w > m_t) || (mu.w == m_t && u + 3 < gt);
+              rk2 += (mv.x > m_t) || (mv.x == m_t && u + 4 < gt);
+              rk2 += (mv.y > m_t) || (mv.y == m_t && u + 5 < gt);
+              rk2 += (mv.z > m_t) || (mv.z == m_t && u + 6 < gt);
+              rk2 += (mv.w > m_t) || (mv.w == m_t && u + 7 < gt);
             }
-            if (rk == k - 1) *reinterpret_cast<volatile float*>(g_pre) = m_t;
+            if (rk + rk2 == k - 1) *reinterpret_cast<volatile float*>(g_pre) = m_t;
+            fst();                                                          // rank among the maxima
             ptx::named_bar_sync(gbar, gn);
+            fst();
             const float tau = *reinterpret_cast<volatile float*>(g_pre);
-            // gather everything >= tau without atomics: per-thread count, warp scan, warp totals through shared memory
-            int cnt = 0;
-            for (int i = gt; i < NL; i += gn) cnt += z[i] >= tau ? 1 : 0;
+            // gather everything >= tau without atomics: per-thread bit mask (at most NL / gn <= 64 elements per thread),
+            // warp scan of the counts, warp totals through shared memory, then only the set bits are revisited
+            unsigned long long take = 0ull;
+            {
+              int i = gt, j = 0;
+#pragma unroll 2
+              for (; i + 2 * gn < NL; i += 3 * gn, j += 3) {
+                const float a = z[i], b = z[i + gn], c3 = z[i + 2 * gn];
+                take |= (a >= tau ? 1ull : 0ull) << j;
+                take |= (b >= tau ? 2ull : 0ull) << j;
+                take |= (c3 >= tau ? 4ull : 0ull) << j;
+              }
+              for (; i < NL; i += gn, ++j) take |= (z[i] >= tau ? 1ull : 0ull) << j;
+            }
+            const int cnt = __popcll(take);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1023,22 +1062,27 @@ decode_mega_kernel(const MegaParams p) {
               if (lane >= o) inc += up;
             }
             if (lane == 31) misc.wtot[s][wi] = inc;
+            fst();                                                          // count + warp scan
             ptx::named_bar_sync(gbar, gn);
+            fst();
             int pos = inc - cnt, total = 0;
-            for (int w = 0; w < nws; ++w) {
-              const int wt = misc.wtot[s][w];
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) {
+              const int wt = w < nws ? misc.wtot[s][w] : 0;
               pos += w < wi ? wt : 0;
               total += wt;
             }
-            for (int i = gt; i < NL; i += gn) {
-              const float zi = z[i];
-              if (zi >= tau) {
-                if (pos < kCandCap) clist[pos] = make_uint2(__float_as_uint(zi), static_cast<uint32_t>(r * p.VS + i));
-                ++pos;
-              }
+            while (take) {
+              const int j = __ffsll(static_cast<long long>(take)) - 1;
+              take &= take - 1;
+              const int i = gt + j * gn;
+              if (pos < kCandCap) clist[pos] = make_uint2(__float_as_uint(z[i]), static_cast<uint32_t>(r * p.VS + i));
+              ++pos;
             }
             if (gt == 0) *g_cnt = total;
+            fst();                                                          // candidates written
             ptx::named_bar_sync(gbar, gn);
+            fst();
             const int c = *g_cnt;
             overflow = c > kCandCap || c < k;
             if (!overflow) {
@@ -1165,13 +1209,16 @@ decode_mega_kernel(const MegaParams p) {
             }
           }
         }
+        fst();                                                              // ranked + shipped
         bar_compute();
+        fst();
         stamp(step);                                                        // local top-k done
         // ---- owner: merge CL x k candidates, draw, publish ----
         if (r < S) {
           const int s = r;
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.cand, (CL - 1) * k * 8);
           ptx::mbar_wait(&bars.cand, cand_use & 1);
+          fst();                                                            // candidates of the peers have landed
           ++cand_use;
           int tok = 0;
           if (k == 1) {
@@ -1216,7 +1263,9 @@ decode_mega_kernel(const MegaParams p) {
             }
             uint2* sorted = local_list + SMAX * KMAX;           // [KMAX] behind the per-sequence local lists
             if (ct < n && rk < k) sorted[rk] = mine;            // value descending, index ascending
+            fst();                                                          // merged
             bar_compute();
+            fst();
             if (cw == 0) {
               const float v0 = __uint_as_float(sorted[0].x);
               float w0 = lane < k ? expf(__uint_as_float(sorted[lane].x) - v0) : 0.f;
@@ -1245,9 +1294,9 @@ decode_mega_kernel(const MegaParams p) {
               misc.result = tok;
               if (!misc.fin[s]) {
                 const int b = b0 + s;
-                const int pos = p.st.out_len[b];
+                const int pos = misc.outlen[s];
                 p.st.out_ids[static_cast<size_t>(b) * p.st.out_stride + pos] = tok;      // api_cache.py:179
-                p.st.out_len[b] = pos + 1;
+                misc.outlen[s] = pos + 1;
               }
             }
             __syncwarp();
@@ -1266,7 +1315,9 @@ decode_mega_kernel(const MegaParams p) {
         {
           const int owned_elsewhere = S - (r < S ? 1 : 0);
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.tok, owned_elsewhere * 4);
+          fst();                                                            // token drawn / sent (owner warp 0)
           ptx::mbar_wait(&bars.tok, tok_use & 1);
+          fst();
           ++tok_use;
           bar_compute();
           if (ct < S && !misc.fin[ct]) {
@@ -1297,6 +1348,7 @@ decode_mega_kernel(const MegaParams p) {
         p.st.lens[b] = misc.len[s];
         p.st.n_new[b] = misc.nnew[s];
         p.st.finished[b] = static_cast<uint8_t>(misc.fin[s]);
+        p.st.out_len[b] = misc.outlen[s];
       }
     }
   }

@@ -434,7 +434,9 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
     fprintf(stderr, "[mega prof] step %d (ns since first stamp):", p.prof_step);
     for (int i = 0; i < 64 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
     fprintf(stderr, "\n[mega prof] layer 1 fine trace (SM cycles since layer start, warp 1 lane 0):");
-    for (int i = 64; i < 128 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[64]));
+    for (int i = 64; i < 96 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[64]));
+    fprintf(stderr, "\n[mega prof] sampler fine trace (SM cycles since sampler start):");
+    for (int i = 96; i < 128 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[96]));
     fprintf(stderr, "\n");
   }
   e->t_steps = e->cur_steps;
