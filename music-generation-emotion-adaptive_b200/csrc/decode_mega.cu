@@ -504,6 +504,7 @@ decode_mega_kernel(const MegaParams p) {
       }
     }
   }
+  for (int i = threadIdx.x; i < CL * KMAX; i += NTHREADS) cand[i] = make_uint2(__float_as_uint(-INFINITY), 0xffffffffu);
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars.full[s], 1); ptx::mbar_init(&bars.empty[s], GW); }
     ptx::mbar_init(&bars.step_go, 1);
@@ -697,9 +698,9 @@ decode_mega_kernel(const MegaParams p) {
       // NEXT LayerNorm (or the plain cast in front of the head) by the same warp: one pass, two barriers
       auto exchange_finish_ln = [&](const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ b) {
         const int buf = xuse & 1;
-        ptx::mbar_wait(&bars.xchg[buf], (xuse >> 1) & 1);
+        if (cw == 0) ptx::mbar_wait_spin(&bars.xchg[buf], (xuse >> 1) & 1);   // one warp polls (see mbar_wait_spin) ...
         fst();                                                // peers' partial sums have landed
-        bar_compute();                                        // local slot writes visible, everyone past the wait
+        bar_compute();                                        // ... and releases the others; local slot writes visible
         if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.xchg[buf], (CL - 1) * D * SMAX * 4);   // re-arm for use + 2
         if (cw < S) {
           const int s = cw;
@@ -1217,7 +1218,7 @@ decode_mega_kernel(const MegaParams p) {
         if (r < S) {
           const int s = r;
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.cand, (CL - 1) * k * 8);
-          ptx::mbar_wait(&bars.cand, cand_use & 1);
+          if (cw == 0) ptx::mbar_wait_spin(&bars.cand, cand_use & 1);       // warp 0 polls; the barriers below release the rest
           fst();                                                            // candidates of the peers have landed
           ++cand_use;
           int tok = 0;
@@ -1239,30 +1240,40 @@ decode_mega_kernel(const MegaParams p) {
             bar_compute();
             // every CTA's list arrives sorted (value descending, index ascending): the global rank of an entry is
             // its own position plus, for each other list, the number of entries that precede it (binary search)
-            const int n = CL * k;                               // <= 256 candidates, one per thread
-            uint2 mine = make_uint2(0, 0);
-            int rk = 0;
-            if (ct < n) {
-              const int src = ct / k, j = ct - src * k;
-              mine = cand[src * KMAX + j];
-              const float mv = __uint_as_float(mine.x);
-              rk = j;
+            // one thread per candidate slot (list = ct / KMAX, position = ct % KMAX); the lists are padded to KMAX entries
+            // with (-inf, 0xffffffff) sentinels at kernel start and the senders only ever write the first k, so the three
+            // searches are branch-free, have a fixed depth of 6 and advance in lock-step (their dependent loads overlap)
+            static_assert(KMAX == 64 && CL * KMAX == NCT, "merge: one thread per candidate slot, 6-step searches");
+            const int src = ct >> 6, j = ct & 63;
+            const bool live = j < k;
+            const uint2 mine = cand[src * KMAX + j];
+            const float mv = __uint_as_float(mine.x);
+            int pos[CL];
+#pragma unroll
+            for (int si = 0; si < CL; ++si) pos[si] = 0;                     // entries of list si that precede `mine`
+#pragma unroll
+            for (int stp = 32; stp >= 1; stp >>= 1) {
+#pragma unroll
               for (int si = 0; si < CL; ++si) {
-                if (si == src) continue;
-                const uint2* lst = cand + si * KMAX;
-                int lo = 0, hi = k;                             // first position whose entry does NOT precede `mine`
-                while (lo < hi) {
-                  const int mid = (lo + hi) >> 1;
-                  const uint2 o = lst[mid];
-                  const float ov = __uint_as_float(o.x);
-                  const bool before = (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && si < src)));
-                  if (before) lo = mid + 1; else hi = mid;
-                }
-                rk += lo;
+                const uint2 o = cand[si * KMAX + pos[si] + stp - 1];
+                const float ov = __uint_as_float(o.x);
+                const bool before = (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && si < src)));
+                pos[si] += before ? stp : 0;
               }
             }
+            fst();                                                          // searches done
+            int rk = j;
+#pragma unroll
+            for (int si = 0; si < CL; ++si) {
+              // the 6-step search counts at most 63 predecessors: a full list (k == KMAX) whose last entry precedes has 64
+              const uint2 o = cand[si * KMAX + KMAX - 1];
+              const float ov = __uint_as_float(o.x);
+              const bool all = (ov > mv) || (ov == mv && (o.y < mine.y || (o.y == mine.y && si < src)));
+              rk += si == src ? 0 : (all ? KMAX : pos[si]);
+            }
+            const int n = live ? 1 : 0;
             uint2* sorted = local_list + SMAX * KMAX;           // [KMAX] behind the per-sequence local lists
-            if (ct < n && rk < k) sorted[rk] = mine;            // value descending, index ascending
+            if (n && rk < k) sorted[rk] = mine;                 // value descending, index ascending
             fst();                                                          // merged
             bar_compute();
             fst();
@@ -1316,7 +1327,7 @@ decode_mega_kernel(const MegaParams p) {
           const int owned_elsewhere = S - (r < S ? 1 : 0);
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.tok, owned_elsewhere * 4);
           fst();                                                            // token drawn / sent (owner warp 0)
-          ptx::mbar_wait(&bars.tok, tok_use & 1);
+          if (cw == 0) ptx::mbar_wait_spin(&bars.tok, tok_use & 1);
           fst();
           ++tok_use;
           bar_compute();

@@ -53,6 +53,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++tries > (1u << 26)) __trap();               // seconds of waiting: a lost arrival, fail instead of hanging
   }
 }
+// Polling wait (mbarrier.test_wait, never suspends): for SHORT waits by ONE warp -- a thread suspended inside try_wait can be
+// woken thousands of cycles after the phase completes (measured: 3100 cycles of skew between the warps of a CTA that all
+// try_wait on the same DSMEM barrier), while many spinning warps steal issue slots; so one warp polls and releases the rest
+// of the CTA through a named barrier.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, tries = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (++tries > (1u << 24)) break;                   // no trap in here (ptxas then stops honouring setmaxnreg: 168 registers)
+  }
+  if (!ok) mbar_wait(bar, parity);                     // not seen after ~1 s of polling: blocking wait, which traps on a lost arrival
+}
 // Warp-collective wait: one lane polls, the others observe the completed phase once (no 32-way polling).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
