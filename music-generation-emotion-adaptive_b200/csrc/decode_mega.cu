@@ -613,7 +613,7 @@ decode_mega_kernel(const MegaParams p) {
 
       auto bar_compute = [&]() { ptx::named_bar_sync(BAR_COMPUTE, NCT); };
       int stamp_id = 0;
-      const bool prof_on = p.prof != nullptr && cluster == 0 && rank == 0 && ct == 0;
+      const bool prof_on = p.prof != nullptr && cluster == 0 && rank == 0 && ct == p.prof_thread;
       auto stamp = [&](int step_now) {
         if (prof_on && step_now == p.prof_step && stamp_id < 64) p.prof[stamp_id++] = ptx::global_timer_ns();
       };
@@ -1218,7 +1218,9 @@ decode_mega_kernel(const MegaParams p) {
         if (r < S) {
           const int s = r;
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.cand, (CL - 1) * k * 8);
-          if (cw == 0) ptx::mbar_wait_spin(&bars.cand, cand_use & 1);       // warp 0 polls; the barriers below release the rest
+          // every thread observes the arrival itself (greedy: only warp 0 needs the data): no CTA barrier behind the wait --
+          // the local candidates became visible at the barrier above, the remote ones through the mbarrier
+          if (k != 1 || cw == 0) ptx::mbar_wait_spin(&bars.cand, cand_use & 1);
           fst();                                                            // candidates of the peers have landed
           ++cand_use;
           int tok = 0;
@@ -1237,9 +1239,9 @@ decode_mega_kernel(const MegaParams p) {
               tok = __shfl_sync(0xffffffffu, bi, 0);
             }
           } else {
-            bar_compute();
-            // every CTA's list arrives sorted (value descending, index ascending): the global rank of an entry is
-            // its own position plus, for each other list, the number of entries that precede it (binary search)
+            fst();                                                          // owner: merge starts
+            // every CTA's list arrives sorted (value descending, index ascending): the global rank of an entry is its own
+            // position plus, for each other list, the number of entries that precede it (binary search):
             // one thread per candidate slot (list = ct / KMAX, position = ct % KMAX); the lists are padded to KMAX entries
             // with (-inf, 0xffffffff) sentinels at kernel start and the senders only ever write the first k, so the three
             // searches are branch-free, have a fixed depth of 6 and advance in lock-step (their dependent loads overlap)

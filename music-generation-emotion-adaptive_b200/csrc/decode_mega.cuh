@@ -51,6 +51,7 @@ struct MegaParams {
   // optional phase timeline of one step (globaltimer ns), written by cluster 0 / CTA 0: [64] entries
   unsigned long long* prof;
   int prof_step;
+  int prof_thread;                    // compute thread (0..255) of cluster 0 / CTA 0 that writes the stamps
   int stagger_groups, stagger_ns;     // start offset (cluster % groups) * ns: phase de-synchronisation of the clusters
   int dbg_gemm;                       // timing experiment only: 1 = skip ldmatrix, 2 = skip the MMAs of the weight GEMMs (garbage results)
   int dbg_skip_loads;                 // timing experiment only: signal the stages without copying (results are garbage)

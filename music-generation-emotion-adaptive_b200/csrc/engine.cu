@@ -423,6 +423,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
     if (e->d_prof) {
       cudaMemsetAsync(e->d_prof, 0, 128 * sizeof(unsigned long long), e->stream);
       p.prof = e->d_prof; p.prof_step = std::atoi(ps);
+      p.prof_thread = std::getenv("MG_MEGA_PROF_THREAD") ? std::atoi(std::getenv("MG_MEGA_PROF_THREAD")) : 0;
     }
   }
   *rc = mega::mega_relayout_kv(e->stream, e->d_mega_layers, e->st.lens, B, g.n_layer, e->max_seq, p.Tvt, p.head_dim);
