@@ -297,13 +297,14 @@ __device__ __forceinline__ uint4 ldg_stream16(const bf16* p) { return ptx::ld_gl
 template <int HD>
 __device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int b, int lane,
                                                 uint4 (&kq)[4][HD / 32], uint4 (&vq)[HD / 8]) {
-  const int g = lane >> 2, t = lane & 3, key0 = b << 5;
+  const int g = lane >> 2, t = lane & 3;
+  // rows past the end of the sequence are read too (finite: the cache is zero-filled once and only ever holds bf16 data; its
+  // row count is rounded up to a multiple of 32) and masked in attn_tc: one pointer per block, immediate offsets per load
+  const bf16* kb = kh + (static_cast<size_t>(b) * 32 + g) * HD + 8 * t;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = min(key0 + 8 * j + g, len - 1);            // rows past the end are masked in attn_tc; never read them
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int c = 0; c < HD / 32; ++c) kq[j][c] = ldg_stream16(kh + static_cast<size_t>(row) * HD + 32 * c + 8 * t);
-  }
+    for (int c = 0; c < HD / 32; ++c) kq[j][c] = ldg_stream16(kb + j * 8 * HD + 32 * c);
   const bf16* vb = vt + static_cast<size_t>(b) * (HD * 32) + g * 32 + 8 * t;
 #pragma unroll
   for (int n = 0; n < HD / 8; ++n) vq[n] = ldg_stream16(vb + n * 256);
@@ -356,9 +357,16 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
         mma_bf16_16816(c4, a0, kq[j][c].x, kq[j][c].y);
         mma_bf16_16816(c4, a1, kq[j][c].z, kq[j][c].w);
       }
-      const int key = key0 + 8 * j + 2 * t;
-      sc[j][0] = key < len ? c4[0] + c4[2] : -INFINITY;          // row 0 (hi) + row 8 (lo)
-      sc[j][1] = key + 1 < len ? c4[1] + c4[3] : -INFINITY;
+      sc[j][0] = c4[0] + c4[2];                                  // row 0 (hi) + row 8 (lo)
+      sc[j][1] = c4[1] + c4[3];
+    }
+    if (key0 + 32 > len) {                                       // only the last block of a sequence is partial
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = key0 + 8 * j + 2 * t;
+        sc[j][0] = key < len ? sc[j][0] : -INFINITY;
+        sc[j][1] = key + 1 < len ? sc[j][1] : -INFINITY;
+      }
     }
     float mb = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1])),
                      fmaxf(fmaxf(sc[2][0], sc[2][1]), fmaxf(sc[3][0], sc[3][1])));
@@ -749,13 +757,13 @@ decode_mega_kernel(const MegaParams p) {
           constexpr bool kAttnPre = HD == 32;
 #endif
           uint4 kq0[4][HD / 32], vq0[HD / 8];
-          const size_t kv_seq = static_cast<size_t>(CL) * p.Tmax * FS;       // K cache elements per sequence
+          const size_t kv_seq = static_cast<size_t>(CL) * p.Tvt * FS;        // K cache elements per sequence
           const size_t vt_seq = static_cast<size_t>(CL) * p.Tvt * FS;        // V cache elements per sequence
-          bf16* const kbase = misc.kvp[l][0] + (static_cast<size_t>(b0) * CL + r) * p.Tmax * FS;   // [head][T][hd]
+          bf16* const kbase = misc.kvp[l][0] + (static_cast<size_t>(b0) * CL + r) * p.Tvt * FS;    // [head][Tvt][hd]
           bf16* const vbase = misc.kvp[l][1] + (static_cast<size_t>(b0) * CL + r) * p.Tvt * FS;    // [head][T / 32][hd][32]
           const int at_s = att_pair >> nh_shift, at_h = att_pair & ((1 << nh_shift) - 1);
           const int at_len = misc.fin[at_s] ? 0 : misc.len[at_s];
-          const bf16* at_kh = kbase + at_s * kv_seq + static_cast<size_t>(at_h) * p.Tmax * hd;
+          const bf16* at_kh = kbase + at_s * kv_seq + static_cast<size_t>(at_h) * p.Tvt * hd;
           const bf16* at_vt = vbase + at_s * vt_seq + static_cast<size_t>(at_h) * p.Tvt * hd;
           if (kAttnPre && (att_wi << 5) < at_len) attn_load_block<HD>(at_kh, at_vt, at_len, att_wi, lane, kq0, vq0);
           // ---- QKV (LN1 was applied by the previous epilogue): stage rows 0..63 = q, 64..127 = k, 128..191 = v slice ----
@@ -795,7 +803,7 @@ decode_mega_kernel(const MegaParams p) {
           // ---- append the new K row / V^T column (api_cache.py:66-67) + flash-decoding over this CTA's slice ----
           if (cw < S && lane < 8 && !misc.fin[cw]) {
             const int s = cw, c = lane, h = (8 * c) >> hd_shift, d0 = (8 * c) & (hd - 1);
-            bf16* dst = kbase + s * kv_seq + (static_cast<size_t>(h) * p.Tmax + misc.len[s]) * hd + d0;
+            bf16* dst = kbase + s * kv_seq + (static_cast<size_t>(h) * p.Tvt + misc.len[s]) * hd + d0;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(knew + s * FS + c * 8);
           }
           if (ct < S * FS) {
@@ -1432,12 +1440,12 @@ __global__ void mega_relayout_kv_kernel(const MegaLayer* __restrict__ layers, co
   const int len = lens[bs / CL];
   const bf16* ksrc = layers[l].kc + static_cast<size_t>(bs) * Tmax * FS;
   const bf16* vsrc = layers[l].vc + static_cast<size_t>(bs) * Tmax * FS;
-  bf16* kdst = layers[l].kh + static_cast<size_t>(bs) * Tmax * FS;
+  bf16* kdst = layers[l].kh + static_cast<size_t>(bs) * Tvt * FS;
   bf16* vdst = layers[l].vt + static_cast<size_t>(bs) * Tvt * FS;
   for (int i = threadIdx.x; i < len * FS; i += blockDim.x) {
     const int t = i >> 6, f = i & 63, h = f / hd, d = f - h * hd, ki = t & 31;
     const int pos = 8 * ((ki >> 1) & 3) + 2 * (ki >> 3) + (ki & 1);
-    kdst[(static_cast<size_t>(h) * Tmax + t) * hd + d] = ksrc[i];
+    kdst[(static_cast<size_t>(h) * Tvt + t) * hd + d] = ksrc[i];
     vdst[(static_cast<size_t>(h) * (Tvt >> 5) + (t >> 5)) * (hd * 32) + d * 32 + pos] = vsrc[i];
   }
 }

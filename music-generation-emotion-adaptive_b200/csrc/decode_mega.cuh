@@ -28,7 +28,7 @@ constexpr int kMegaMaxSeqPerCluster = 4;
 struct MegaLayer {
   const float *b_in, *b_out, *b1, *b2, *ln1w, *ln1b, *ln2w, *ln2b;
   bf16 *kc, *vc;                      // cache slices [B][4][Tmax][64], written by the prefill
-  bf16 *kh, *vt;                      // caches of the persistent kernel: K head-major [B][4][head][Tmax][hd],
+  bf16 *kh, *vt;                      // caches of the persistent kernel: K head-major [B][4][head][Tvt][hd],
                                       // V per 32-key block transposed [B][4][head][Tvt / 32][hd][32] (see attn_tc)
 };
 

@@ -373,7 +373,10 @@ int setup_mega(mg_engine* e) {
       const size_t vt_bytes = sizeof(bf16) * static_cast<size_t>(e->max_batch) * g.d_model * mega_tvt(e->max_seq);
       MG_TRY(e->dmalloc(&w.vt, vt_bytes));
       MG_CUDA_OK(cudaMemsetAsync(w.vt, 0, vt_bytes, e->stream));
-      MG_TRY(e->dmalloc(&w.kh, sizeof(bf16) * static_cast<size_t>(e->max_batch) * g.d_model * e->max_seq));
+      // + one 32-row block of slack: the last block of the last sequence is read whole
+      const size_t kh_bytes = vt_bytes + sizeof(bf16) * 32 * g.d_model;
+      MG_TRY(e->dmalloc(&w.kh, kh_bytes));
+      MG_CUDA_OK(cudaMemsetAsync(w.kh, 0, kh_bytes, e->stream));
     }
     lay[l] = mega::MegaLayer{w.b_in, w.b_out, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
                              reinterpret_cast<bf16*>(w.kc), reinterpret_cast<bf16*>(w.vc), reinterpret_cast<bf16*>(w.kh),
