@@ -10,7 +10,7 @@
 //     [256r, 256r+256) of the MLP and vocabulary rows [r*VS, (r+1)*VS) of the head (Megatron-style
 //     column-parallel -> row-parallel pairs, so a layer needs two exchanges only);
 //   * the weights were re-laid out at load time (mega_pack_weights) as the exact shared-memory image of
-//     every 32 KB stage [256 weight rows x 64 K, 128B-swizzled] in consumption order, so the producer warp
+//     every 32 KB stage [256 weight rows x 64 K, ldmatrix-fragment-major] in consumption order, so the producer warp
 //     streams them L2 -> shared memory with ONE cp.async.bulk per stage into a 4-stage ring ("full" = mbarrier
 //     with complete_tx, "free" = named barrier: bar.arrive by the compute warps, bar.sync by the producer warp);
 //   * the contractions are warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 -> fp32) issued by all eight
@@ -185,21 +185,15 @@ struct RingPos {
 // A-operand (weight) fragments of one stage for this warp: 2 m16 tiles x 4 k-steps, double-buffered across stages.
 struct WFrag {
   uint32_t a[2][2][4][4];
-  uint32_t off[2][4];             // fragment offsets inside a stage (the same for every stage)
+  uint32_t off;                   // this lane's offset inside a stage: warp * 4 KB + lane * 16 (fragment-major layout)
   RingPos ld;                     // next stage to load (runs ahead of the release position)
   int dbg;                        // timing experiments: 1 = skip ldmatrix, 2 = skip the MMAs (results are garbage)
 };
-__device__ __forceinline__ void wfrag_init(WFrag& wf, int cw, int lane) {
-  // ldmatrix row address of this lane: matrix m = lane / 8 -> rows (m & 1) * 8 + lane % 8, k chunk (m >> 1)
-  const int lrow = ((lane >> 3) & 1) * 8 + (lane & 7), lchunk = lane >> 4;
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int i = cw * 32 + t * 16 + lrow;                     // stage row 0..255
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-      wf.off[t][ks] = (i >> 7) * (STAGE_BYTES / 2) + (i & 127) * 128 + (((ks * 2 + lchunk) ^ (i & 7)) << 4);
-  }
-}
+// Stage layout (mega_pack_kernel): fragment-major.  The 32 KB of a stage are 64 blocks of 512 bytes, block (w, t, ks) =
+// the ldmatrix.x4 fragment of warp w for its m16 tile t and k-step ks, stored in ldmatrix lane order (lane l supplies the
+// 16-byte row l of the block: matrix l / 8 = rows (m & 1) * 8.. of the tile, k chunk m >> 1).  Every ldmatrix of a warp is
+// one contiguous, conflict-free 512-byte read at an IMMEDIATE offset from one per-lane register.
+__device__ __forceinline__ void wfrag_init(WFrag& wf, int cw, int lane) { wf.off = cw * 4096 + lane * 16; }
 template <int NSTAGE>
 __device__ __forceinline__ void wfrag_load(WFrag& wf, int buf, uint32_t ring_addr, uint64_t* full, bool active) {
   ptx::mbar_wait(&full[wf.ld.stage], wf.ld.phase);
@@ -208,7 +202,7 @@ __device__ __forceinline__ void wfrag_load(WFrag& wf, int buf, uint32_t ring_add
 #pragma unroll
     for (int t = 0; t < 2; ++t)
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(sbase + wf.off[t][ks], wf.a[buf][t][ks]);
+      for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(sbase + wf.off + (t * 4 + ks) * 512, wf.a[buf][t][ks]);
   }
   wf.ld.template advance<NSTAGE>();
 }
@@ -1381,8 +1375,7 @@ decode_mega_kernel(const MegaParams p) {
 }
 
 // ---- weight re-layout: the shared-memory image of every stage, in consumption order, per rank -------
-// Stage = [256 rows x 64 K] bf16 as two SW128 K-major tiles; row i lives at (i / 128) * 16 KB + (i % 128) * 128 B,
-// 16-byte chunk c at position c ^ (i & 7).  Order per rank: for every layer {in_proj kb 0..3 | out_proj | mlp.0
+// Stage = [256 rows x 64 K] bf16 in fragment-major order (see wfrag_init).  Order per rank: for every layer {in_proj kb 0..3 | out_proj | mlp.0
 // kb 0..3 | mlp.2 kb 0..3}, then the head pairs {kb 0..3}.
 struct PackSrc {
   const bf16* w_in[kMegaMaxLayers];
@@ -1400,10 +1393,11 @@ __global__ void mega_pack_kernel(PackSrc src, uint4* __restrict__ dst, int n_lay
     const int chunk_pos = static_cast<int>(idx % (STAGE_BYTES / 16));
     const int stage_g = static_cast<int>(idx / (STAGE_BYTES / 16));
     const int r = stage_g / stages_per_rank, st = stage_g % stages_per_rank;
-    const int tile = chunk_pos / 1024, in_tile = chunk_pos % 1024;
-    const int row_in_tile = in_tile / 8, cpos = in_tile % 8;
-    const int i = tile * 128 + row_in_tile;               // stage row 0..255
-    const int c = cpos ^ (row_in_tile & 7);                // logical 16-byte chunk (8 bf16 along K)
+    // fragment-major: chunk_pos = ((warp * 8 + t * 4 + ks) * 32 + lane), see wfrag_init
+    const int pw = chunk_pos >> 8, pf = (chunk_pos >> 5) & 7, pl = chunk_pos & 31;
+    const int pt = pf >> 2, pks = pf & 3, pm = pl >> 3;
+    const int i = pw * 32 + pt * 16 + (pm & 1) * 8 + (pl & 7);   // stage row 0..255
+    const int c = pks * 2 + (pm >> 1);                           // logical 16-byte chunk (8 bf16 along K) of the stage's 64 K
     const bf16* w = nullptr;
     int row = -1, col = 0, ld = D;
     if (st < n_layer * kMegaStagesPerLayer) {
