@@ -207,6 +207,57 @@ __device__ __forceinline__ void wfrag_load(WFrag& wf, int buf, uint32_t ring_add
   wf.ld.template advance<NSTAGE>();
 }
 
+// in_proj of this CTA's slice: 192 rows (q | k | v, 64 each) x K = 256 = 12 m16 tiles x 16 k-steps = 192 fragments = exactly
+// THREE stages with every warp busy (the row-major [256 x 64] stage format needed four, a quarter of them padding):
+//   warp w owns the k / v tile 4 + w over all 16 k-steps (stages 0 and 1: fragment f = k-step 8 s + f) and HALF of the
+//   k-steps of q tile w / 2 (stage 2: fragment f = k-step 8 (w % 2) + f); the two warps of a q tile add their halves into the
+//   fp32 q vector in shared memory (two commutative additions onto zero: deterministic).
+//   acc_kv: rows frow / frow + 8 of tile 4 + w, acc_q: this warp's half of tile w / 2; sequences fs, fs + 1.
+template <int NSTAGE>
+__device__ __forceinline__ void gemm_qkv(uint8_t* ring, uint64_t* full, RingPos& rp, WFrag& wf, const bf16* act, int pitch, int cw,
+                                         int lane, float (&acc_kv)[4], float (&acc_q)[4], unsigned long long*& tr) {
+  const uint32_t ring_addr = ptx::smem_u32(ring);
+  const bf16* bp = act + (lane >> 2) * pitch + (lane & 3) * 2;
+  uint32_t bq[2][8][2];
+  auto load_b = [&](int buf, int ks0) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      bq[buf][f][0] = *reinterpret_cast<const uint32_t*>(bp + (ks0 + f) * 16);
+      bq[buf][f][1] = *reinterpret_cast<const uint32_t*>(bp + (ks0 + f) * 16 + 8);
+    }
+  };
+  float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { acc_kv[e] = 0.f; acc_q[e] = 0.f; }
+  load_b(0, 0);
+  wf.ld = rp;
+  wfrag_load<NSTAGE>(wf, 0, ring_addr, full, true);
+  MG_TR(tr);
+#pragma unroll
+  for (int st = 0; st < 3; ++st) {
+    if (st + 1 < 3) {
+      load_b((st + 1) & 1, st == 0 ? 8 : 8 * (cw & 1));
+      wfrag_load<NSTAGE>(wf, (st + 1) & 1, ring_addr, full, true);
+    }
+    if (!(wf.dbg & 2)) {
+      if (st == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc_kv[e] += acc2[e]; acc2[e] = 0.f; }
+      }
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        float (&dst)[4] = (f & 1) ? acc2 : (st == 2 ? acc_q : acc_kv);
+        mma_bf16_16816(dst, wf.a[st & 1][f >> 2][f & 3], bq[st & 1][f][0], bq[st & 1][f][1]);
+      }
+    }
+    ptx::named_bar_arrive(BAR_STAGE_FREE + rp.stage, NCT + 32);
+    rp.template advance<NSTAGE>();
+    MG_TR(tr);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc_q[e] += acc2[e];
+}
+
 // One GEMM "pair": NKB stages of [256 weight rows x 64 K]; this warp owns weight rows [32 cw, 32 cw + 32)
 // (two m16 tiles) and accumulates D[16 rows x 8 sequences] per tile over the stages.
 //   act   : activations bf16 [8][pitch] (row = sequence), K contiguous
@@ -507,6 +558,7 @@ decode_mega_kernel(const MegaParams p) {
     }
   }
   for (int i = threadIdx.x; i < CL * KMAX; i += NTHREADS) cand[i] = make_uint2(__float_as_uint(-INFINITY), 0xffffffffu);
+  for (int i = threadIdx.x; i < SMAX * FS; i += NTHREADS) qs[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&bars.full[s], 1); ptx::mbar_init(&bars.empty[s], GW); }
     ptx::mbar_init(&bars.step_go, 1);
@@ -762,31 +814,27 @@ decode_mega_kernel(const MegaParams p) {
           if (kAttnPre && (att_wi << 5) < at_len) attn_load_block<HD>(at_kh, at_vt, at_len, att_wi, lane, kq0, vq0);
           // ---- QKV (LN1 was applied by the previous epilogue): stage rows 0..63 = q, 64..127 = k, 128..191 = v slice ----
           if (cw < GW) {
-            const int part_id = cw >> 1;                      // 0 = q, 1 = k, 2 = v
-            float qb[2][2];                                   // biases ahead of the MMAs (no load behind a store in the epilogue)
+            // biases ahead of the MMAs (no load behind a store in the epilogue): k / v tile 4 + cw, q tile cw / 2
+            const int f_kv = (cw & 3) * 16 + frow, f_q = (cw >> 1) * 16 + frow;   // features inside the 64-wide slice (+ 8 h8)
+            const int part_kv = 1 + (cw >> 2);                                 // 1 = k (warps 0..3), 2 = v (warps 4..7)
+            float bkv[2], bqq[2];
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
+            for (int h8 = 0; h8 < 2; ++h8) {
+              bkv[h8] = pl[P_BQKV + part_kv * FS + f_kv + h8 * 8];
+              bqq[h8] = (cw & 1) ? 0.f : pl[P_BQKV + f_q + h8 * 8];            // the bias goes in with the first k-half
+            }
+            float acc_kv[4], acc_q[4];
+            gemm_qkv<NSTAGE>(ring, bars.full, rp, wf, xb, XP, cw, lane, acc_kv, acc_q, tr);
+            if (fs < S) {
+              bf16* kvdst = part_kv == 1 ? knew : vnew;
 #pragma unroll
               for (int h8 = 0; h8 < 2; ++h8)
-                qb[t][h8] = cw < 6 ? pl[P_BQKV + part_id * FS + (cw & 1) * 32 + t * 16 + frow + h8 * 8] : 0.f;
-            float acc[2][4];
-            gemm_pair<4, NSTAGE>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, cw < 6, false, false, acc, tr);
-            if (cw < 6 && fs < S) {
 #pragma unroll
-              for (int t = 0; t < 2; ++t)
-#pragma unroll
-                for (int h8 = 0; h8 < 2; ++h8) {
-                  const int f = (cw & 1) * 32 + t * 16 + frow + h8 * 8;      // feature inside the 64-wide slice
-                  const float bias = qb[t][h8];
-#pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-                    const int s = fs + e;
-                    if (s < S) {
-                      const float v = acc[t][h8 * 2 + e] + bias;
-                      if (part_id == 0) qs[s * FS + f] = v * scale_log2;
-                      else if (part_id == 1) knew[s * FS + f] = __float2bfloat16_rn(v);
-                      else vnew[s * FS + f] = __float2bfloat16_rn(v);
-                    }
+                for (int e = 0; e < 2; ++e) {
+                  const int s = fs + e;
+                  if (s < S) {
+                    kvdst[s * FS + f_kv + h8 * 8] = __float2bfloat16_rn(acc_kv[h8 * 2 + e] + bkv[h8]);
+                    atomicAdd(qs + s * FS + f_q + h8 * 8, (acc_q[h8 * 2 + e] + bqq[h8]) * scale_log2);
                   }
                 }
             }
@@ -843,6 +891,7 @@ decode_mega_kernel(const MegaParams p) {
               o = fmaf(ow[k], fw, o);
             }
             attb[mg_s * AP + mg_f] = __float2bfloat16_rn(__fdividef(o, Lsum));
+            qs[mg_s * FS + mg_f] = 0.f;                                     // the next in_proj ADDS its two k-halves into q
           }
           fst();                                                            // merge done
           bar_compute();
@@ -1402,17 +1451,18 @@ __global__ void mega_pack_kernel(PackSrc src, uint4* __restrict__ dst, int n_lay
     int row = -1, col = 0, ld = D;
     if (st < n_layer * kMegaStagesPerLayer) {
       const int l = st / kMegaStagesPerLayer, q = st % kMegaStagesPerLayer;
-      if (q < 4) {                                          // in_proj: q rows | k rows | v rows | unused
-        w = src.w_in[l]; col = q * 64;
-        if (i < 64) row = r * FS + i;
-        else if (i < 128) row = D + r * FS + (i - 64);
-        else if (i < 192) row = 2 * D + r * FS + (i - 128);
-      } else if (q == 4) {                                  // out_proj: all 256 output rows, this rank's 64 input columns
+      if (q < 3) {                                          // in_proj, fragment layout of gemm_qkv (NOT the generic one)
+        const int tile = q < 2 ? 4 + pw : (pw >> 1);        // m16 tile of the 192 rows q | k | v
+        const int ks = q < 2 ? 8 * q + pf : 8 * (pw & 1) + pf;
+        const int i192 = tile * 16 + (pm & 1) * 8 + (pl & 7);
+        w = src.w_in[l]; col = ks * 16 + (pm >> 1) * 8 - c * 8;   // (c * 8 is added back below)
+        row = (i192 >> 6) * D + r * FS + (i192 & 63);
+      } else if (q == 3) {                                  // out_proj: all 256 output rows, this rank's 64 input columns
         w = src.w_out[l]; row = i; col = r * FS;
-      } else if (q < 9) {                                   // mlp.0: this rank's 256 hidden rows
-        w = src.w1[l]; row = r * HS + i; col = (q - 5) * 64;
+      } else if (q < 8) {                                   // mlp.0: this rank's 256 hidden rows
+        w = src.w1[l]; row = r * HS + i; col = (q - 4) * 64;
       } else {                                              // mlp.2: all 256 output rows, this rank's 256 hidden columns
-        w = src.w2[l]; row = i; col = r * HS + (q - 9) * 64; ld = 4 * D;
+        w = src.w2[l]; row = i; col = r * HS + (q - 8) * 64; ld = 4 * D;
       }
     } else {
       const int hq = st - n_layer * kMegaStagesPerLayer, pr = hq / 4, kb = hq % 4;

@@ -15,7 +15,7 @@ constexpr int kMegaCluster = 4;       // CTAs per cluster = d_model / 64 feature
 constexpr int kMegaMaxTopK = 64;      // the in-kernel sampler handles 1 <= top_k <= 64
 constexpr int kMegaMaxNL = 2304;      // vocabulary rows per CTA, padded to 256: ceil(V / 4) <= 2304
 constexpr int kMegaStageBytes = 32768;
-constexpr int kMegaStagesPerLayer = 13;   // in_proj 4 + out_proj 1 + mlp.0 4 + mlp.2 4 stages of 32 KB
+constexpr int kMegaStagesPerLayer = 12;   // in_proj 3 + out_proj 1 + mlp.0 4 + mlp.2 4 stages of 32 KB
 constexpr int kMegaMaxLayers = 8;
 constexpr int kMegaMaxLayersSmem = 4;  // layers whose LN / bias parameters are kept in shared memory
 #ifndef MG_MEGA_STAGES2
