@@ -258,6 +258,34 @@ __device__ __forceinline__ void gemm_qkv(uint8_t* ring, uint64_t* full, RingPos&
   for (int e = 0; e < 4; ++e) acc_q[e] += acc2[e];
 }
 
+// ONE stage holding 64 weight rows x K = 256 (4 m16 tiles x 16 k-steps): warp w owns tile w / 2 and the k-half w % 2
+// (fragment f = k-step 8 (w % 2) + f); the two warps of a tile add their halves in shared memory.  The tail of the head
+// (the last <= 64 vocabulary rows of the slice) goes through this instead of a padded 256-row tile pair.
+// PRE: buffer 0 was loaded by the previous GEMM (preload_next of a pair).
+template <int NSTAGE, bool PRE>
+__device__ __forceinline__ void gemm_khalf(uint8_t* ring, uint64_t* full, RingPos& rp, WFrag& wf, const bf16* act, int pitch, int cw,
+                                           int lane, float (&acc)[4]) {
+  const bf16* bp = act + (lane >> 2) * pitch + (lane & 3) * 2 + 8 * (cw & 1) * 16;
+  uint32_t bq[8][2];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    bq[f][0] = *reinterpret_cast<const uint32_t*>(bp + f * 16);
+    bq[f][1] = *reinterpret_cast<const uint32_t*>(bp + f * 16 + 8);
+  }
+  if (!PRE) { wf.ld = rp; wfrag_load<NSTAGE>(wf, 0, ptx::smem_u32(ring), full, true); }
+  float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[e] = 0.f;
+  if (!(wf.dbg & 2)) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f) mma_bf16_16816((f & 1) ? acc2 : acc, wf.a[0][f >> 2][f & 3], bq[f][0], bq[f][1]);
+  }
+  ptx::named_bar_arrive(BAR_STAGE_FREE + rp.stage, NCT + 32);
+  rp.template advance<NSTAGE>();
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
+}
+
 // One GEMM "pair": NKB stages of [256 weight rows x 64 K]; this warp owns weight rows [32 cw, 32 cw + 32)
 // (two m16 tiles) and accumulates D[16 rows x 8 sequences] per tile over the stages.
 //   act   : activations bf16 [8][pitch] (row = sequence), K contiguous
@@ -535,7 +563,7 @@ decode_mega_kernel(const MegaParams p) {
   const int cluster = static_cast<int>(ptx::cluster_id_x());
   const int S = min(p.S, p.B - cluster * p.S);             // sequences of this cluster (may be <= 0)
   const int b0 = cluster * p.S;                            // first global sequence index
-  const int n_layer = p.n_layer, NL = 2 * p.NP * 128;      // head rows per CTA, padded to tile pairs
+  const int n_layer = p.n_layer, NL = 256 * p.NP + 64 * p.head_tail;   // head rows per CTA, padded to tile pairs (+ tail tiles)
   constexpr int hd = HD;
 
   // ---------------- one-time setup ----------------
@@ -598,7 +626,7 @@ decode_mega_kernel(const MegaParams p) {
       if (warp == 0) {
         // warp 0: all lanes take part in the named-barrier waits, lane 0 issues the copies
         RingPos rp;
-        const int stages_per_step = n_layer * kMegaStagesPerLayer + 4 * p.NP;
+        const int stages_per_step = n_layer * kMegaStagesPerLayer + 4 * p.NP + p.head_tail;
         const uint8_t* src0 = p.packed + static_cast<size_t>(rank) * stages_per_step * STAGE_BYTES;
         int issued = 0;
         for (int step = 0; step < n_steps; ++step) {
@@ -721,6 +749,12 @@ decode_mega_kernel(const MegaParams p) {
             v[2 * j4 + 1] = __bfloat162float(t2.y) + __bfloat162float(p2.y);
           }
           ln_store(s, v, w, b);
+        }
+        if (p.head_tail && ct >= NCT - 64) {
+          // the head's tail tiles ADD their two k-halves into the logits: real rows start from 0, padding rows stay -inf
+          const int lr = 256 * p.NP + (ct - (NCT - 64));
+          const float init = (lr < p.VS && r * p.VS + lr < p.V) ? 0.f : -INFINITY;
+          for (int s = 0; s < S; ++s) logits[s * NL + lr] = init;
         }
         bar_compute();
       };
@@ -969,8 +1003,9 @@ decode_mega_kernel(const MegaParams p) {
                 hbv[t][h8] = vr < v_hi ? __ldg(p.head_b + vr) : 0.f;
               }
             float acc[2][4];
-            if (first) gemm_pair<4, NSTAGE, false>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, true, pr + 1 < p.NP, true, acc, tr);
-            else gemm_pair<4, NSTAGE, true>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, true, pr + 1 < p.NP, true, acc, tr);
+            const bool more = pr + 1 < p.NP + p.head_tail;         // another pair, or the single-stage tail, follows
+            if (first) gemm_pair<4, NSTAGE, false>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, true, more, true, acc, tr);
+            else gemm_pair<4, NSTAGE, true>(ring, bars.full, bars.empty, rp, wf, xb, XP, lane, true, more, true, acc, tr);
             if (fs < S) {
               const int lr0 = pr * 256 + cw * 32 + frow;                     // row inside the slice: lr0 + 16 t + 8 h8
 #pragma unroll
@@ -997,11 +1032,38 @@ decode_mega_kernel(const MegaParams p) {
             }
           };
           if (cw < GW) {
-            head_pair(0, true);
+            if (p.NP > 0) head_pair(0, true);
             for (int pr = 1; pr < p.NP; ++pr) head_pair(pr, false);
+            if (p.head_tail) {
+              // tail: tile cw / 2 of the last 64 rows, k-half cw % 2; the bias goes in with the first half
+              const int lr0 = 256 * p.NP + (cw >> 1) * 16 + frow;
+              float tb[2];
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                const int vr = v_lo + lr0 + h8 * 8;
+                tb[h8] = (!(cw & 1) && vr < v_hi) ? __ldg(p.head_b + vr) : 0.f;
+              }
+              float acc[4];
+              if (p.NP > 0) gemm_khalf<NSTAGE, true>(ring, bars.full, rp, wf, xb, XP, cw, lane, acc);
+              else gemm_khalf<NSTAGE, false>(ring, bars.full, rp, wf, xb, XP, cw, lane, acc);
+              if (fs < S) {
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8)
+#pragma unroll
+                  for (int e = 0; e < 2; ++e)
+                    if (fs + e < S && v_lo + lr0 + h8 * 8 < v_hi)
+                      atomicAdd(logits + (fs + e) * NL + lr0 + h8 * 8, (acc[h8 * 2 + e] + tb[h8]) * inv_temp);
+              }
+            }
           }
         }
         bar_compute();
+        if (p.dbg_logits && p.head_tail && ct < 64) {                        // parity / debug path: raw logits of the tail rows
+          const int lr = 256 * p.NP + ct, vr = r * p.VS + lr;
+          if (lr < p.VS && vr < p.V)
+            for (int s = 0; s < S; ++s)
+              p.dbg_logits[(static_cast<size_t>(step) * p.B + b0 + s) * p.V + vr] = logits[s * NL + lr] * sp.temperature;
+        }
         stamp(step);                                                        // head done
 
         // ---- sampler (api_cache.py:169-181): local top-k -> owner CTA ranks, draws, broadcasts ----
@@ -1434,8 +1496,8 @@ struct PackSrc {
   const bf16* head;
 };
 
-__global__ void mega_pack_kernel(PackSrc src, uint4* __restrict__ dst, int n_layer, int V, int VS, int NP) {
-  const int stages_per_rank = n_layer * kMegaStagesPerLayer + 4 * NP;
+__global__ void mega_pack_kernel(PackSrc src, uint4* __restrict__ dst, int n_layer, int V, int VS, int NP, int tail) {
+  const int stages_per_rank = n_layer * kMegaStagesPerLayer + 4 * NP + tail;
   const size_t total = static_cast<size_t>(CL) * stages_per_rank * (STAGE_BYTES / 16);
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1465,10 +1527,19 @@ __global__ void mega_pack_kernel(PackSrc src, uint4* __restrict__ dst, int n_lay
         w = src.w2[l]; row = i; col = r * HS + (q - 8) * 64; ld = 4 * D;
       }
     } else {
-      const int hq = st - n_layer * kMegaStagesPerLayer, pr = hq / 4, kb = hq % 4;
-      const int lr = pr * 256 + i;                          // row inside this rank's vocabulary slice
-      w = src.head; col = kb * 64;
-      if (lr < VS && r * VS + lr < V) row = r * VS + lr;
+      const int hq = st - n_layer * kMegaStagesPerLayer;
+      w = src.head;
+      if (hq < 4 * NP) {
+        const int pr = hq / 4, kb = hq % 4;
+        const int lr = pr * 256 + i;                        // row inside this rank's vocabulary slice
+        col = kb * 64;
+        if (lr < VS && r * VS + lr < V) row = r * VS + lr;
+      } else {                                              // tail stage, fragment layout of gemm_khalf
+        const int tile = pw >> 1, ks = 8 * (pw & 1) + pf;
+        const int lr = 256 * NP + tile * 16 + (pm & 1) * 8 + (pl & 7);
+        col = ks * 16 + (pm >> 1) * 8 - c * 8;              // (c * 8 is added back below)
+        if (lr < VS && r * VS + lr < V) row = r * VS + lr;
+      }
     }
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row >= 0) v = *reinterpret_cast<const uint4*>(w + static_cast<size_t>(row) * ld + col + c * 8);
@@ -1506,17 +1577,17 @@ int mega_smem_bytes(int smax) {
   return (smax <= 2 ? Smem<2, kMegaStages2>::kTotal : Smem<4, kMegaStages4>::kTotal) + 1024;
 }
 
-size_t mega_packed_bytes(int n_layer, int NP) {
-  return static_cast<size_t>(CL) * (n_layer * kMegaStagesPerLayer + 4 * NP) * STAGE_BYTES;
+size_t mega_packed_bytes(int n_layer, int NP, int tail) {
+  return static_cast<size_t>(CL) * (n_layer * kMegaStagesPerLayer + 4 * NP + tail) * STAGE_BYTES;
 }
 
 int mega_pack_weights(cudaStream_t stream, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1,
-                      const bf16* const* w2, const bf16* head, int n_layer, int V, int VS, int NP, void* dst) {
+                      const bf16* const* w2, const bf16* head, int n_layer, int V, int VS, int NP, int tail, void* dst) {
   if (n_layer > kMegaMaxLayers) return MG_E_SHAPE;
   PackSrc src{};
   for (int l = 0; l < n_layer; ++l) { src.w_in[l] = w_in[l]; src.w_out[l] = w_out[l]; src.w1[l] = w1[l]; src.w2[l] = w2[l]; }
   src.head = head;
-  mega_pack_kernel<<<148 * 4, 256, 0, stream>>>(src, reinterpret_cast<uint4*>(dst), n_layer, V, VS, NP);
+  mega_pack_kernel<<<148 * 4, 256, 0, stream>>>(src, reinterpret_cast<uint4*>(dst), n_layer, V, VS, NP, tail);
   MG_LAUNCH_CHECK();
   return MG_OK;
 }

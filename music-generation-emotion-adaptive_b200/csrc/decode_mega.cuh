@@ -40,7 +40,8 @@ struct MegaParams {
   const float* head_b;
   const SampleParams* sp;
   DecodeState st;
-  int n_layer, head_dim, V, VS, NP;   // VS = ceil(V / 4) vocabulary rows per CTA, NP = ceil(VS / 256) tile pairs
+  int n_layer, head_dim, V, VS, NP;   // VS = ceil(V / 4) vocabulary rows per CTA, NP = 256-row tile pairs of the head (4 stages each)
+  int head_tail;                      // 1: the last <= 64 rows of the slice are ONE extra stage (mega_head_tail)
   int B, S, Tmax, n_steps;            // S = sequences per cluster
   int Tvt;                            // keys per (sequence, head) of the V cache: Tmax rounded up to 32
   int early_exit;                     // EOS enabled: a cluster stops as soon as all of its sequences have finished
@@ -58,9 +59,12 @@ struct MegaParams {
 };
 
 int mega_init();
-size_t mega_packed_bytes(int n_layer, int NP);
+// head rows per CTA -> 256-row tile pairs + an optional single-stage tail for a remainder of at most 64 rows
+inline int mega_head_tail(int VS) { const int rem = VS % 256; return rem > 0 && rem <= 64 ? 1 : 0; }
+inline int mega_head_pairs(int VS) { return mega_head_tail(VS) ? VS / 256 : (VS + 255) / 256; }
+size_t mega_packed_bytes(int n_layer, int NP, int tail);
 int mega_pack_weights(cudaStream_t stream, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1,
-                      const bf16* const* w2, const bf16* head, int n_layer, int V, int VS, int NP, void* dst);
+                      const bf16* const* w2, const bf16* head, int n_layer, int V, int VS, int NP, int tail, void* dst);
 int mega_relayout_kv(cudaStream_t stream, const MegaLayer* layers, const int32_t* lens, int B, int n_layer, int Tmax, int Tvt, int hd);
 int mega_max_clusters(int smax);      // co-resident clusters (0 when the query fails)
 int launch_decode_mega(cudaStream_t stream, const MegaParams& p, int n_clusters);

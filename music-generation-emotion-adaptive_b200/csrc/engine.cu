@@ -361,7 +361,7 @@ int setup_mega(mg_engine* e) {
   if (e->mega_clusters2 <= 0 && e->mega_clusters4 <= 0) return MG_OK;
   const int L = g.n_layer;
   if (L > mega::kMegaMaxLayers || L > mega::kMegaMaxLayersSmem) return MG_OK;
-  const int NP = ceil_div(VS, 256);
+  const int NP = mega::mega_head_pairs(VS), head_tail = mega::mega_head_tail(VS);
   std::vector<mega::MegaLayer> lay(L);
   std::vector<const bf16*> w_in(L), w_out(L), w1(L), w2(L);
   for (int l = 0; l < L; ++l) {
@@ -383,11 +383,11 @@ int setup_mega(mg_engine* e) {
                              reinterpret_cast<bf16*>(w.vt)};
   }
   if (!e->d_mega_packed) {
-    MG_TRY(e->dmalloc(&e->d_mega_packed, mega::mega_packed_bytes(L, NP)));
+    MG_TRY(e->dmalloc(&e->d_mega_packed, mega::mega_packed_bytes(L, NP, head_tail)));
     MG_TRY(e->dmalloc(&e->d_mega_layers, sizeof(mega::MegaLayer) * L));
   }
   MG_TRY(mega::mega_pack_weights(e->stream, w_in.data(), w_out.data(), w1.data(), w2.data(),
-                                 reinterpret_cast<const bf16*>(e->head_w), L, g.vocab_size, VS, NP, e->d_mega_packed));
+                                 reinterpret_cast<const bf16*>(e->head_w), L, g.vocab_size, VS, NP, head_tail, e->d_mega_packed));
   MG_CUDA_OK(cudaMemcpyAsync(e->d_mega_layers, lay.data(), sizeof(mega::MegaLayer) * L, cudaMemcpyHostToDevice, e->stream));
   MG_CUDA_OK(cudaStreamSynchronize(e->stream));
   e->mega_ok = true;
@@ -412,7 +412,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   p.tok_emb = reinterpret_cast<const bf16*>(e->tok_emb); p.pos_emb = reinterpret_cast<const bf16*>(e->pos_emb);
   p.head_b = e->head_b; p.sp = e->d_sp; p.st = e->st;
   p.n_layer = g.n_layer; p.head_dim = g.d_model / g.n_head; p.V = g.vocab_size;
-  p.VS = ceil_div(g.vocab_size, mega::kMegaCluster); p.NP = ceil_div(p.VS, 256);
+  p.VS = ceil_div(g.vocab_size, mega::kMegaCluster); p.NP = mega::mega_head_pairs(p.VS); p.head_tail = mega::mega_head_tail(p.VS);
   p.B = B; p.S = S; p.Tmax = e->max_seq; p.n_steps = e->cur_steps; p.Tvt = mega_tvt(e->max_seq);
   p.dbg_logits = dbg_logits; p.forced = forced; p.forced_stride = forced_stride;
   p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
