@@ -160,6 +160,13 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
   f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
   f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
 }
+// ex2.approx.ftz (MUFU.EX2 alone, relative error 2^-22): the arguments of the attention soft-max are <= 0 (score - running
+// maximum), exp2f() without fast-math wraps the same instruction in range handling that is dead weight here
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ---- warp-level tensor-core helpers ---------------------------------------------------------------
@@ -446,14 +453,14 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
     mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
     mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
     const float m_new = fmaxf(m_run, mb);                        // finite: key0 < len, so the quad holds a valid key
-    const float corr = exp2f(m_run - m_new);
+    const float corr = fast_exp2(m_run - m_new);
     float psum = 0.f;
     uint32_t pa[2][2];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        const float p0 = exp2f(sc[2 * u + w][0] - m_new), p1 = exp2f(sc[2 * u + w][1] - m_new);
+        const float p0 = fast_exp2(sc[2 * u + w][0] - m_new), p1 = fast_exp2(sc[2 * u + w][1] - m_new);
         psum += p0 + p1;
         pa[u][w] = pack_bf16(p0, p1);
       }
@@ -515,7 +522,7 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
     sn += __shfl_xor_sync(0xffffffffu, sn, 1);
     sn += __shfl_xor_sync(0xffffffffu, sn, 2);
     const float m_new = fmaxf(m_run, sn);
-    const float corr = exp2f(m_run - m_new), pw = exp2f(sn - m_new);
+    const float corr = fast_exp2(m_run - m_new), pw = fast_exp2(sn - m_new);
     l_run = fmaf(l_run, corr, t == 0 ? pw : 0.f);
     m_run = m_new;
 #pragma unroll
@@ -920,7 +927,7 @@ decode_mega_kernel(const MegaParams p) {
             float Lsum = 0.f, o = 0.f;
 #pragma unroll
             for (int k = 0; k < NCW; ++k) {
-              const float fw = exp2f(mw[k] - M);                            // exp2(-inf) = 0 for an idle worker
+              const float fw = fast_exp2(mw[k] - M);                        // exp2(-inf) = 0 for an idle worker
               Lsum = fmaf(lw_[k], fw, Lsum);
               o = fmaf(ow[k], fw, o);
             }
@@ -1331,6 +1338,10 @@ decode_mega_kernel(const MegaParams p) {
         if (r < S) {
           const int s = r;
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.cand, (CL - 1) * k * 8);
+          // the uniform draw depends on nothing the wait delivers: ten Philox rounds hidden behind the DSMEM latency
+          const float u01 = (cw == 0 && k != 1)
+                                ? philox_uniform(sp.seed, sp.seq_base + static_cast<uint64_t>(b0 + s), static_cast<uint32_t>(misc.nnew[s]))
+                                : 0.f;
           // every thread observes the arrival itself (greedy: only warp 0 needs the data): no CTA barrier behind the wait --
           // the local candidates became visible at the barrier above, the remote ones through the mbarrier
           if (k != 1 || cw == 0) ptx::mbar_wait_spin(&bars.cand, cand_use & 1);
@@ -1405,7 +1416,6 @@ decode_mega_kernel(const MegaParams p) {
               const float tot0 = __shfl_sync(0xffffffffu, i0, 31);
               i1 += tot0;
               const float total = __shfl_sync(0xffffffffu, i1, 31);
-              const float u01 = philox_uniform(sp.seed, sp.seq_base + static_cast<uint64_t>(b0 + s), static_cast<uint32_t>(misc.nnew[s]));
               const float target = u01 * total;
               const unsigned c0 = __ballot_sync(0xffffffffu, lane < k && i0 > target);
               const unsigned c1 = __ballot_sync(0xffffffffu, lane + 32 < k && i1 > target);
