@@ -106,6 +106,14 @@ __device__ __forceinline__ float warp_max(float v) {
 // Exact GELU (nn.GELU() default, reference api_cache.py:47; HF "gelu").
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// ex2.approx.ftz (MUFU.EX2 alone, relative error 2^-22) for the soft-max of the bf16 tensor-core attention kernels: the
+// arguments are <= 0 there, exp2f() without fast-math wraps the same instruction in range handling that costs more than the MMAs
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_GELU) return gelu_erf(v);

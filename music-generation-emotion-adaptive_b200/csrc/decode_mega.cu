@@ -160,13 +160,6 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
   f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
   f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
 }
-// ex2.approx.ftz (MUFU.EX2 alone, relative error 2^-22): the arguments of the attention soft-max are <= 0 (score - running
-// maximum), exp2f() without fast-math wraps the same instruction in range handling that is dead weight here
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ---- warp-level tensor-core helpers ---------------------------------------------------------------

@@ -789,7 +789,7 @@ encoder_attn_tc_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
       msafe[r] = (m_new == -INFINITY) ? 0.f : m_new;       // every key so far masked: keep everything at zero
-      corr[r] = exp2f(m_run[r] - msafe[r]);
+      corr[r] = fast_exp2(m_run[r] - msafe[r]);
       m_run[r] = m_new;
       l_run[r] *= corr[r];
     }
@@ -800,8 +800,8 @@ encoder_attn_tc_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__
     }
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      s[t][0] = exp2f(s[t][0] - msafe[0]); s[t][1] = exp2f(s[t][1] - msafe[0]);
-      s[t][2] = exp2f(s[t][2] - msafe[1]); s[t][3] = exp2f(s[t][3] - msafe[1]);
+      s[t][0] = fast_exp2(s[t][0] - msafe[0]); s[t][1] = fast_exp2(s[t][1] - msafe[0]);
+      s[t][2] = fast_exp2(s[t][2] - msafe[1]); s[t][3] = fast_exp2(s[t][3] - msafe[1]);
       l_run[0] += s[t][0] + s[t][1];
       l_run[1] += s[t][2] + s[t][3];
     }
