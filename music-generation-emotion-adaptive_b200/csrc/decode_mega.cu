@@ -1130,7 +1130,12 @@ decode_mega_kernel(const MegaParams p) {
               for (; i < NL; i += gn) m0 = fmaxf(m0, z[i]);
               m_t = fmaxf(m0, fmaxf(m1, m2));
             }
-            maxima[gt] = m_t;
+            // rank the maxima on UNIQUE packed keys (monotonic float key with its low 8 bits replaced by the thread index):
+            // one unsigned compare per pair, no tie-break.  The threshold is the k-th key with the index bits cleared, i.e.
+            // a float <= that thread's maximum: at least k maxima (hence >= k logits) are >= it, so the superset stays exact.
+            const uint32_t pk = (float_key(m_t) & 0xffffff00u) | static_cast<uint32_t>(gt);      // gn <= 256
+            uint32_t* pkeys = reinterpret_cast<uint32_t*>(maxima);
+            pkeys[gt] = pk;
             if (gt == 0) *g_exact = 0;
             fst();                                                          // per-thread maxima
             ptx::named_bar_sync(gbar, gn);
@@ -1138,18 +1143,16 @@ decode_mega_kernel(const MegaParams p) {
             int rk = 0, rk2 = 0;
 #pragma unroll 4
             for (int u = 0; u < gn; u += 8) {                               // gn is a multiple of 32
-              const float4 mu = *reinterpret_cast<const float4*>(maxima + u);
-              const float4 mv = *reinterpret_cast<const float4*>(maxima + u + 4);
-              rk += (mu.x > m_t) || (mu.x == m_t && u < gt);
-              rk += (mu.y > m_t) || (mu.y == m_t && u + 1 < gt);
-              rk += (mu.z > m_t) || (mu.z == m_t && u + 2 < gt);
-              rk += (mu.w > m_t) || (mu.w == m_t && u + 3 < gt);
-              rk2 += (mv.x > m_t) || (mv.x == m_t && u + 4 < gt);
-              rk2 += (mv.y > m_t) || (mv.y == m_t && u + 5 < gt);
-              rk2 += (mv.z > m_t) || (mv.z == m_t && u + 6 < gt);
-              rk2 += (mv.w > m_t) || (mv.w == m_t && u + 7 < gt);
+              const uint4 mu = *reinterpret_cast<const uint4*>(pkeys + u);
+              const uint4 mv = *reinterpret_cast<const uint4*>(pkeys + u + 4);
+              rk += (mu.x > pk) + (mu.y > pk) + (mu.z > pk) + (mu.w > pk);
+              rk2 += (mv.x > pk) + (mv.y > pk) + (mv.z > pk) + (mv.w > pk);
             }
-            if (rk + rk2 == k - 1) *reinterpret_cast<volatile float*>(g_pre) = m_t;
+            if (rk + rk2 == k - 1) {
+              const uint32_t tk = pk & 0xffffff00u;                        // inverse of float_key; keys of -inf / NaN clamp to -inf
+              const float tf = tk <= 0x007fffffu ? -INFINITY : __uint_as_float((tk & 0x80000000u) ? (tk & 0x7fffffffu) : ~tk);
+              *reinterpret_cast<volatile float*>(g_pre) = tf;
+            }
             fst();                                                          // rank among the maxima
             ptx::named_bar_sync(gbar, gn);
             fst();
@@ -1445,17 +1448,21 @@ decode_mega_kernel(const MegaParams p) {
           const int owned_elsewhere = S - (r < S ? 1 : 0);
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.tok, owned_elsewhere * 4);
           fst();                                                            // token drawn / sent (owner warp 0)
-          if (cw == 0) ptx::mbar_wait_spin(&bars.tok, tok_use & 1);
+          if (cw == 0) {
+            // the polling warp also advances the (replicated) state: the tokens are visible to it through the mbarrier
+            // (remote) / its own store (local), so ONE barrier publishes tokens and state to the other warps
+            ptx::mbar_wait_spin(&bars.tok, tok_use & 1);
+            __syncwarp();
+            if (lane < S && !misc.fin[lane]) {
+              const int s = lane;
+              misc.len[s] += 1;
+              const int n = misc.nnew[s] + 1;
+              misc.nnew[s] = n;
+              if (misc.tok[s] == sp.eos_id || n >= misc.maxnew[s]) misc.fin[s] = 1;        // api_cache.py:181
+            }
+          }
           fst();
           ++tok_use;
-          bar_compute();
-          if (ct < S && !misc.fin[ct]) {
-            const int s = ct;
-            misc.len[s] += 1;
-            const int n = misc.nnew[s] + 1;
-            misc.nnew[s] = n;
-            if (misc.tok[s] == sp.eos_id || n >= misc.maxnew[s]) misc.fin[s] = 1;          // api_cache.py:181
-          }
           bar_compute();
           stamp(step);                                                      // token published, state advanced
         }
