@@ -1203,17 +1203,37 @@ decode_mega_kernel(const MegaParams p) {
             const int c = *g_cnt;
             overflow = c > kCandCap || c < k;
             if (!overflow) {
-              for (int j = gt; j < c; j += gn) {
-                const uint2 mine = clist[j];
+              const int lg = (c <= 64 && gn >= 128) ? (gn >= 256 ? 2 : 1) : 0;   // 4 / 2 / 1 threads per candidate (uniform)
+              if (lg) {
+                // c <= 64 candidates, gn >> lg == 64 slots: the inner loop is split over the 2 / 4 neighbouring lanes of a
+                // candidate and the partial ranks are added by shuffle (the loop is a pure latency chain of c loads)
+                const int j = gt >> lg, part = gt & ((1 << lg) - 1);
+                const int chunk = (c + (1 << lg) - 1) >> lg, i0 = part * chunk, i1 = min(c, i0 + chunk);
+                const uint2 mine = clist[min(j, c - 1)];
                 const float mv = __uint_as_float(mine.x);
                 int rank_j = 0;
 #pragma unroll 4
-                for (int i = 0; i < c; ++i) {
+                for (int i = i0; i < i1; ++i) {
                   const uint2 o = clist[i];
                   const float ov = __uint_as_float(o.x);
                   rank_j += (ov > mv) || (ov == mv && o.y < mine.y);
                 }
-                if (rank_j < k) gl[rank_j] = mine;            // sorted: value descending, index ascending
+                rank_j += __shfl_xor_sync(0xffffffffu, rank_j, 1);
+                if (lg == 2) rank_j += __shfl_xor_sync(0xffffffffu, rank_j, 2);
+                if (part == 0 && j < c && rank_j < k) gl[rank_j] = mine;   // sorted: value descending, index ascending
+              } else {
+                for (int j = gt; j < c; j += gn) {
+                  const uint2 mine = clist[j];
+                  const float mv = __uint_as_float(mine.x);
+                  int rank_j = 0;
+#pragma unroll 4
+                  for (int i = 0; i < c; ++i) {
+                    const uint2 o = clist[i];
+                    const float ov = __uint_as_float(o.x);
+                    rank_j += (ov > mv) || (ov == mv && o.y < mine.y);
+                  }
+                  if (rank_j < k) gl[rank_j] = mine;          // sorted: value descending, index ascending
+                }
               }
             }
             ptx::named_bar_sync(gbar, gn);
