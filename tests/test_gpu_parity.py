@@ -476,20 +476,23 @@ def test_persistent_kernel_ragged_max_new_eos_and_fallbacks():
     multi.close()
 
 
-def test_persistent_kernel_sampler_distribution_chi_square():
+@pytest.mark.parametrize("B,iters", [(16, 640), (64, 160), (128, 80)])
+def test_persistent_kernel_sampler_distribution_chi_square(B, iters):
     """The in-kernel sampler (local top-k -> owner merge -> Philox) draws from the reference's top-k softmax:
-    one decode step from identical prompts, 4096 rows x 16 seeds, against the oracle's distribution."""
+    one decode step from identical prompts, 10240 draws, against the oracle's distribution -- at 1, 2 and 4
+    sequences per cluster (B = 16 / 64 / 128: 256, 128 and 64 sampler threads per sequence, which take different
+    paths through the candidate ranking)."""
     geo = mg.GEOMETRIES["train_large"]
     ck = checkpoint("train_large", 0)
     prompt = mg.encode(ck["vocab"], mg.synthetic_prompts(ck["vocab"], 1, seed=0)[0])
     ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head, torch.float64)
-    e = engine("train_large", 0, "bf16", max_batch=64, max_seq=1088)
+    e = engine("train_large", 0, "bf16", max_batch=B, max_seq=1088)
     lg = e.step_logits([prompt], None, 1)[0, 0]                   # the engine's own bf16 logits of that step
     probs = gpt_kv.topk_probs(torch.from_numpy(lg.astype(np.float64)), 1.0, 40).numpy()
     want_fp64 = gpt_kv.topk_probs(gpt_kv.teacher_forced_logits(ora, prompt, [], 1)[0], 1.0, 40).numpy()
     assert np.abs(probs - want_fp64).max() < 2e-2                 # bf16 logits give (nearly) the reference distribution
     counts = np.zeros(geo.vocab_size, np.int64)
-    for it in range(160):
-        out = e.generate([prompt] * 64, 1, 1.0, 40, seed=1000 + it)
+    for it in range(iters):
+        out = e.generate([prompt] * B, 1, 1.0, 40, seed=1000 + it)
         counts += np.bincount([o[-1] for o in out], minlength=geo.vocab_size)
     assert _chi_square_p(counts, probs / probs.sum()) > 1e-3
