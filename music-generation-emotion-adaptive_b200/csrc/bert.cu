@@ -86,6 +86,7 @@ namespace {
 int bgemm(mg_bert* b, const bf16* A, const CUtensorMap* tmA, const bf16* W, const WMaps* wm, int M, int N, int K,
           const GemmEpilogue& epi) {
   if (b->use_tc && M >= 32) {
+    if (gemm_use_pair(M, N)) return launch_gemm_tc_pair(b->stream, tmA, &wm->m[bn_index(128)], M, N, K, epi);
     const int bn = pick_gemm_bn(M, N);
     return launch_gemm_tc(b->stream, tmA, &wm->m[bn_index(bn)], M, N, K, epi, bn);
   }

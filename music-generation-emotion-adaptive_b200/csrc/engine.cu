@@ -151,6 +151,7 @@ int gemm(mg_engine* e, const void* A, const CUtensorMap* tmA, const void* W, con
   }
   if (out_f32_typed) epi.out_f32 = out_f32_typed;
   if (std::is_same<T, bf16>::value && e->use_tc && M >= 32 && tmA && wm && wm->ok) {
+    if (gemm_use_pair(M, N)) return launch_gemm_tc_pair(e->stream, tmA, &wm->m[bn_index(128)], M, N, K, epi);
     const int bn = pick_gemm_bn(M, N);
     return launch_gemm_tc(e->stream, tmA, &wm->m[bn_index(bn)], M, N, K, epi, bn);
   }
@@ -1070,12 +1071,14 @@ int mg_test_gemm_bf16(int device, const float* A, const float* W, const float* b
     }
     MG_TRY(launch_convert<bf16>(nullptr, dA32, dA, static_cast<size_t>(M) * K));
     MG_TRY(launch_convert<bf16>(nullptr, dW32, dW, static_cast<size_t>(N) * K));
-    const int bn = pick_gemm_bn(M, N);
+    const bool pair = gemm_use_pair(M, N);
+    const int bn = pair ? 128 : pick_gemm_bn(M, N);
     CUtensorMap ta, tw;
     MG_TRY(make_tmap_bf16_2d(&ta, dA, Mp, K, kGemmBM));
     MG_TRY(make_tmap_bf16_2d(&tw, dW, N, K, bn));
     GemmEpilogue epi; epi.bias = dbias; epi.act = act; epi.out_f32 = dC; epi.ld_out = N;
-    MG_TRY(launch_gemm_tc(nullptr, &ta, &tw, M, N, K, epi, bn));
+    if (pair) MG_TRY(launch_gemm_tc_pair(nullptr, &ta, &tw, M, N, K, epi));
+    else MG_TRY(launch_gemm_tc(nullptr, &ta, &tw, M, N, K, epi, bn));
     MG_CUDA_OK(cudaDeviceSynchronize());
     MG_CUDA_OK(cudaMemcpy(C, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost));
     return MG_OK;

@@ -30,6 +30,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int N, int K,
                    const GemmEpilogue& epi, int bn);
 int pick_gemm_bn(int M, int N);
+// CTA-pair (cta_group::2) kernel for large-M GEMMs with N % 256 == 0: 256 x 256 tiles per cluster of two CTAs.
+// `tmap_w_half` is the weight map with a 128-row box (each CTA loads half of the 256 weight rows of a tile).
+bool gemm_use_pair(int M, int N);
+int launch_gemm_tc_pair(cudaStream_t stream, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w_half, int M, int N, int K,
+                        const GemmEpilogue& epi);
 
 // Weight tensor maps for every compiled block-N (32 / 64 / 128 / 256), built once per weight matrix.
 struct WMaps {

@@ -39,7 +39,7 @@ def engine(geo_name, seed, dtype, max_batch=8, max_seq=None):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K,act", [(128, 128, 64, 0), (64, 768, 256, 0), (200, 260, 256, 1), (33, 8324, 256, 0),
                                        (384, 1024, 256, 1), (130, 256, 1024, 2), (1024, 2304, 768, 0), (5, 40, 64, 0),
-                                       (4146, 3072, 768, 1), (16384, 768, 3072, 0), (5000, 2312, 256, 2)])
+                                       (4146, 3072, 768, 1), (16384, 768, 3072, 0), (5000, 2312, 256, 2), (6528, 768, 328, 1)])
 def test_tc_gemm_matches_fp32_reference_on_bf16_inputs(M, N, K, act):
     g = torch.Generator().manual_seed(M * 7 + N)
     A = torch.randn(M, K, generator=g)
