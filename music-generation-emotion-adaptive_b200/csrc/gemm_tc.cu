@@ -223,9 +223,12 @@ __device__ __forceinline__ void epi_chunk_coalesced(const GemmEpilogue& epi, flo
       v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
     }
   }
-  if (epi.act != ACT_NONE) {
+  if (epi.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], epi.act);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_poly(v[j]);
+  } else if (epi.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
   if (epi.resid_bf16) {
     uint4 u[4];
