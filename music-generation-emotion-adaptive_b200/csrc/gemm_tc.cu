@@ -211,15 +211,33 @@ __device__ __forceinline__ bool epi_can_coalesce(const GemmEpilogue& epi) {
   return epi.out_bf16 != nullptr && epi.out_f32 == nullptr && epi.resid_f32 == nullptr;
 }
 
+// Bias (8 x float4, identical in every lane) and residual (coalesced layout) of a chunk: issued between tcgen05.ld and
+// tcgen05.wait::ld so that their latency runs in parallel with the accumulator read instead of behind it.
+__device__ __forceinline__ void epi_prefetch(const GemmEpilogue& epi, bool fast, int row_base, int lane, int M, int col0,
+                                             float4 (&bb)[8], uint4 (&u)[4]) {
+  const size_t ld = static_cast<size_t>(epi.ld_out);
+  const int sub = lane >> 2, piece = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    bb[j] = (fast && epi.bias) ? __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = row_base + 8 * i + sub;
+    u[i] = (fast && epi.resid_bf16 && rr < M)
+               ? *reinterpret_cast<const uint4*>(epi.resid_bf16 + static_cast<size_t>(rr) * ld + col0 + 8 * piece)
+               : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // v: this lane's row (row_base + lane), columns col0 .. col0 + 31, raw accumulators.  All 32 lanes must call.
-__device__ __forceinline__ void epi_chunk_coalesced(const GemmEpilogue& epi, float (&v)[32], int row_base, int lane, int M,
-                                                    int col0, uint8_t* stg) {
+__device__ __forceinline__ void epi_chunk_coalesced(const GemmEpilogue& epi, float (&v)[32], const float4 (&bb)[8],
+                                                    const uint4 (&u)[4], int row_base, int lane, int M, int col0, uint8_t* stg) {
   const size_t ld = static_cast<size_t>(epi.ld_out);
   const int sub = lane >> 2, piece = lane & 3;       // coalesced layout: rows 8 i + sub, 16-byte piece of the 64-byte row
-  if (epi.bias) {
+  if (epi.bias) {                                     // bb / u: fetched by epi_prefetch ahead of the accumulator wait
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + j));
+      const float4 b4 = bb[j >> 2];
       v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
     }
   }
@@ -231,13 +249,6 @@ __device__ __forceinline__ void epi_chunk_coalesced(const GemmEpilogue& epi, flo
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
   if (epi.resid_bf16) {
-    uint4 u[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = row_base + 8 * i + sub;
-      u[i] = rr < M ? *reinterpret_cast<const uint4*>(epi.resid_bf16 + static_cast<size_t>(rr) * ld + col0 + 8 * piece)
-                    : make_uint4(0u, 0u, 0u, 0u);
-    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (8 * i + sub) * kEpiPitch + 16 * piece) = u[i];
     __syncwarp();
@@ -377,14 +388,18 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c * 32, r);
-        ptx::tmem_ld_wait();
         const int col0 = n0 + c * 32;
+        const bool fast = coalesce && col0 + 32 <= N;               // warp-uniform (col0 is a multiple of 32)
+        float4 bb[8];
+        uint4 ru[4];
+        epi_prefetch(epi, fast, m0 + quarter * 32, lane, M, col0, bb, ru);
+        ptx::tmem_ld_wait();
         if (col0 >= N) continue;                                    // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (coalesce && col0 + 32 <= N && (col0 % 8 == 0)) {        // warp-uniform: all lanes take part in the transpose
-          epi_chunk_coalesced(epi, v, m0 + quarter * 32, lane, M, col0, stg);
+        if (fast) {                                                 // all lanes take part in the transpose
+          epi_chunk_coalesced(epi, v, bb, ru, m0 + quarter * 32, lane, M, col0, stg);
           continue;
         }
         if (!row_ok) continue;
@@ -572,14 +587,18 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c * 32, r);
-        ptx::tmem_ld_wait();
         const int col0 = n0 + c * 32;
+        const bool fast = coalesce && col0 + 32 <= N;               // warp-uniform (col0 is a multiple of 32)
+        float4 bb[8];
+        uint4 ru[4];
+        epi_prefetch(epi, fast, m0 + quarter * 32, lane, M, col0, bb, ru);
+        ptx::tmem_ld_wait();
         if (col0 >= N) continue;                                    // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (coalesce && col0 + 32 <= N && (col0 % 8 == 0)) {        // warp-uniform: all lanes take part in the transpose
-          epi_chunk_coalesced(epi, v, m0 + quarter * 32, lane, M, col0, stg);
+        if (fast) {                                                 // all lanes take part in the transpose
+          epi_chunk_coalesced(epi, v, bb, ru, m0 + quarter * 32, lane, M, col0, stg);
           continue;
         }
         if (!row_ok) continue;
@@ -639,7 +658,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(lead_empty0 + buf * 8);   // the leader's tmem_empty[buf]
+      if (lane == 0) ptx::mbar_arrive_cluster_relaxed(lead_empty0 + buf * 8);   // the leader's tmem_empty[buf]
     }
   }
 

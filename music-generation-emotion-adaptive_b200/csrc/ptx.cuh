@@ -162,6 +162,11 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {      // shared::cluster address (mapa)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Same without memory ordering (no MEMBAR / ERRBAR in front of it): for hand-offs whose data is ordered by other means, e.g.
+// "this TMEM buffer has been read" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync), not for published global stores.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns; thread t of the warp gets lane
 // (taddr.lane + t).  A warp may only touch lanes [32*(warp_id%4), 32*(warp_id%4)+32).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
