@@ -71,6 +71,12 @@ struct mg_bert {
 
   uint64_t h2d = 0, d2h = 0, launches0 = 0;
 
+  // the ~50 launches of a pass replayed as ONE CUDA graph per (N, T) shape (MG_BERT_GRAPH=0: eager launches)
+  bool use_graph = true;
+  cudaGraphExec_t graph = nullptr;
+  int graph_N = 0, graph_T = 0;
+  uint64_t graph_kernels = 0;
+
   template <typename P> int dmalloc(P** p, size_t bytes) {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
@@ -119,6 +125,30 @@ int bert_forward(mg_bert* b) {
   { GemmEpilogue epi; epi.bias = b->bcls; epi.out_f32 = b->logits; epi.ld_out = g.num_labels;
     MG_TRY(bgemm(b, b->cls2, &b->tm_cls2, b->wcls, &b->m_cls, N, g.num_labels, d, epi)); }
   MG_TRY(launch_argmax_rows(b->stream, b->logits, N, g.num_labels, b->labels));
+  return MG_OK;
+}
+
+int bert_run(mg_bert* b) {
+  if (!b->use_graph) return bert_forward(b);
+  if (!b->graph || b->graph_N != b->cur_N || b->graph_T != b->cur_T) {
+    if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+    cudaGraph_t gr = nullptr;
+    MG_CUDA_OK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+    const uint64_t before = g_kernel_launches.load();
+    const int rc = bert_forward(b);
+    b->graph_kernels = g_kernel_launches.load() - before;
+    g_kernel_launches.fetch_sub(b->graph_kernels);            // capture launches nothing; replays are counted
+    cudaError_t ce = cudaStreamEndCapture(b->stream, &gr);
+    if (rc != MG_OK) { if (gr) cudaGraphDestroy(gr); return rc; }
+    if (ce != cudaSuccess) return fail(MG_E_CUDA, std::string("classifier graph capture: ") + cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&b->graph, gr, 0);
+    cudaGraphDestroy(gr);
+    if (ce != cudaSuccess) return fail(MG_E_CUDA, std::string("classifier graph instantiate: ") + cudaGetErrorString(ce));
+    b->graph_N = b->cur_N;
+    b->graph_T = b->cur_T;
+  }
+  MG_CUDA_OK(cudaGraphLaunch(b->graph, b->stream));
+  g_kernel_launches.fetch_add(b->graph_kernels, std::memory_order_relaxed);
   return MG_OK;
 }
 
@@ -218,6 +248,8 @@ int mg_bert_create(const mg_bert_geometry* geo, int device, int max_tokens, mg_b
   b->max_tokens = ceil_div(max_tokens, 128) * 128;
   const char* env_gemm = std::getenv("MG_GEMM");
   b->use_tc = !(env_gemm && std::strcmp(env_gemm, "simt") == 0);
+  const char* env_graph = std::getenv("MG_BERT_GRAPH");
+  b->use_graph = !(env_graph && std::atoi(env_graph) == 0);
   b->launches0 = g_kernel_launches.load();
   auto body = [&]() -> int {
     MG_CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
@@ -290,6 +322,7 @@ int mg_bert_create(const mg_bert_geometry* geo, int device, int max_tokens, mg_b
 void mg_bert_destroy(mg_bert* b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : b->allocs) cudaFree(p);
   if (b->h_arena) cudaFreeHost(b->h_arena);
@@ -387,7 +420,7 @@ int mg_bert_run(mg_bert* b) {
   std::lock_guard<std::mutex> lk(b->mu);
   MG_CUDA_OK(cudaSetDevice(b->device));
   if (!b->uploaded) return fail(MG_E_STATE, "mg_bert_run before mg_bert_upload");
-  return bert_forward(b);
+  return bert_run(b);
 }
 
 int mg_bert_download(mg_bert* b, float* logits_out, int32_t* label_out) {
@@ -402,7 +435,7 @@ int mg_classify(mg_bert* b, const int32_t* ids, const uint8_t* mask, int N, int 
   std::lock_guard<std::mutex> lk(b->mu);
   MG_CUDA_OK(cudaSetDevice(b->device));
   MG_TRY(bert_upload_impl(b, ids, mask, N, T));
-  MG_TRY(bert_forward(b));
+  MG_TRY(bert_run(b));
   return bert_download_impl(b, logits_out, label_out);
 }
 
