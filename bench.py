@@ -112,9 +112,9 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic_bytes():
     """DRAM bytes (read + write) per launch of the persistent decode kernel from the committed `ncu --set full`
-    capture of this same workload (profiles/r1i_decode_mega_full_raw.csv); None when the file is missing."""
+    capture of this same workload (profiles/r1j_decode_mega_full_raw.csv); None when the file is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1i_decode_mega_full_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r1j_decode_mega_full_raw.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -297,7 +297,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": ncu_traffic_bytes(), "traffic_note": "DRAM read+write bytes per launch (= per job), ncu --set full, profiles/r1i_decode_mega_full_raw.csv",
+                     "traffic": ncu_traffic_bytes(), "traffic_note": "DRAM read+write bytes per launch (= per job), ncu --set full, profiles/r1j_decode_mega_full_raw.csv",
                      "peak_source": peak_src,
                      "kernel": ("decode_mega_kernel: ONE persistent cluster launch per job runs all 1024 decode steps "
                                 "(embedding, 4 blocks, head, top-k sampler); achieved = algorithmic bytes of the decode "

@@ -71,10 +71,11 @@ struct mg_bert {
 
   uint64_t h2d = 0, d2h = 0, launches0 = 0;
 
-  // the ~50 launches of a pass replayed as ONE CUDA graph per (N, T) shape (MG_BERT_GRAPH=0: eager launches)
+  // the ~50 launches of a pass replayed as ONE CUDA graph once a (N, T) shape has been seen three times in a row
+  // (MG_BERT_GRAPH=0: always eager launches)
   bool use_graph = true;
   cudaGraphExec_t graph = nullptr;
-  int graph_N = 0, graph_T = 0;
+  int graph_N = 0, graph_T = 0, shape_runs = 0;
   uint64_t graph_kernels = 0;
 
   template <typename P> int dmalloc(P** p, size_t bytes) {
@@ -130,8 +131,15 @@ int bert_forward(mg_bert* b) {
 
 int bert_run(mg_bert* b) {
   if (!b->use_graph) return bert_forward(b);
-  if (!b->graph || b->graph_N != b->cur_N || b->graph_T != b->cur_T) {
+  if (b->graph_N != b->cur_N || b->graph_T != b->cur_T) {       // new shape: start counting again
     if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+    b->graph_N = b->cur_N;
+    b->graph_T = b->cur_T;
+    b->shape_runs = 0;
+  }
+  // capture + instantiate costs tens of milliseconds: only a shape that keeps coming back (third pass on) is worth it
+  if (!b->graph && ++b->shape_runs < 3) return bert_forward(b);
+  if (!b->graph) {
     cudaGraph_t gr = nullptr;
     MG_CUDA_OK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
     const uint64_t before = g_kernel_launches.load();
@@ -144,8 +152,6 @@ int bert_run(mg_bert* b) {
     ce = cudaGraphInstantiate(&b->graph, gr, 0);
     cudaGraphDestroy(gr);
     if (ce != cudaSuccess) return fail(MG_E_CUDA, std::string("classifier graph instantiate: ") + cudaGetErrorString(ce));
-    b->graph_N = b->cur_N;
-    b->graph_T = b->cur_T;
   }
   MG_CUDA_OK(cudaGraphLaunch(b->graph, b->stream));
   g_kernel_launches.fetch_add(b->graph_kernels, std::memory_order_relaxed);
