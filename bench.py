@@ -267,7 +267,7 @@ def main():
     for i in range(args.steps):
         out = eng.generate(prompts, NEW_TOKENS, TEMPERATURE, TOP_K, eos_id=-1, seed=i, seq_index_base=rank * BATCH)
         if world > 1:
-            mg.gather_token_lists(out, BATCH * world)             # the only exchange of the path: final token gather
+            mg.gather_token_lists(out, BATCH * world, as_arrays=True)   # the only exchange of the path: final token gather
     barrier()
     e2e_s = time.perf_counter() - e0
     st1 = eng.stats()

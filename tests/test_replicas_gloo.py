@@ -28,6 +28,8 @@ def _worker(rank, world, port, n_total, ret):
         mine = mg.shard(prompts, rank, world)
         local = [_fake_generate(p) for p in mine]
         full = mg.gather_token_lists(local, n_total)
+        arrs = mg.gather_token_lists(local, n_total, as_arrays=True)      # same rows as int32 arrays (bench e2e path)
+        assert [a.tolist() for a in arrs] == full and all(str(a.dtype) == "int32" for a in arrs)
         ret[rank] = full
     finally:
         dist.destroy_process_group()
