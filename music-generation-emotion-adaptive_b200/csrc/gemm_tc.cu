@@ -13,6 +13,10 @@
 //                 tcgen05.commit releases the smem stage and finally signals the epilogue
 //   warps 2..5  : epilogue -- tcgen05.ld 32x32b (each warp owns one 32-lane TMEM quarter), fused
 //                 bias / exact-GELU / ReLU / residual, vectorised global stores
+//
+// Large M (classifier, long prefill) runs one of two persistent kernels instead (further down): one CTA per SM looping over
+// 128 x BN tiles with two TMEM accumulator buffers, or -- N % 256 == 0 -- a CTA PAIR (tcgen05.mma.cta_group::2) on 256 x 256
+// tiles.  Both share the coalesced bf16 epilogue (warp transpose through padded shared memory, polynomial erf GELU).
 #include "gemm_tc.cuh"
 
 #include <cstdlib>
