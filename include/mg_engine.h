@@ -115,6 +115,13 @@ void* mg_engine_stream(mg_engine* e);
 int mg_step_logits(mg_engine* e, const int32_t* prompt_ids, const int32_t* prompt_offsets, int B,
                    const int32_t* forced_ids, int n_steps, float* logits_out);
 
+/* The same run, keeping only the steps listed in want_steps[n_want] (distinct, each in [0, n_steps)):
+ * logits_out is [n_want][B][vocab], block i = step want_steps[i].  For parity checks at the cache lengths
+ * of BASELINE configs 3 and 4 (1030 / 4352 positions), where all steps x batch x vocab would be gigabytes. */
+int mg_step_logits_at(mg_engine* e, const int32_t* prompt_ids, const int32_t* prompt_offsets, int B,
+                      const int32_t* forced_ids, int n_steps, const int32_t* want_steps, int n_want,
+                      float* logits_out);
+
 /* Recompute mode: the no-cache twin `GPT.forward` + `sample` of generate_music/generate.py:25-61
  * (post-LN, ReLU, unmasked, true positions, whole sequence recomputed every step). Same arguments
  * as mg_generate; prompt + max_new_tokens must fit the position table. */
@@ -135,6 +142,11 @@ int mg_engine_stats(mg_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes
 /* Milliseconds of the last mg_run measured with CUDA events on the engine stream
  * (total, prefill part, decode part) and the number of decode steps it executed. */
 int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* decode_ms, int* steps);
+
+/* Which decode path served the last mg_run / mg_generate / mg_step_logits of this engine: 0 = step graph (one launch per
+ * kernel and step), 1 = persistent cluster kernel (decode_mega.cu), 2 = weight-stationary flow kernel (decode_flow.cu).
+ * Tests assert that parity was checked on the path the benchmark runs. */
+int mg_last_decode_path(mg_engine* e);
 
 /* ---- classifier ------------------------------------------------------------------------------ */
 typedef struct mg_bert_geometry {

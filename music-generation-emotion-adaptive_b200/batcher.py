@@ -18,6 +18,7 @@ the whole generation; a cluster stops early when all of its sequences have hit E
 from __future__ import annotations
 
 import itertools
+import os
 import threading
 import time
 from concurrent.futures import Future
@@ -35,11 +36,14 @@ class _Request:
 class RequestBatcher:
     """Thread-safe front end: ``submit`` returns a Future, ``generate`` blocks.  One worker thread drives the engine."""
 
-    def __init__(self, engine, max_batch: int = 64, max_wait_ms: float = 2.0, seed: int = 0):
+    def __init__(self, engine, max_batch: int = 64, max_wait_ms: float = 2.0, seed: Optional[int] = None):
+        """``seed=None`` (default): a fresh 64-bit Philox key per batcher, so outputs do not repeat after a process
+        restart (the reference samples from torch's global RNG); requests of one batcher never share a stream
+        (sequence index = a running request counter)."""
         if max_batch < 1:
             raise ValueError("max_batch must be positive")
         self.engine, self.max_batch, self.max_wait = engine, int(max_batch), float(max_wait_ms) * 1e-3
-        self._seed = seed
+        self._seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
         self._cv = threading.Condition()
         self._queue: List[_Request] = []
         self._closed = False
@@ -105,19 +109,32 @@ class RequestBatcher:
                 self.batches.append(len(batch))
                 for r, o in zip(batch, out):
                     r.future.set_result(o)
-            except BaseException as e:                     # KeyError / RuntimeError / ValueError of the engine call
-                if len(batch) == 1:
-                    batch[0].future.set_exception(e)
+            except (ValueError, RuntimeError, KeyError) as e:   # argument / prompt validation of the engine call
+                if len(batch) == 1 or _is_device_failure(e):
+                    for r in batch:                          # a CUDA error or OOM fails the whole batch: no serial re-runs
+                        r.future.set_exception(e)
                 else:
-                    # one bad request (e.g. a prompt longer than the position table) must not fail its neighbours
-                    for r in batch:
+                    # one bad request (e.g. a prompt longer than the position table) must not fail its neighbours;
+                    # request i keeps the Philox sequence index base + i it would have had inside the batch
+                    for i, r in enumerate(batch):
                         try:
                             o = self.engine.generate([r.prompt], [r.max_new], temperature, top_k, eos_id=eos_id,
-                                                     seed=self._seed, seq_index_base=base)[0]
+                                                     seed=self._seed, seq_index_base=base + i)[0]
                             r.future.set_result(o)
-                        except BaseException as e1:
+                        except (ValueError, RuntimeError, KeyError) as e1:
                             r.future.set_exception(e1)
                     self.batches.extend([1] * len(batch))
+            except BaseException as e:                       # MemoryError, KeyboardInterrupt, ...: propagate to every caller
+                for r in batch:
+                    r.future.set_exception(e)
+                if not isinstance(e, Exception):
+                    raise
+
+
+def _is_device_failure(e: BaseException) -> bool:
+    """MG_E_CUDA (-4) / MG_E_OOM (-5) / MG_E_STATE (-6) as re-raised by engine._check: not a property of one request."""
+    msg = str(e)
+    return isinstance(e, MemoryError) or any(f"[mg status {c}]" in msg for c in (-4, -5, -6))
 
 
 def stats(batcher: RequestBatcher) -> Dict[str, float]:

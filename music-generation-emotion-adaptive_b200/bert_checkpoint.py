@@ -113,19 +113,43 @@ def make_bert_state_dict(geo: BertGeometry = DISTILBERT_BASE, seed: int = 0, wit
 def merge_lora_state_dict(sd: Dict[str, torch.Tensor], alpha: float = LORA_ALPHA, r: int = LORA_R) -> Dict[str, torch.Tensor]:
     """Fold ``*.lora_A.weight`` / ``*.lora_B.weight`` into their base weights; returns plain HF keys.
 
-    Also accepts PEFT's saved adapter spelling ``base_model.model.<name>.lora_A.weight`` and the
-    wrapped base spelling ``<name>.base_layer.weight``.
+    Accepts every spelling the reference's load path can produce (emotion_analysis/modeling.py:14-21: a base model wrapped
+    by ``PeftModel.from_pretrained``; the adapter was trained with ``TaskType.SEQ_CLS``, Scripts/finetuneDistillBert.ipynb:790-795,
+    so PEFT also saves the two classification heads as ``modules_to_save``):
+      * adapter file on disk:      ``base_model.model.<m>.lora_A.weight``, ``base_model.model.classifier.weight``
+      * live ``PeftModel.state_dict()``: ``base_model.model.<m>.base_layer.weight``, ``<m>.lora_A.default.weight``,
+        ``classifier.original_module.weight`` (the UNTRAINED base head) and ``classifier.modules_to_save.default.weight``
+        (the fine-tuned head)
+      * a plain dict merge ``{**base, **adapter}`` or ``{**adapter, **base}``: the adapter's head wins in both orders.
+    Priority for one target key: modules_to_save > adapter-file spelling (had the ``base_model.model.`` prefix) > plain key;
+    ``original_module`` entries are dropped.
     """
     clean: Dict[str, torch.Tensor] = {}
+    rank: Dict[str, int] = {}
     loras: Dict[str, Dict[str, torch.Tensor]] = {}
-    for k, v in sd.items():
-        k = k.replace("base_model.model.", "").replace(".base_layer.", ".").replace(".default.", ".")
+    for k0, v in sd.items():
+        k = k0
+        prio = 0
+        if k.startswith("base_model.model."):
+            k = k[len("base_model.model."):]
+            prio = 1
+        if ".original_module." in k:
+            continue                                         # the frozen copy of a modules_to_save head
+        if ".modules_to_save." in k:
+            head, tail = k.split(".modules_to_save.", 1)     # tail = "<adapter>.weight" or "weight"
+            k = head + "." + tail.split(".")[-1]
+            prio = 2
+        k = k.replace(".base_layer.", ".")
+        for ab in ("lora_A", "lora_B"):                      # "<m>.lora_A.<adapter>.weight" -> "<m>.lora_A.weight"
+            if f".{ab}." in k:
+                k = k.split(f".{ab}.")[0] + f".{ab}.weight"
         if k.endswith(".lora_A.weight"):
             loras.setdefault(k[: -len(".lora_A.weight")], {})["A"] = v
         elif k.endswith(".lora_B.weight"):
             loras.setdefault(k[: -len(".lora_B.weight")], {})["B"] = v
-        else:
+        elif k not in clean or prio >= rank[k]:
             clean[k] = v
+            rank[k] = prio
     for base, ab in loras.items():
         if "A" not in ab or "B" not in ab:
             raise KeyError(f"incomplete LoRA pair for {base}")

@@ -1018,8 +1018,9 @@ decode_mega_kernel(const MegaParams p) {
                   for (int e = 0; e < 2; ++e)
                     if (fs + e < S) logits[(fs + e) * NL + lr] = ok ? (acc[t][h8 * 2 + e] + hbv[t][h8]) * inv_temp : -INFINITY;
                 }
-              if (p.dbg_logits) {                                            // parity / debug path only (mg_step_logits)
-                float* dl = p.dbg_logits + (static_cast<size_t>(step) * p.B + b0 + fs) * p.V + v_lo + lr0;
+              const int dslot = !p.dbg_logits ? -1 : (p.dbg_slot ? p.dbg_slot[step] : step);   // mg_step_logits_at: selected steps only
+              if (dslot >= 0) {                                              // parity / debug path only (mg_step_logits)
+                float* dl = p.dbg_logits + (static_cast<size_t>(dslot) * p.B + b0 + fs) * p.V + v_lo + lr0;
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
 #pragma unroll
@@ -1058,11 +1059,12 @@ decode_mega_kernel(const MegaParams p) {
           }
         }
         bar_compute();
-        if (p.dbg_logits && p.head_tail && ct < 64) {                        // parity / debug path: raw logits of the tail rows
+        const int dslot_t = !p.dbg_logits ? -1 : (p.dbg_slot ? p.dbg_slot[step] : step);
+        if (dslot_t >= 0 && p.head_tail && ct < 64) {         // parity / debug path: raw logits of the tail rows
           const int lr = 256 * p.NP + ct, vr = r * p.VS + lr;
           if (lr < p.VS && vr < p.V)
             for (int s = 0; s < S; ++s)
-              p.dbg_logits[(static_cast<size_t>(step) * p.B + b0 + s) * p.V + vr] = logits[s * NL + lr] * sp.temperature;
+              p.dbg_logits[(static_cast<size_t>(dslot_t) * p.B + b0 + s) * p.V + vr] = logits[s * NL + lr] * sp.temperature;
         }
         stamp(step);                                                        // head done
 

@@ -47,6 +47,7 @@ struct MegaParams {
   int early_exit;                     // EOS enabled: a cluster stops as soon as all of its sequences have finished
   // parity/debug (mg_step_logits): raw logits [n_steps][B][V] and teacher-forced next tokens [B][forced_stride]
   float* dbg_logits;
+  const int32_t* dbg_slot;            // optional [n_steps]: row block of dbg_logits for each step, -1 = not kept
   const int32_t* forced;
   int forced_stride;
   // optional phase timeline of one step (globaltimer ns), written by cluster 0 / CTA 0: [64] entries

@@ -20,11 +20,13 @@
 #include <cstring>
 #include <mutex>
 #include <type_traits>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "decode_flow.cuh"
 #include "decode_mega.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -104,6 +106,20 @@ struct mg_engine {
   unsigned long long* d_prof = nullptr;
   int mega_clusters2 = 0, mega_clusters4 = 0;   // co-resident clusters for <= 2 / <= 4 sequences per cluster
 
+  // weight-stationary flow kernel (decode_flow.cu): bf16, d_model 256, d_ff 1024, <= 64 sequences
+  bool flow_candidate = false, flow_ok = false, use_flow = true, last_run_flow = false;
+  std::map<std::string, float*> masters;     // fp32 device copies of the matrices, kept until the flow weights are packed
+  flow::FlowPlan* flow_plan = nullptr;
+  flow::FlowExchange flow_xc{};
+  uint8_t* d_flow_packed = nullptr;
+  flow::SmProgram* d_flow_prog = nullptr;
+  flow::FlowLayer* d_flow_layers = nullptr;
+  std::vector<flow::FlowLayer> flow_layers;
+  int32_t* d_flow_status = nullptr;
+  int32_t* h_flow_status = nullptr;           // pinned
+  unsigned long long* d_flow_prof = nullptr;
+  int flow_tcap = 0, n_sm = 0;
+
   cudaGraphExec_t graph = nullptr;
   int graph_B = -1;
   uint64_t graph_kernels = 0;          // kernels inside the captured decode step (counted per replay)
@@ -131,8 +147,16 @@ struct mg_engine {
 namespace {
 
 bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits = nullptr,
-                     const int32_t* forced = nullptr, int forced_stride = 0);
+                     const int32_t* forced = nullptr, int forced_stride = 0, const int32_t* dbg_slot = nullptr);
+bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits = nullptr,
+                     const int32_t* forced = nullptr, int forced_stride = 0, const int32_t* dbg_slot = nullptr);
+// The persistent decode paths, best first: the weight-stationary flow kernel (decode_flow.cu), then the cluster kernel
+// (decode_mega.cu).  Returns false when neither can serve the call (the caller falls back to the step-graph path).
+bool run_decode_persistent(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits = nullptr,
+                           const int32_t* forced = nullptr, int forced_stride = 0, const int32_t* dbg_slot = nullptr);
+int persistent_status(mg_engine* e);          // after a stream sync: MG_E_CUDA if the flow kernel's watchdog fired
 int setup_mega(mg_engine* e);
+int setup_flow(mg_engine* e);
 
 int decode_nsplit(const mg_engine* e, int B) {
   int n = ceil_div(2 * 148, B);
@@ -309,7 +333,7 @@ int run_impl(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t se
   MG_TRY(prefill<T>(e));
   MG_CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
   int mrc = MG_OK;
-  e->last_run_mega = std::is_same<T, bf16>::value && run_decode_mega(e, top_k, eos_id, &mrc);
+  e->last_run_mega = std::is_same<T, bf16>::value && run_decode_persistent(e, top_k, eos_id, &mrc);
   MG_TRY(mrc);
   if (!e->last_run_mega) MG_TRY(run_decode_loop<T>(e, eos_id));
   MG_CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
@@ -396,7 +420,8 @@ int setup_mega(mg_engine* e) {
 }
 
 // Returns true (and launches) when the persistent kernel can serve this call.
-bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride) {
+bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride,
+                     const int32_t* dbg_slot) {
   *rc = MG_OK;
   if (!e->mega_ok || top_k < 1 || top_k > mega::kMegaMaxTopK || e->cur_steps <= 0) return false;
   const int B = e->cur_B;
@@ -415,7 +440,7 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   p.n_layer = g.n_layer; p.head_dim = g.d_model / g.n_head; p.V = g.vocab_size;
   p.VS = ceil_div(g.vocab_size, mega::kMegaCluster); p.NP = mega::mega_head_pairs(p.VS); p.head_tail = mega::mega_head_tail(p.VS);
   p.B = B; p.S = S; p.Tmax = e->max_seq; p.n_steps = e->cur_steps; p.Tvt = mega_tvt(e->max_seq);
-  p.dbg_logits = dbg_logits; p.forced = forced; p.forced_stride = forced_stride;
+  p.dbg_logits = dbg_logits; p.dbg_slot = dbg_slot; p.forced = forced; p.forced_stride = forced_stride;
   p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
   p.prof = nullptr; p.prof_step = -1;
   p.dbg_skip_loads = std::getenv("MG_MEGA_SKIP_LOADS") ? 1 : 0;
@@ -448,6 +473,157 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   return true;
 }
 
+// ---- weight-stationary flow kernel: eligibility, plan, packing, launch ---------------------------------------------
+int setup_flow(mg_engine* e) {
+  const mg_geometry& g = e->geo;
+  e->flow_ok = false;
+  if (!e->flow_candidate) return MG_OK;
+  const int L = g.n_layer, hd = g.d_model / g.n_head;
+  for (int l = 0; l < L; ++l)
+    for (const char* leaf : {"attn.in_proj_weight", "attn.out_proj.weight", "mlp.0.weight", "mlp.2.weight"})
+      if (!e->masters.count("layers." + std::to_string(l) + "." + leaf)) return MG_OK;
+  if (!e->masters.count("head.weight")) return MG_OK;
+  MG_TRY(flow::flow_init());
+  if (!e->flow_plan) e->flow_plan = new flow::FlowPlan();
+  if (flow::flow_plan(L, g.vocab_size, e->n_sm, e->flow_plan) != MG_OK) return MG_OK;       // does not fit: other paths serve
+  {
+    uint64_t* keep = e->flow_xc.base;
+    e->flow_xc = flow::flow_exchange_layout(g.vocab_size, g.n_head, hd, e->n_sm);
+    e->flow_xc.base = keep;
+  }
+  e->flow_tcap = flow::flow_tcap(e->max_seq, hd);
+  if (!e->d_flow_packed) {
+    MG_TRY(e->dmalloc(&e->d_flow_packed, e->flow_plan->packed_bytes));
+    MG_TRY(e->dmalloc(&e->d_flow_prog, sizeof(flow::SmProgram) * e->n_sm));
+    MG_TRY(e->dmalloc(&e->d_flow_layers, sizeof(flow::FlowLayer) * L));
+    MG_TRY(e->dmalloc(&e->d_flow_status, 4 * sizeof(int32_t)));
+    MG_CUDA_OK(cudaMallocHost(&e->h_flow_status, 4 * sizeof(int32_t)));
+    uint64_t* xbase = nullptr;
+    MG_TRY(e->dmalloc(&xbase, sizeof(uint64_t) * e->flow_xc.group_words * flow::kMaxGroups));
+    e->flow_xc.base = xbase;
+    e->flow_layers.resize(L);
+    // zero-filled once: rows past a sequence's length are masked, but must be finite (they meet probability 0)
+    const size_t cache_bytes = sizeof(bf16) * static_cast<size_t>(e->max_batch) * g.d_model * e->flow_tcap;
+    for (int l = 0; l < L; ++l) {
+      MG_TRY(e->dmalloc(&e->flow_layers[l].kc, cache_bytes));
+      MG_TRY(e->dmalloc(&e->flow_layers[l].vc, cache_bytes));
+      MG_CUDA_OK(cudaMemsetAsync(e->flow_layers[l].kc, 0, cache_bytes, e->stream));
+      MG_CUDA_OK(cudaMemsetAsync(e->flow_layers[l].vc, 0, cache_bytes, e->stream));
+    }
+    MG_CUDA_OK(cudaMemcpyAsync(e->d_flow_layers, e->flow_layers.data(), sizeof(flow::FlowLayer) * L, cudaMemcpyHostToDevice, e->stream));
+  }
+  std::vector<flow::FlowWeightSrc> src(L);
+  for (int l = 0; l < L; ++l) {
+    LayerW& w = e->layers[l];
+    const std::string pfx = "layers." + std::to_string(l) + ".";
+    src[l] = flow::FlowWeightSrc{e->masters[pfx + "attn.in_proj_weight"], w.b_in, e->masters[pfx + "attn.out_proj.weight"], w.b_out,
+                                 e->masters[pfx + "mlp.0.weight"], w.b1, e->masters[pfx + "mlp.2.weight"], w.b2,
+                                 w.ln1w, w.ln1b, w.ln2w, w.ln2b};
+  }
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_flow_prog, e->flow_plan->prog, sizeof(flow::SmProgram) * e->n_sm, cudaMemcpyHostToDevice, e->stream));
+  MG_TRY(flow::flow_pack_weights(e->stream, *e->flow_plan, src.data(), L, g.n_head, e->masters["head.weight"], e->head_b,
+                                 g.vocab_size, e->d_flow_packed));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  for (auto& kv : e->masters) e->dfree(kv.second);                     // packed: the fp32 copies are not needed any more
+  e->masters.clear();
+  e->flow_ok = true;
+  return MG_OK;
+}
+
+bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride,
+                     const int32_t* dbg_slot) {
+  *rc = MG_OK;
+  const int B = e->cur_B;
+  if (!e->flow_ok || !e->use_flow || top_k < 1 || top_k > flow::kMaxTopK || e->cur_steps <= 0 ||
+      B > flow::kMaxGroups * flow::kGroupSeqs)
+    return false;
+  const mg_geometry& g = e->geo;
+  const int hd = g.d_model / g.n_head;
+  flow::FlowParams p{};
+  p.packed = e->d_flow_packed; p.prog = e->d_flow_prog; p.layers = e->d_flow_layers;
+  p.tok_emb = reinterpret_cast<const bf16*>(e->tok_emb); p.pos_emb = reinterpret_cast<const bf16*>(e->pos_emb);
+  p.sp = e->d_sp; p.st = e->st; p.xc = e->flow_xc;
+  p.n_layer = g.n_layer; p.n_head = g.n_head; p.head_dim = hd; p.V = g.vocab_size; p.B = B;
+  p.n_groups = std::min(flow::kMaxGroups, (B + flow::kGroupSeqs - 1) / flow::kGroupSeqs);
+  if (const char* gs = std::getenv("MG_FLOW_GROUPS")) p.n_groups = std::max(1, std::min({flow::kMaxGroups, B, std::atoi(gs)}));
+  if ((B + p.n_groups - 1) / p.n_groups > flow::kGroupSeqs) return false;
+  p.n_steps = e->cur_steps; p.Tcap = e->flow_tcap; p.n_sm = e->n_sm;
+  p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
+  p.stagger_ns = std::getenv("MG_FLOW_STAGGER_NS") ? std::atoi(std::getenv("MG_FLOW_STAGGER_NS")) : 6000;
+  p.dbg_logits = dbg_logits; p.dbg_slot = dbg_slot; p.forced = forced; p.forced_stride = forced_stride;
+  p.status = e->d_flow_status;
+  p.prof = nullptr; p.prof_steps = 0;
+  const size_t prof_words = static_cast<size_t>(flow::kMaxSM) * 48 * 6;
+  if (const char* ps = std::getenv("MG_FLOW_PROF")) {               // debug: timeline of group 0 in one step -> stderr
+    p.prof_steps = std::max(0, std::atoi(ps));
+    if (!e->d_flow_prof && e->dmalloc(&e->d_flow_prof, sizeof(unsigned long long) * prof_words) != MG_OK) e->d_flow_prof = nullptr;
+    if (e->d_flow_prof) { cudaMemsetAsync(e->d_flow_prof, 0, sizeof(unsigned long long) * prof_words, e->stream); p.prof = e->d_flow_prof; }
+  }
+  auto cuda_ok = [&](cudaError_t ce, const char* what) {
+    if (ce == cudaSuccess) return true;
+    *rc = fail(MG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+    return false;
+  };
+  if (!cuda_ok(cudaMemsetAsync(e->d_flow_status, 0, 4 * sizeof(int32_t), e->stream), "flow status reset")) return true;
+  // stamps restart at every launch: the exchange words of the previous job must not look valid
+  if (!cuda_ok(cudaMemsetAsync(e->flow_xc.base, 0, sizeof(uint64_t) * e->flow_xc.group_words * flow::kMaxGroups, e->stream),
+               "flow exchange reset")) return true;
+  for (int l = 0; l < g.n_layer && *rc == MG_OK; ++l)
+    *rc = flow::flow_relayout_kv(e->stream, reinterpret_cast<const bf16*>(e->layers[l].kc), reinterpret_cast<const bf16*>(e->layers[l].vc),
+                                 e->flow_layers[l].kc, e->flow_layers[l].vc, e->st.lens, B, g.n_head, hd, e->max_seq, e->flow_tcap);
+  if (*rc == MG_OK) *rc = flow::launch_decode_flow(e->stream, p, e->flow_plan->smem_bytes);
+  if (*rc == MG_OK && !cuda_ok(cudaMemcpyAsync(e->h_flow_status, e->d_flow_status, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream),
+                               "flow status copy")) return true;
+  if (p.prof && *rc == MG_OK) {
+    std::vector<unsigned long long> h(prof_words);
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(h.data(), e->d_flow_prof, sizeof(unsigned long long) * prof_words, cudaMemcpyDeviceToHost);
+    static const char* kind[5] = {"qkv", "attn", "out", "mlp1", "mlp2"};
+    unsigned long long t_origin = ~0ull;
+    for (size_t i = 0; i < prof_words; i += 6) if (h[i]) t_origin = std::min(t_origin, h[i]);
+    fprintf(stderr, "[flow prof] step %d, group 0: per phase over its units: n | entry first..last | inputs complete first..last | done first..last | "
+            "mean (done - inputs complete) ns\n", p.prof_steps);
+    for (int slot = 0; slot < 5 * g.n_layer + 2; ++slot) {
+      unsigned long long e0 = ~0ull, e1 = 0, r0 = ~0ull, r1 = 0, d0 = ~0ull, d1 = 0, work = 0, sen0 = ~0ull, sen1 = 0, retr = 0, rd = 0; int n = 0;
+      for (int smi = 0; smi < e->n_sm; ++smi) {
+        const unsigned long long* q = &h[(static_cast<size_t>(smi) * 48 + slot) * 6];
+        if (!q[0]) continue;
+        if (q[3]) { sen0 = std::min(sen0, q[3]); sen1 = std::max(sen1, q[3]); retr += q[4]; rd += q[5] - q[3]; }
+        ++n; e0 = std::min(e0, q[0]); e1 = std::max(e1, q[0]);
+        if (q[1]) { r0 = std::min(r0, q[1]); r1 = std::max(r1, q[1]); work += q[2] - q[1]; }
+        d0 = std::min(d0, q[2]); d1 = std::max(d1, q[2]);
+      }
+      if (!n) continue;
+      char name[32];
+      if (slot < 5 * g.n_layer) snprintf(name, sizeof name, "L%d %s", slot / 5, kind[slot % 5]);
+      else snprintf(name, sizeof name, "%s", slot == 5 * g.n_layer ? "head" : "sampler");
+      fprintf(stderr, "[flow prof] %-8s n %3d | entry %7llu..%7llu | ready %7llu..%7llu | done %7llu..%7llu | work %5llu", name, n, e0 - t_origin,
+              e1 - t_origin, r0 == ~0ull ? 0 : r0 - t_origin, r1 ? r1 - t_origin : 0, d0 - t_origin, d1 - t_origin, n ? work / n : 0);
+      if (sen1) fprintf(stderr, " | sentinel seen %7llu..%7llu, mean batch retries %.1f, mean read time %llu", sen0 - t_origin, sen1 - t_origin, double(retr) / n, rd / n);
+      fprintf(stderr, "\n");
+    }
+  }
+  e->t_steps = e->cur_steps;
+  e->last_run_flow = true;
+  return true;
+}
+
+bool run_decode_persistent(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride,
+                           const int32_t* dbg_slot) {
+  e->last_run_flow = false;
+  if (run_decode_flow(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
+  return run_decode_mega(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot);
+}
+
+// After the stream has been synchronised: did the flow kernel's watchdog fire?
+int persistent_status(mg_engine* e) {
+  if (!e->last_run_flow || !e->h_flow_status || e->h_flow_status[0] == 0) return MG_OK;
+  const int32_t* s = e->h_flow_status;
+  e->flow_ok = false;                                                  // do not trust it again in this process
+  return fail(MG_E_CUDA, "flow decode kernel aborted: code " + std::to_string(s[0]) + " (1 = exchange word never arrived, 2 = K/V tile "
+              "never arrived), SM " + std::to_string(s[1]) + ", group " + std::to_string(s[2]) + ", detail " + std::to_string(s[3]));
+}
+
 int parse_layer_name(const std::string& name, int* layer, std::string* leaf) {
   if (name.compare(0, 7, "layers.") != 0) return -1;
   const size_t dot = name.find('.', 7);
@@ -457,7 +633,17 @@ int parse_layer_name(const std::string& name, int* layer, std::string* leaf) {
   return 0;
 }
 
-int upload_tensor(mg_engine* e, void* dst, bool typed, const float* data, size_t n) {
+int upload_tensor(mg_engine* e, void* dst, bool typed, const float* data, size_t n, float** keep_master = nullptr) {
+  if (keep_master && typed && e->dtype == MG_DTYPE_BF16) {
+    // the flow kernel folds LayerNorm into its packed weights: it packs from the fp32 values, not from the bf16 copy
+    if (*keep_master) { e->dfree(*keep_master); *keep_master = nullptr; }
+    MG_TRY(e->dmalloc(keep_master, n * sizeof(float)));
+    MG_CUDA_OK(cudaMemcpyAsync(*keep_master, data, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    MG_TRY(launch_convert<bf16>(e->stream, *keep_master, reinterpret_cast<bf16*>(dst), n));
+    MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->h2d += n * sizeof(float);
+    return MG_OK;
+  }
   if (!typed || e->dtype == MG_DTYPE_FP32) {
     MG_CUDA_OK(cudaMemcpyAsync(dst, data, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     MG_CUDA_OK(cudaStreamSynchronize(e->stream));
@@ -597,6 +783,7 @@ int download_impl(mg_engine* e, int32_t* out_ids, int out_stride, int32_t* out_l
   const size_t ints = static_cast<size_t>(B) * (stride + 1);
   MG_CUDA_OK(cudaMemcpyAsync(e->h_out_block, e->d_out_block, ints * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  MG_TRY(persistent_status(e));
   e->d2h += ints * sizeof(int32_t);
   const int32_t* hl = e->h_out_block;
   const int32_t* hi = e->h_out_block + B;
@@ -700,6 +887,16 @@ int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max
   e->use_graph = !(env_graph && env_graph[0] == '1');
   const char* env_mega = std::getenv("MG_NO_MEGA");
   e->use_mega = !(env_mega && env_mega[0] == '1');
+  const char* env_flow = std::getenv("MG_NO_FLOW");
+  e->use_flow = !(env_flow && env_flow[0] == '1');
+  {
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->n_sm = prop.multiProcessorCount;
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    e->flow_candidate = e->use_flow && coop && dtype_mode == MG_DTYPE_BF16 &&
+                        flow::flow_eligible(g.d_model, g.d_ff, g.n_head, g.n_layer, g.vocab_size, e->n_sm);
+  }
   e->launches0 = g_kernel_launches.load();
   int rc = MG_OK;
   auto body = [&]() -> int {
@@ -766,6 +963,8 @@ void mg_engine_destroy(mg_engine* e) {
   if (e->h_out_block) cudaFreeHost(e->h_out_block);
   if (e->h_sp) cudaFreeHost(e->h_sp);
   if (e->h_active) cudaFreeHost(e->h_active);
+  if (e->h_flow_status) cudaFreeHost(e->h_flow_status);
+  delete e->flow_plan;
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -805,7 +1004,9 @@ int mg_load_weight(mg_engine* e, const char* name_c, const float* data, const in
   if (!dst) return fail(MG_E_SHAPE, "unknown tensor name '" + name + "' for this geometry");
   const bool shape_ok = (s1 == 0) ? (ndim == 1 && shape[0] == s0) : (ndim == 2 && shape[0] == s0 && shape[1] == s1);
   if (!shape_ok) return fail(MG_E_SHAPE, "shape mismatch for '" + name + "'");
-  MG_TRY(upload_tensor(e, dst, typed, data, static_cast<size_t>(s0) * (s1 ? s1 : 1)));
+  const bool is_matrix = typed && s1 != 0 && name != "tok_emb.weight" && name != "pos_emb";
+  MG_TRY(upload_tensor(e, dst, typed, data, static_cast<size_t>(s0) * (s1 ? s1 : 1),
+                       (e->flow_candidate && is_matrix) ? &e->masters[name] : nullptr));
   e->loaded.insert(name);
   e->ready = false;
   return MG_OK;
@@ -829,6 +1030,7 @@ int mg_engine_finalize(mg_engine* e) {
     MG_TRY(make_wmaps(&e->m_head, e->head_w, e->geo.vocab_size, d));
   }
   MG_TRY(setup_mega(e));
+  MG_TRY(setup_flow(e));
   e->ready = true;
   return MG_OK;
 }
@@ -865,7 +1067,12 @@ int mg_synchronize(mg_engine* e) {
   if (!e) return fail(MG_E_ARG, "null engine");
   MG_CUDA_OK(cudaSetDevice(e->device));
   MG_CUDA_OK(cudaStreamSynchronize(e->stream));
-  return MG_OK;
+  return persistent_status(e);
+}
+
+int mg_last_decode_path(mg_engine* e) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  return e->last_run_flow ? 2 : (e->last_run_mega ? 1 : 0);
 }
 
 void* mg_engine_stream(mg_engine* e) { return e ? reinterpret_cast<void*>(e->stream) : nullptr; }
@@ -882,10 +1089,22 @@ int mg_generate(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, in
   return download_impl(e, out_ids, out_stride, out_lens);
 }
 
-int mg_step_logits(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, const int32_t* forced, int n_steps,
-                   float* logits_out) {
+// Shared body of mg_step_logits / mg_step_logits_at.  want == nullptr: every step is kept (slot = step).
+static int step_logits_impl(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, const int32_t* forced, int n_steps,
+                            const int32_t* want, int n_want, float* logits_out) {
   if (!e || !logits_out) return fail(MG_E_ARG, "null argument");
   if (n_steps <= 0) return fail(MG_E_ARG, "n_steps must be positive");
+  std::vector<int32_t> slot;                       // step -> row block of logits_out, -1 = not kept
+  int n_keep = n_steps;
+  if (want) {
+    if (n_want <= 0) return fail(MG_E_ARG, "n_want must be positive");
+    slot.assign(n_steps, -1);
+    for (int i = 0; i < n_want; ++i) {
+      if (want[i] < 0 || want[i] >= n_steps || slot[want[i]] >= 0) return fail(MG_E_ARG, "want_steps must be distinct steps in [0, n_steps)");
+      slot[want[i]] = i;
+    }
+    n_keep = n_want;
+  }
   std::lock_guard<std::mutex> lk(e->mu);
   MG_CUDA_OK(cudaSetDevice(e->device));
   MG_TRY(upload_impl(e, ids, offs, B, n_steps, nullptr, true));
@@ -906,36 +1125,64 @@ int mg_step_logits(mg_engine* e, const int32_t* ids, const int32_t* offs, int B,
   }
   const bool is_bf16 = e->dtype == MG_DTYPE_BF16;
   MG_TRY(is_bf16 ? prefill<bf16>(e) : prefill<float>(e));
-  if (is_bf16 && e->mega_ok) {
-    // the persistent cluster kernel in teacher-forcing mode: same code path as mg_run, logits dumped per step
+  if (is_bf16 && (e->mega_ok || e->flow_ok)) {
+    // the persistent kernels in teacher-forcing mode: same code path as mg_run, logits of the kept steps dumped
     float* d_lg = nullptr;
-    const size_t n = static_cast<size_t>(n_steps) * B * V;
+    int32_t* d_slot = nullptr;
+    const size_t n = static_cast<size_t>(n_keep) * B * V;
     MG_TRY(e->dmalloc(&d_lg, n * sizeof(float)));
+    int rc = MG_OK;
+    if (want) {
+      rc = e->dmalloc(&d_slot, sizeof(int32_t) * n_steps);
+      if (rc == MG_OK && cudaMemcpyAsync(d_slot, slot.data(), sizeof(int32_t) * n_steps, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) rc = MG_E_CUDA;
+      if (rc == MG_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = MG_E_CUDA;   // `slot` is pageable host memory
+    }
     *e->h_sp = SampleParams{1.0f, 1, -1, 0, 0, 0};
-    int rc = cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream) == cudaSuccess ? MG_OK : MG_E_CUDA;
+    if (rc == MG_OK && cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream) != cudaSuccess) rc = MG_E_CUDA;
     int mrc = MG_OK;
-    if (rc == MG_OK && run_decode_mega(e, 1, -1, &mrc, d_lg, n_steps > 1 ? e->d_forced : nullptr, n_steps)) {
+    e->last_run_mega = false;
+    if (rc == MG_OK && run_decode_persistent(e, 1, -1, &mrc, d_lg, n_steps > 1 ? e->d_forced : nullptr, n_steps, d_slot)) {
+      e->last_run_mega = true;
       rc = mrc;
       if (rc == MG_OK && cudaMemcpyAsync(logits_out, d_lg, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = MG_E_CUDA;
       if (rc == MG_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(MG_E_CUDA, std::string("persistent decode kernel: ") + cudaGetErrorString(cudaGetLastError()));
+      if (rc == MG_OK) rc = persistent_status(e);
       e->dfree(d_lg);
+      e->dfree(d_slot);
       e->d2h += n * sizeof(float);
       e->uploaded = false;
       return rc;
     }
     e->dfree(d_lg);
+    e->dfree(d_slot);
     MG_TRY(rc);
+    MG_TRY(mrc);
   }
+  e->last_run_mega = e->last_run_flow = false;
   for (int i = 0; i < n_steps; ++i) {
     MG_TRY(is_bf16 ? decode_forward<bf16>(e) : decode_forward<float>(e));
-    MG_CUDA_OK(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(i) * B * V, sizeof(float) * V, e->logits,
-                                 sizeof(float) * e->ld_logits, sizeof(float) * V, B, cudaMemcpyDeviceToHost, e->stream));
-    e->d2h += sizeof(float) * V * B;
+    const int sl = want ? slot[i] : i;
+    if (sl >= 0) {
+      MG_CUDA_OK(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(sl) * B * V, sizeof(float) * V, e->logits,
+                                   sizeof(float) * e->ld_logits, sizeof(float) * V, B, cudaMemcpyDeviceToHost, e->stream));
+      e->d2h += sizeof(float) * V * B;
+    }
     if (i + 1 < n_steps) MG_TRY(launch_force_next(e->stream, e->d_forced, n_steps, i, e->st, B));
   }
   MG_CUDA_OK(cudaStreamSynchronize(e->stream));
   e->uploaded = false;
   return MG_OK;
+}
+
+int mg_step_logits(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, const int32_t* forced, int n_steps,
+                   float* logits_out) {
+  return step_logits_impl(e, ids, offs, B, forced, n_steps, nullptr, 0, logits_out);
+}
+
+int mg_step_logits_at(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, const int32_t* forced, int n_steps,
+                      const int32_t* want_steps, int n_want, float* logits_out) {
+  if (!want_steps) return fail(MG_E_ARG, "want_steps is null");
+  return step_logits_impl(e, ids, offs, B, forced, n_steps, want_steps, n_want, logits_out);
 }
 
 int mg_generate_nocache(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, int max_new, float temperature,

@@ -33,12 +33,12 @@ MG_E_SHAPE, MG_E_PROMPT_TOO_LONG, MG_E_TOPK, MG_E_CUDA, MG_E_OOM, MG_E_STATE, MG
 MG_DTYPE_FP32, MG_DTYPE_BF16 = 0, 1
 _DTYPES = {"fp32": MG_DTYPE_FP32, "float32": MG_DTYPE_FP32, "bf16": MG_DTYPE_BF16, "bfloat16": MG_DTYPE_BF16}
 
-# every symbol include/mg_engine.h declares (tests/test_abi_cpu.py checks the list against the header)
+# every symbol include/mg_engine.h declares (tests/test_host_cpu.py checks the list against the header)
 EXPORTED_SYMBOLS = [
     "mg_abi_version", "mg_last_error", "mg_device_count", "mg_engine_create", "mg_engine_destroy", "mg_load_weight",
     "mg_engine_finalize", "mg_generate", "mg_upload_prompts", "mg_run", "mg_download", "mg_synchronize",
-    "mg_engine_stream", "mg_step_logits", "mg_generate_nocache", "mg_forward_nocache", "mg_sample_logits",
-    "mg_engine_stats", "mg_last_run_timing", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
+    "mg_engine_stream", "mg_step_logits", "mg_step_logits_at", "mg_generate_nocache", "mg_forward_nocache", "mg_sample_logits",
+    "mg_engine_stats", "mg_last_run_timing", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
     "mg_bert_finalize", "mg_classify", "mg_bert_upload", "mg_bert_run", "mg_bert_download", "mg_bert_synchronize",
     "mg_bert_stream", "mg_bert_stats", "mg_test_gemm_bf16",
 ]
@@ -85,12 +85,14 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mg_synchronize": (c.c_int, [vp]),
         "mg_engine_stream": (vp, [vp]),
         "mg_step_logits": (c.c_int, [vp, i32p, i32p, c.c_int, i32p, c.c_int, f32p]),
+        "mg_step_logits_at": (c.c_int, [vp, i32p, i32p, c.c_int, i32p, c.c_int, i32p, c.c_int, f32p]),
         "mg_generate_nocache": (c.c_int, [vp, i32p, i32p, c.c_int, c.c_int, c.c_float, c.c_int, c.c_int, u64, u64,
                                           i32p, c.c_int, i32p]),
         "mg_forward_nocache": (c.c_int, [vp, i32p, i32p, c.c_int, f32p]),
         "mg_sample_logits": (c.c_int, [vp, f32p, c.c_int, c.c_int, c.c_float, c.c_int, u64, u64, c.c_uint32, i32p]),
         "mg_engine_stats": (c.c_int, [vp, u64p, u64p, u64p]),
         "mg_last_run_timing": (c.c_int, [vp, f32p, f32p, f32p, c.POINTER(c.c_int)]),
+        "mg_last_decode_path": (c.c_int, [vp]),
         "mg_bert_create": (c.c_int, [c.POINTER(_BertGeometry), c.c_int, c.c_int, c.POINTER(vp)]),
         "mg_bert_destroy": (None, [vp]),
         "mg_bert_load_weight": (c.c_int, [vp, c.c_char_p, f32p, i64p, c.c_int]),
@@ -130,6 +132,16 @@ def _i32(a) -> np.ndarray:
 
 def _ptr(a: Optional[np.ndarray], ctype):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def fresh_seed() -> int:
+    """A new 64-bit Philox key per call.  The reference draws from torch's global RNG (api_cache.py:178), so two
+    requests with the same prompt give two different pieces; a fixed default seed would repeat the same one."""
+    return int.from_bytes(os.urandom(8), "little")
+
+
+def _seed(seed: Optional[int]) -> int:
+    return fresh_seed() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
 
 
 def _pack_prompts(prompts: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
@@ -199,28 +211,40 @@ class Generator:
 
     # -- the decode path --------------------------------------------------------------------------
     def generate(self, prompt_tokens: Sequence[Sequence[int]], max_new_tokens, temperature: float = 1.0,
-                 top_k: Optional[int] = 50, eos_id: int = -1, seed: int = 0, seq_index_base: int = 0) -> List[List[int]]:
+                 top_k: Optional[int] = 50, eos_id: int = -1, seed: Optional[int] = None,
+                 seq_index_base: int = 0, as_arrays: bool = False) -> List[List[int]]:
         """Row b of the result == a batch-1 reference ``sample_kvcache`` run on prompt b (ids incl. prompt).
 
-        ``max_new_tokens`` is an int or one int per sequence; ``top_k=None`` disables the top-k mask.
+        ``max_new_tokens`` is an int or one int per sequence (negative = 0: the reference's ``range(max_len - Tp)`` is
+        empty and the prompt comes back unchanged); ``top_k=None`` disables the top-k mask; ``seed=None`` draws a fresh
+        64-bit seed per call (the reference samples from torch's global RNG), an explicit seed makes the call reproducible.
+        ``as_arrays=True`` returns int32 numpy rows (views of the one host buffer the engine filled) instead of lists.
         """
         flat, offs = _pack_prompts(prompt_tokens)
         B = len(prompt_tokens)
         per = None
         if isinstance(max_new_tokens, (list, tuple, np.ndarray)):
-            per = _i32(max_new_tokens)
+            per = np.maximum(_i32(max_new_tokens), 0)
             if per.shape != (B,):
                 raise ValueError("max_new_tokens must have one entry per sequence")
             mx = int(per.max())
         else:
-            mx = int(max_new_tokens)
+            mx = max(int(max_new_tokens), 0)
+        if mx == 0:                                               # api_cache.py:166: empty range, prompt unchanged
+            for p in prompt_tokens:
+                if len(p) > self.geometry.pos_rows:               # the prefill at :163 still runs (and raises) first
+                    raise RuntimeError(f"[mg status {MG_E_PROMPT_TOO_LONG}] prompt of {len(p)} tokens exceeds the "
+                                       f"{self.geometry.pos_rows}-row position table")
+            return [list(map(int, p)) for p in prompt_tokens]
         stride = int(max(len(p) for p in prompt_tokens)) + max(mx, 0)
         out = np.zeros((B, max(stride, 1)), np.int32)
         lens = np.zeros(B, np.int32)
         _check(self.lib, self.lib.mg_generate(self._h, _ptr(flat, ctypes.c_int32), _ptr(offs, ctypes.c_int32), B, mx,
                                               _ptr(per, ctypes.c_int32), float(temperature), 0 if top_k is None else int(top_k),
-                                              int(eos_id), int(seed), int(seq_index_base), _ptr(out, ctypes.c_int32),
+                                              int(eos_id), _seed(seed), int(seq_index_base), _ptr(out, ctypes.c_int32),
                                               out.shape[1], _ptr(lens, ctypes.c_int32)))
+        if as_arrays:
+            return [out[b, :lens[b]] for b in range(B)]
         return [out[b, :lens[b]].tolist() for b in range(B)]
 
     def upload(self, prompt_tokens: Sequence[Sequence[int]], max_new_tokens: int) -> None:
@@ -230,10 +254,10 @@ class Generator:
         _check(self.lib, self.lib.mg_upload_prompts(self._h, _ptr(flat, ctypes.c_int32), _ptr(offs, ctypes.c_int32),
                                                     self._last_B, int(max_new_tokens), None))
 
-    def run(self, temperature: float = 1.0, top_k: Optional[int] = 50, eos_id: int = -1, seed: int = 0,
+    def run(self, temperature: float = 1.0, top_k: Optional[int] = 50, eos_id: int = -1, seed: Optional[int] = None,
             seq_index_base: int = 0) -> None:
         _check(self.lib, self.lib.mg_run(self._h, float(temperature), 0 if top_k is None else int(top_k), int(eos_id),
-                                         int(seed), int(seq_index_base)))
+                                         _seed(seed), int(seq_index_base)))
 
     def synchronize(self) -> None:
         _check(self.lib, self.lib.mg_synchronize(self._h))
@@ -256,6 +280,21 @@ class Generator:
                                                  _ptr(forced, ctypes.c_int32), int(n_steps), _ptr(out, ctypes.c_float)))
         return out
 
+    def step_logits_at(self, prompt_tokens: Sequence[Sequence[int]], forced_ids, n_steps: int, want_steps: Sequence[int]) -> np.ndarray:
+        """The same teacher-forced run, keeping only ``want_steps``: [len(want_steps), B, V].  For parity checks at the
+        cache lengths of BASELINE configs 3 / 4, where all steps x batch x vocab would be gigabytes."""
+        flat, offs = _pack_prompts(prompt_tokens)
+        B = len(prompt_tokens)
+        forced = _i32(forced_ids)
+        if forced.shape != (B, n_steps):
+            raise ValueError("forced_ids must be [B, n_steps]")
+        want = _i32(want_steps)
+        out = np.empty((len(want), B, self.geometry.vocab_size), np.float32)
+        _check(self.lib, self.lib.mg_step_logits_at(self._h, _ptr(flat, ctypes.c_int32), _ptr(offs, ctypes.c_int32), B,
+                                                    _ptr(forced, ctypes.c_int32), int(n_steps), _ptr(want, ctypes.c_int32),
+                                                    len(want), _ptr(out, ctypes.c_float)))
+        return out
+
     def sample_logits(self, logits: np.ndarray, temperature: float = 1.0, top_k: Optional[int] = 50, seed: int = 0,
                       seq_index_base: int = 0, step: int = 0) -> np.ndarray:
         """The fused sampler alone (api_cache.py:169-178) on caller-provided logits [rows, V]."""
@@ -268,16 +307,19 @@ class Generator:
 
     # -- recompute mode: model (A), generate_music/generate.py:25-61 ---------------------------------
     def generate_nocache(self, prompt_tokens: Sequence[Sequence[int]], max_new_tokens: int, temperature: float = 1.0,
-                         top_k: Optional[int] = 50, eos_id: int = -1, seed: int = 0, seq_index_base: int = 0):
+                         top_k: Optional[int] = 50, eos_id: int = -1, seed: Optional[int] = None,
+                         seq_index_base: int = 0):
         flat, offs = _pack_prompts(prompt_tokens)
         B = len(prompt_tokens)
+        if int(max_new_tokens) <= 0:                               # generate.py:50: empty range
+            return [list(map(int, p)) for p in prompt_tokens]
         stride = int(max(len(p) for p in prompt_tokens)) + max(int(max_new_tokens), 0)
         out = np.zeros((B, max(stride, 1)), np.int32)
         lens = np.zeros(B, np.int32)
         _check(self.lib, self.lib.mg_generate_nocache(self._h, _ptr(flat, ctypes.c_int32), _ptr(offs, ctypes.c_int32), B,
                                                       int(max_new_tokens), float(temperature),
                                                       0 if not top_k else int(top_k),      # generate.py:54 `if top_k:`
-                                                      int(eos_id), int(seed), int(seq_index_base),
+                                                      int(eos_id), _seed(seed), int(seq_index_base),
                                                       _ptr(out, ctypes.c_int32), out.shape[1], _ptr(lens, ctypes.c_int32)))
         return [out[b, :lens[b]].tolist() for b in range(B)]
 
@@ -295,6 +337,12 @@ class Generator:
         a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         _check(self.lib, self.lib.mg_engine_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    DECODE_PATHS = {0: "step_graph", 1: "cluster_kernel", 2: "flow_kernel"}
+
+    def last_decode_path(self) -> str:
+        """Which CUDA decode path served the last run: step_graph / cluster_kernel (decode_mega.cu) / flow_kernel (decode_flow.cu)."""
+        return self.DECODE_PATHS[int(self.lib.mg_last_decode_path(self._h))]
 
     def last_timing(self) -> Dict[str, float]:
         t, p, d, s = ctypes.c_float(), ctypes.c_float(), ctypes.c_float(), ctypes.c_int()
@@ -330,24 +378,26 @@ class KVModel:
 
 
 def sample_kvcache(model: KVModel, prompt: Sequence[str], max_len: int = 512, temperature: float = 1.0,
-                   top_k: Optional[int] = 50, device: str = "cpu", seed: int = 0) -> List[str]:
+                   top_k: Optional[int] = 50, device: str = "cpu", seed: Optional[int] = None) -> List[str]:
     """Drop-in for reference api_cache.py:160-184 (same arguments; ``device`` is accepted and ignored:
-    the engine already lives on its GPU).  Returns ALL tokens including the prompt, as strings."""
+    the engine already lives on its GPU).  Returns ALL tokens including the prompt, as strings.  ``seed`` is an
+    addition: None (default) = a fresh seed per call, like the reference's draws from the global torch RNG."""
     ids = [model.tok2id[t] for t in prompt]                      # KeyError on OOV, like :162
     eos = model.tok2id.get("[END_SEQUENCE]", -1)                 # :181
-    if getattr(model, "batcher", None) is not None:             # coalesced with the other requests in flight
-        out = model.batcher.generate(ids, max_len - len(ids), temperature, top_k, eos)
+    max_new = max(0, max_len - len(ids))                         # :166 range() of a negative number is empty
+    if getattr(model, "batcher", None) is not None and seed is None:   # coalesced with the other requests in flight
+        out = model.batcher.generate(ids, max_new, temperature, top_k, eos)
     else:
-        out = model.engine.generate([ids], max_len - len(ids), temperature, top_k, eos_id=eos, seed=seed)[0]
+        out = model.engine.generate([ids], max_new, temperature, top_k, eos_id=eos, seed=seed)[0]
     return [model.id2tok[i] for i in out]
 
 
 def sample(model: KVModel, prompt: Sequence[str], max_len: int = 512, temperature: float = 1.0, top_k: Optional[int] = 50,
-           device: str = "cpu", seed: int = 0) -> List[str]:
+           device: str = "cpu", seed: Optional[int] = None) -> List[str]:
     """Drop-in for the no-cache ``sample`` of reference generate_music/generate.py:46-61."""
     ids = [model.tok2id[t] for t in prompt]
     eos = model.tok2id.get("[END_SEQUENCE]", -1)
-    out = model.engine.generate_nocache([ids], max_len - len(ids), temperature, top_k, eos_id=eos, seed=seed)[0]
+    out = model.engine.generate_nocache([ids], max(0, max_len - len(ids)), temperature, top_k, eos_id=eos, seed=seed)[0]
     return [model.id2tok[i] for i in out]
 
 
@@ -366,6 +416,7 @@ class Classifier:
         self.geometry: BertGeometry = infer_bert_geometry(sd, n_heads)
         g = self.geometry
         self.tokenizer = tokenizer
+        self.max_tokens = int(max_tokens)
         cg = _BertGeometry(g.vocab_size, g.max_pos, g.dim, g.n_heads, g.n_layers, g.hidden_dim, g.num_labels)
         _check(self.lib, self.lib.mg_bert_create(ctypes.byref(cg), device, int(max_tokens), ctypes.byref(self._h)))
         for name, shape in expected_bert_keys(g).items():
@@ -440,6 +491,44 @@ class Classifier:
     def predict_ids(self, input_ids, attention_mask=None) -> List[str]:
         labels, _ = self.classify(input_ids, attention_mask)
         return [ID2LABEL[int(i)] for i in labels]
+
+    # The three other read-outs of the same forward (emotion_analysis/inference.py:26-80): softmax over the logits of ONE
+    # text, probabilities rounded to 4 decimals.  ``*_ids`` variants take token ids (no tokenizer needed).
+    def _encode(self, text: str):
+        if self.tokenizer is None:
+            raise RuntimeError("this call needs the HF tokenizer the reference loads (modeling.py:14)")
+        enc = self.tokenizer(text, return_tensors="np", truncation=True, padding=True)      # inference.py:30,45,66
+        return enc["input_ids"], enc.get("attention_mask")
+
+    def probabilities_ids(self, input_ids, attention_mask=None) -> np.ndarray:
+        """softmax(logits, dim=1) in fp32, [N, num_labels] (inference.py:33, 49, 70)."""
+        _, logits = self.classify(input_ids, attention_mask)
+        return torch.softmax(torch.from_numpy(logits), dim=1).numpy()
+
+    def predict_all_labels_ids(self, input_ids, attention_mask=None) -> Dict[str, float]:
+        probs = self.probabilities_ids(input_ids, attention_mask)[0]
+        return {ID2LABEL[i]: round(float(p), 4) for i, p in enumerate(probs)}               # inference.py:36-38
+
+    def predict_top_k_labels_ids(self, input_ids, attention_mask=None, k: int = 3):
+        probs = torch.from_numpy(self.probabilities_ids(input_ids, attention_mask))
+        top_p, top_i = torch.topk(probs, k)                                                 # inference.py:52 (raises if k > labels)
+        return [(ID2LABEL[int(i)], round(float(p), 4)) for i, p in zip(top_i[0], top_p[0])]  # :55-59
+
+    def predict_labels_above_threshold_ids(self, input_ids, attention_mask=None, threshold: float = 0.2):
+        probs = self.probabilities_ids(input_ids, attention_mask)[0]
+        return [(ID2LABEL[i], round(float(p), 4)) for i, p in enumerate(probs) if float(p) > threshold]   # :73-79
+
+    def predict_all_labels(self, text: str) -> Dict[str, float]:
+        """``inference.predict_all_labels(text)`` (emotion_analysis/inference.py:26-38)."""
+        return self.predict_all_labels_ids(*self._encode(text))
+
+    def predict_top_k_labels(self, text: str, k: int = 3):
+        """``inference.predict_top_k_labels(text, k)`` (emotion_analysis/inference.py:41-60)."""
+        return self.predict_top_k_labels_ids(*self._encode(text), k=k)
+
+    def predict_labels_above_threshold(self, text: str, threshold: float = 0.2):
+        """``inference.predict_labels_above_threshold(text, threshold)`` (emotion_analysis/inference.py:62-80)."""
+        return self.predict_labels_above_threshold_ids(*self._encode(text), threshold=threshold)
 
 
 def tc_gemm(A: np.ndarray, W: np.ndarray, bias: Optional[np.ndarray] = None, act: int = 0, device: int = 0) -> np.ndarray:

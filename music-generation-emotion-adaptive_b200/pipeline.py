@@ -31,9 +31,13 @@ def synthetic_music_params(label: str, rng: Optional[random.Random] = None) -> D
 
 def classify_prompt_generate(clf, gen, tok2id: Dict[str, int], input_ids, attention_mask=None,
                              params_fn: Callable[[str], Dict] = synthetic_music_params, max_len: int = 512,
-                             temperature: float = 1.0, top_k: Optional[int] = 50, seed: int = 0, batch: int = 128,
+                             temperature: float = 1.0, top_k: Optional[int] = 50, seed: Optional[int] = None, batch: int = 128,
                              seq_index_base: int = 0) -> List[List[int]]:
-    """N requests -> N token-id lists (prompt included), exactly the per-request flow of api_cache.py:187-204."""
+    """N requests -> N token-id lists (prompt included), exactly the per-request flow of api_cache.py:187-204.
+    ``seed=None``: one fresh seed for the whole call (requests differ by their Philox sequence index)."""
+    if seed is None:
+        from .engine import fresh_seed
+        seed = fresh_seed()
     ids = np.asarray(input_ids)
     labels: List[int] = []
     step = max(1, clf_capacity(clf) // ids.shape[1])
@@ -50,10 +54,11 @@ def classify_prompt_generate(clf, gen, tok2id: Dict[str, int], input_ids, attent
     out: List[List[int]] = []
     for lo in range(0, len(prompts), batch):
         chunk = prompts[lo:lo + batch]
-        out.extend(gen.generate(chunk, [max_len - len(p) for p in chunk], temperature, top_k, eos_id=eos, seed=seed,
+        out.extend(gen.generate(chunk, [max(0, max_len - len(p)) for p in chunk], temperature, top_k, eos_id=eos, seed=seed,
                                 seq_index_base=seq_index_base + lo))
     return out
 
 
 def clf_capacity(clf) -> int:
-    return 16384
+    """Token budget (N * T) of one ``classify`` call: the ``max_tokens`` the classifier's workspace was sized for."""
+    return int(getattr(clf, "max_tokens", 16384))

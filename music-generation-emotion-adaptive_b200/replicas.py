@@ -30,13 +30,15 @@ def shard(items: Sequence, rank: int, world_size: int) -> List:
 
 
 def gather_token_lists(local: Sequence[Sequence[int]], n_total: int, group=None,
-                       device: Optional[torch.device] = None, as_arrays: bool = False):
+                       device: Optional[torch.device] = None, as_arrays: bool = False, max_len: Optional[int] = None):
     """All ranks receive the token lists of all ``n_total`` requests in request order.
 
-    ``local`` must be this rank's ``shard_range`` slice.  One all_gather of an int32 tensor
-    ``[max_local, 1 + max_len]`` (column 0 = length); rows are padded with -1.  ``as_arrays=True`` returns one int32
-    numpy array per request (views of the gathered buffer) instead of Python lists: building half a million Python
-    ints costs more than the exchange itself at 8 GPUs.
+    ``local`` must be this rank's ``shard_range`` slice.  ONE ``all_gather`` (into views of one contiguous buffer) of an int32 tensor
+    ``[max_local, 1 + max_len]`` (column 0 = length, rows padded with -1) and ONE device -> host copy of the gathered block.
+    ``max_len``: the known output stride (longest prompt + max_new_tokens).  When given, no length exchange happens at all
+    (the caller knows it from its own arguments); when None, one extra ``all_reduce(MAX)`` finds it.
+    ``as_arrays=True`` returns one int32 numpy array per request (views of the gathered buffer) instead of Python lists:
+    building half a million Python ints costs more than the exchange itself at 8 GPUs.
     """
     import numpy as np
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -48,24 +50,28 @@ def gather_token_lists(local: Sequence[Sequence[int]], n_total: int, group=None,
     lo, hi = shard_range(n_total, rank, world)
     if len(local) != hi - lo:
         raise ValueError(f"rank {rank} holds {len(local)} results, expected {hi - lo}")
-    dev = device or (torch.device("cuda", torch.cuda.current_device())
-                     if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = device or (torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu"))
     max_local = -(-n_total // world)
     my_max = max((len(x) for x in local), default=0)
-    t = torch.tensor([my_max], dtype=torch.int32, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    max_len = int(t.item())
-    nbuf = np.full((max_local, 1 + max_len), -1, dtype=np.int32)
+    if max_len is None:
+        t = torch.tensor([my_max], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        max_len = int(t.item())
+    elif my_max > max_len:
+        raise ValueError(f"a result of {my_max} tokens exceeds max_len={max_len}")
+    stage = torch.empty((max_local, 1 + max_len), dtype=torch.int32, pin_memory=on_gpu)
+    nbuf = stage.numpy()
+    nbuf.fill(-1)
     for i, x in enumerate(local):
         nbuf[i, 0] = len(x)
         if len(x):
-            nbuf[i, 1:1 + len(x)] = np.asarray(x, dtype=np.int32)
-    buf = torch.from_numpy(nbuf)
-    buf = buf.to(dev)
-    outs = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(outs, buf, group=group)
+            nbuf[i, 1:1 + len(x)] = x
+    buf = stage.to(dev, non_blocking=True) if on_gpu else stage
+    allo_t = torch.empty((world,) + tuple(buf.shape), dtype=torch.int32, device=dev)
+    dist.all_gather(list(allo_t.unbind(0)), buf, group=group)   # views of ONE buffer: NCCL gathers in place, no copy-out
+    allo = allo_t.cpu().numpy()                            # one device -> host copy for all ranks' rows
     result = []
-    allo = torch.stack(outs).cpu().numpy()                 # one device -> host copy for all ranks' rows
     for r in range(world):
         o = allo[r]
         rlo, rhi = shard_range(n_total, r, world)

@@ -196,3 +196,154 @@ def test_request_batcher_isolates_a_failing_request():
     assert out == {0: [1, 2, 3, 3], 2: [5, 5, 5]} and list(err) == [1] and "position table" in err[1]
     with pytest.raises(RuntimeError):
         b.submit([1], 1)
+
+
+def test_request_batcher_retry_keeps_distinct_streams_and_fails_whole_batch_on_device_errors():
+    """the per-request retry after a failed batch must give request i the Philox sequence index base + i (not
+    base for all of them), and a device failure (MG_E_CUDA / MG_E_OOM) must fail the batch instead of N serial re-runs."""
+    import threading
+    eng = _FakeEngine()
+    b = mg.RequestBatcher(eng, max_batch=4, max_wait_ms=100.0, seed=5)
+    threads = [threading.Thread(target=lambda p=p: _swallow(b.generate, p, 2)) for p in ([1, 2], list(range(9)), [5], [7, 7])]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    singles = [c for c in eng.calls if c[0] == 1]
+    assert len(singles) == 3 and len({c[3] for c in singles}) == 3                     # three survivors, three streams
+
+    class _Broken(_FakeEngine):
+        def generate(self, prompts, *a, **k):
+            with self.lock:
+                self.calls.append(len(prompts))
+            raise RuntimeError("[mg status -4] cudaStreamSynchronize: an illegal memory access was encountered")
+    bad = _Broken()
+    b2 = mg.RequestBatcher(bad, max_batch=4, max_wait_ms=100.0)
+    errs = []
+    threads = [threading.Thread(target=lambda i=i: errs.append(_swallow(b2.generate, [i], 2))) for i in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    b.close(); b2.close()
+    assert len(errs) == 3 and all(isinstance(e, RuntimeError) for e in errs)
+    assert sum(bad.calls) == 3                                                          # no re-run of a failed batch
+
+
+def _swallow(fn, *a):
+    try:
+        return fn(*a)
+    except Exception as e:                # noqa: BLE001 - the tests inspect the exception object
+        return e
+
+
+def test_batcher_and_engine_default_to_fresh_seeds():
+    """seed=None must not mean seed 0 (identical prompts would always give the identical piece)."""
+    from mgea_b200 import engine as eng
+    assert eng._seed(7) == 7 and eng._seed(None) != eng._seed(None)
+    b1, b2 = mg.RequestBatcher(_FakeEngine(), seed=None), mg.RequestBatcher(_FakeEngine(), seed=None)
+    assert b1._seed != b2._seed
+    b1.close(); b2.close()
+    import inspect
+    for fn in (mg.sample_kvcache, mg.sample, mg.Generator.generate, mg.Generator.run, mg.classify_prompt_generate):
+        assert inspect.signature(fn).parameters["seed"].default is None, fn
+
+
+def test_peft_spellings_of_the_finetuned_classifier_load():
+    """SURVEY 8(f) rank 4 / ADVICE r1: the adapter was trained with TaskType.SEQ_CLS (Scripts/finetuneDistillBert.ipynb:790-795),
+    so pre_classifier / classifier are PEFT modules_to_save.  Every spelling modeling.load_model() can yield must map to the
+    plain HF keys with the FINE-TUNED heads and W + 2 B A on q_lin / v_lin."""
+    import torch
+    geo = mg.TINY_BERT
+    base = mg.make_bert_state_dict(geo, 0, with_lora=False)
+    g = torch.Generator().manual_seed(1)
+    tuned = {k: torch.randn(v.shape, generator=g) for k, v in base.items() if k.split(".")[0] in ("pre_classifier", "classifier")}
+    lora = {}
+    for i in range(geo.n_layers):
+        for lin in ("q_lin", "v_lin"):
+            m = f"distilbert.transformer.layer.{i}.attention.{lin}"
+            lora[m] = (0.05 * torch.randn(8, geo.dim, generator=g), 0.05 * torch.randn(geo.dim, 8, generator=g))
+
+    want = dict(base)
+    want.update(tuned)
+    for m, (A, B) in lora.items():
+        want[m + ".weight"] = base[m + ".weight"] + 2.0 * (B @ A)
+
+    def check(sd):
+        got = mg.merge_lora_state_dict(sd)
+        assert set(got) == set(want), sorted(set(got) ^ set(want))[:4]
+        for k in want:
+            assert torch.allclose(got[k], want[k], atol=1e-6), k
+
+    # (1) adapter_model.safetensors as PEFT writes it + the base checkpoint, merged in BOTH dict orders
+    disk = {f"base_model.model.{m}.lora_A.weight": A for m, (A, B) in lora.items()}
+    disk.update({f"base_model.model.{m}.lora_B.weight": B for m, (A, B) in lora.items()})
+    disk.update({f"base_model.model.{k}": v for k, v in tuned.items()})
+    check({**base, **disk})
+    check({**disk, **base})
+    # (2) live PeftModel.state_dict(): base_layer wrappers, .default adapters, original_module + modules_to_save.default heads
+    live = {}
+    for k, v in base.items():
+        mod = k.rsplit(".", 1)[0]
+        if mod in lora:
+            live[f"base_model.model.{mod}.base_layer.{k.rsplit('.', 1)[1]}"] = v
+        elif k.split(".")[0] in ("pre_classifier", "classifier"):
+            leaf = k.split(".", 1)[1]
+            live[f"base_model.model.{k.split('.')[0]}.original_module.{leaf}"] = v
+            live[f"base_model.model.{k.split('.')[0]}.modules_to_save.default.{leaf}"] = tuned[k]
+        else:
+            live[f"base_model.model.{k}"] = v
+    for m, (A, B) in lora.items():
+        live[f"base_model.model.{m}.lora_A.default.weight"] = A
+        live[f"base_model.model.{m}.lora_B.default.weight"] = B
+    check(live)
+    check(dict(reversed(list(live.items()))))
+
+
+def test_classifier_readouts_follow_inference_py():
+    """predict_all_labels / predict_top_k_labels / predict_labels_above_threshold (emotion_analysis/inference.py:26-80):
+    softmax of one text's logits, rounded to 4 decimals, k default 3, threshold default 0.2 and strict."""
+    import numpy as np
+    import torch
+    from mgea_b200.engine import Classifier
+    logits = torch.randn(1, 28, generator=torch.Generator().manual_seed(3)).numpy() * 2.0
+
+    class _Tok:
+        def __call__(self, text, return_tensors, truncation, padding):
+            assert (return_tensors, truncation, padding) == ("np", True, True)
+            return {"input_ids": np.array([[101, 7, 102]]), "attention_mask": np.array([[1, 1, 1]])}
+
+    class _Stub(Classifier):
+        def __init__(self):
+            self.tokenizer = _Tok()
+
+        def classify(self, ids, mask=None):
+            return logits.argmax(1).astype(np.int32), logits
+
+        def __del__(self):
+            pass
+
+    c = _Stub()
+    p = torch.softmax(torch.from_numpy(logits), 1)[0]
+    allp = c.predict_all_labels("x")
+    assert list(allp) == [mg.ID2LABEL[i] for i in range(28)] and allp == {mg.ID2LABEL[i]: round(float(p[i]), 4) for i in range(28)}
+    top = c.predict_top_k_labels("x")
+    order = torch.argsort(p, descending=True)[:3]
+    assert top == [(mg.ID2LABEL[int(i)], round(float(p[i]), 4)) for i in order]
+    assert len(c.predict_top_k_labels("x", k=5)) == 5
+    thr = c.predict_labels_above_threshold("x")
+    assert thr == [(mg.ID2LABEL[i], round(float(p[i]), 4)) for i in range(28) if float(p[i]) > 0.2]
+    assert c.predict("x") == mg.ID2LABEL[int(p.argmax())]
+    with pytest.raises(RuntimeError):
+        c.predict_top_k_labels("x", k=29)                       # torch.topk raises in the reference too
+
+
+def test_generate_with_no_room_returns_the_prompt_like_the_reference():
+    """api_cache.py:166: range(max_len - Tp) is empty when max_len <= len(prompt): the prompt comes back unchanged."""
+    from mgea_b200.engine import Generator
+    g = Generator.__new__(Generator)
+    g.geometry = mg.GEOMETRIES["tiny"]
+    assert Generator.generate(g, [[1, 2, 3]], -4) == [[1, 2, 3]] and Generator.generate(g, [[1], [2, 3]], [0, -1]) == [[1], [2, 3]]
+    with pytest.raises(RuntimeError):
+        Generator.generate(g, [list(range(g.geometry.pos_rows + 1))], 0)
+    assert mg.clf_capacity(type("C", (), {"max_tokens": 4096})()) == 4096

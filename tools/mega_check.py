@@ -16,7 +16,7 @@ forced = np.random.default_rng(0).integers(0, geo.vocab_size, (B, n)).astype(np.
 eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=max(B, 64), max_seq=1088)
 t0 = time.time()
 lg = eng.step_logits(prompts, forced, n)
-print("step_logits done in %.2fs" % (time.time() - t0), flush=True)
+print("step_logits done in %.2fs" % (time.time() - t0), "path", eng.last_decode_path(), flush=True)
 ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head, torch.float64)
 for b in range(min(B, 4)):
     want = gpt_kv.teacher_forced_logits(ora, prompts[b], forced[b].tolist(), n).numpy()
@@ -25,4 +25,4 @@ for b in range(min(B, 4)):
 if B >= 8:
     for k in (1, 40):
         out = eng.generate(prompts, 64, 1.0, k, seed=5)
-        print("generate top_k", k, "ok", [len(o) for o in out[:4]], eng.last_timing(), flush=True)
+        print("generate top_k", k, "ok", eng.last_decode_path(), [len(o) for o in out[:4]], eng.last_timing(), flush=True)

@@ -26,4 +26,4 @@ eng.synchronize()
 t = eng.last_timing()
 out = eng.download()
 assert all(len(o) == len(p) + new_tokens for o, p in zip(out, prompts))
-print("profile_step ok", t, eng.stats())
+print("profile_step ok", eng.last_decode_path(), t, eng.stats())
