@@ -144,12 +144,14 @@ struct Warp {
   int fin;                             // finished (EOS or budget) -- or no such sequence
   int nnew;                            // tokens generated so far
   int maxT;                            // max len over the running sequences of the group
-  // K/V ring
-  uint32_t ring, bars;                 // shared-memory addresses: stages, full barriers
+  // K/V stages: a pool of kPoolStages stages shared by the 8 warps of the SM (a warp that streams takes up to kMaxInFlight of
+  // them, a warp that waits for its query holds the 2 it requested ahead); `q` = FIFO of the stages this warp has in flight
+  uint32_t ring, bars;                 // shared-memory addresses: stage 0, barrier 0
+  uint32_t pool;                       // shared-memory address of {free mask, parity mask}
   int step;
   int out0, maxnew;                    // out_len at kernel start, token budget (sequence i in lane i)
-  int cs, is;                          // next stage to consume / to fill
-  uint32_t cph;                        // parity bits of the stages (consumer side)
+  uint32_t q;                          // 4 bits per entry, oldest in the low nibble
+  int qn;
   const bf16* pf_k;                    // first K tile of the unit whose tiles were requested ahead (pf_n of them)
   int pf_n;
   uint64_t pol;
@@ -167,9 +169,13 @@ __device__ __forceinline__ void flow_fail(Warp& w, int code, int detail) {      
   w.dead = true;
 }
 // true = keep polling
+// what this warp was waiting for when the kernel was aborted: status[8 + 2 (sm * 8 + group)] = {detail, step + 1}
+__device__ __noinline__ void flow_waitlog(int32_t* status, int sm, int g, int detail, int step) {
+  if ((threadIdx.x & 31) == 0) { status[8 + 2 * (sm * kMaxGroups + g)] = detail; status[9 + 2 * (sm * kMaxGroups + g)] = step + 1; }
+}
 __device__ __forceinline__ bool poll_ok(Warp& w, uint32_t& tries, int detail) {
-  if (++tries > kMaxTries) { flow_fail(w, FS_TIMEOUT_LL, detail); return false; }
-  if ((tries & 255u) == 0 && *reinterpret_cast<volatile int32_t*>(w.status) != 0) { w.dead = true; return false; }
+  if (++tries > kMaxTries) { flow_fail(w, FS_TIMEOUT_LL, detail); flow_waitlog(w.status, w.sm, w.g, detail, w.step); return false; }
+  if ((tries & 255u) == 0 && *reinterpret_cast<volatile int32_t*>(w.status) != 0) { w.dead = true; flow_waitlog(w.status, w.sm, w.g, detail, w.step); return false; }
   return true;
 }
 
@@ -185,58 +191,57 @@ __device__ __forceinline__ bool ll_wait_word(Warp& w, const uint64_t* p, uint32_
   }
 }
 
-// ---- B operand from an fp32 row buffer [8][256] (payload = float): lane (qd, tq) gets, for its sequence qd and every k-step,
-// features 16 ks + {2 tq, 2 tq + 1, 2 tq + 8, 2 tq + 9}; optional LayerNorm (scale / shift are folded into the weights).
+// ---- B operand from a bf16 row buffer [8][128 pair words] (payload = two bf16, stored at word 8 ks + 2 tq + j so that one
+// 16-byte load brings the two pairs of a k-step): lane (qd, tq) gets, for its sequence qd and every k-step, features
+// 16 ks + {2 tq, 2 tq + 1} and {2 tq + 8, 2 tq + 9}; optional LayerNorm (scale / shift are folded into the weights).  The
+// residual stream itself stays fp32 (separate words, read by the units that add to it); only this GEMM operand is bf16.
+__device__ __forceinline__ int pair_pos(int pair) { return (pair & ~7) | (2 * (pair & 3)) | ((pair >> 2) & 1); }
 __device__ __forceinline__ bool load_rows_bf16(Warp& w, const uint64_t* buf, uint32_t want, bool ln, uint32_t (&b)[16][2], int detail) {
   const bool act = w.qd < w.nseq;
-  const uint64_t* row = buf + w.qd * D + 2 * w.tq;
   if (!ll_wait_word(w, buf, want, detail)) return false;
   if (w.prof && w.lane == 0) w.prof[3] = ptx::global_timer_ns();
-  // All 32 loads are issued back to back (no branch, no short-circuit between them: a conditional around a volatile load makes
-  // ptxas wait for each load before the next -- measured 7-8 us for this batch instead of 0.5); lanes without a sequence read
+  // All loads are issued back to back (no branch, no short-circuit between them: a conditional around a volatile load makes
+  // ptxas wait for each load before the next -- measured 7-8 us for a batch instead of 0.5); lanes without a sequence read
   // row 0 and ignore what they get.
-  const uint64_t* ldrow = act ? row : buf + 2 * w.tq;
-  float v[16][4];
+  const uint64_t* row = buf + (act ? w.qd : 0) * (D / 2) + 2 * w.tq;
   uint32_t tries = 0;
   while (true) {
     uint32_t bad = 0;
 #pragma unroll
     for (int ks = 0; ks < 16; ++ks) {
-      uint32_t d0, s0, d1, s1, d2, s2, d3, s3;
-      ll_ld2(ldrow + ks * 16, d0, s0, d1, s1);
-      ll_ld2(ldrow + ks * 16 + 8, d2, s2, d3, s3);
-      v[ks][0] = __uint_as_float(d0); v[ks][1] = __uint_as_float(d1); v[ks][2] = __uint_as_float(d2); v[ks][3] = __uint_as_float(d3);
-      bad |= (s0 ^ want) | (s1 ^ want) | (s2 ^ want) | (s3 ^ want);
+      uint32_t s0, s1;
+      ll_ld2(row + ks * 8, b[ks][0], s0, b[ks][1], s1);
+      bad |= (s0 ^ want) | (s1 ^ want);
     }
     if (__all_sync(kFull, bad == 0 || !act)) break;
     if (!poll_ok(w, tries, detail + 1)) return false;
   }
   if (w.prof && w.lane == 0) { w.prof[4] = tries; w.prof[5] = ptx::global_timer_ns(); }
-  if (!act) {                                      // no divergent return: the shuffles below are executed by every lane
-#pragma unroll
-    for (int ks = 0; ks < 16; ++ks) { v[ks][0] = v[ks][1] = v[ks][2] = v[ks][3] = 0.f; }
-  }
-  float mean = 0.f, rstd = 1.f;
   if (ln) {
     float s = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) s += (v[ks][0] + v[ks][1]) + (v[ks][2] + v[ks][3]);
+    for (int ks = 0; ks < 16; ++ks) s += (bf_lo(b[ks][0]) + bf_hi(b[ks][0])) + (bf_lo(b[ks][1]) + bf_hi(b[ks][1]));
     s += __shfl_xor_sync(kFull, s, 1);
     s += __shfl_xor_sync(kFull, s, 2);
-    mean = s * (1.0f / D);
+    const float mean = s * (1.0f / D);
     float q = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { const float c = v[ks][e] - mean; q = fmaf(c, c, q); }
+    for (int ks = 0; ks < 16; ++ks) {
+      const float c0 = bf_lo(b[ks][0]) - mean, c1 = bf_hi(b[ks][0]) - mean, c2 = bf_lo(b[ks][1]) - mean, c3 = bf_hi(b[ks][1]) - mean;
+      q = fmaf(c0, c0, q); q = fmaf(c1, c1, q); q = fmaf(c2, c2, q); q = fmaf(c3, c3, q);
+    }
     q += __shfl_xor_sync(kFull, q, 1);
     q += __shfl_xor_sync(kFull, q, 2);
-    rstd = rsqrtf(q * (1.0f / D) + 1e-5f);
-  }
+    const float rstd = rsqrtf(q * (1.0f / D) + 1e-5f);
 #pragma unroll
-  for (int ks = 0; ks < 16; ++ks) {
-    b[ks][0] = act ? pack_bf16((v[ks][0] - mean) * rstd, (v[ks][1] - mean) * rstd) : 0u;
-    b[ks][1] = act ? pack_bf16((v[ks][2] - mean) * rstd, (v[ks][3] - mean) * rstd) : 0u;
+    for (int ks = 0; ks < 16; ++ks) {
+      b[ks][0] = pack_bf16((bf_lo(b[ks][0]) - mean) * rstd, (bf_hi(b[ks][0]) - mean) * rstd);
+      b[ks][1] = pack_bf16((bf_lo(b[ks][1]) - mean) * rstd, (bf_hi(b[ks][1]) - mean) * rstd);
+    }
+  }
+  if (!act) {
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) { b[ks][0] = 0u; b[ks][1] = 0u; }
   }
   return true;
 }
@@ -272,7 +277,7 @@ template <int HD>
 __device__ __forceinline__ bool unit_qkv(Warp& w, const FlowParams& p, int layer, int tile, uint32_t wt) {
   const uint32_t st = stamp_of(w.step, layer);
   uint32_t b[16][2];
-  if (!load_rows_bf16(w, w.xg + p.xc.off_xin, st, true, b, 100 + layer * 10)) return false;
+  if (!load_rows_bf16(w, w.xg + p.xc.off_xb, st, true, b, 100 + layer * 10)) return false;
   FLOW_READY(w);
   float acc[4];
   tile_mma<16>(wt, w.lane, b, acc);
@@ -301,16 +306,18 @@ __device__ __forceinline__ bool unit_qkv(Warp& w, const FlowParams& p, int layer
   return true;
 }
 
-// x slice of this tile's 16 features for the 4 accumulators of a lane (rows qd / qd + 8, sequences 2 tq / 2 tq + 1)
+// Residual slice of this tile's 16 features for the 4 accumulators of a lane.  Every tile but the head's has the paired row order
+// (MMA row r < 8 = feature 2 r, row r + 8 = feature 2 r + 1), so the lane owns features f0 + 2 qd, + 1 of sequences 2 tq (values 0, 2)
+// and 2 tq + 1 (values 1, 3): one 16-byte word pair per sequence in the fp32 buffer.
 __device__ __forceinline__ bool load_slice(Warp& w, const uint64_t* buf, uint32_t want, int f0, float (&r)[4], int detail) {
   const int s0 = 2 * w.tq;
   const bool a0_ok = s0 < w.nseq, a1_ok = s0 + 1 < w.nseq;
-  const uint64_t* a0 = buf + (a0_ok ? s0 : 0) * D + f0 + w.qd;
-  const uint64_t* a1 = buf + (a1_ok ? s0 + 1 : 0) * D + f0 + w.qd;
+  const uint64_t* a0 = buf + (a0_ok ? s0 : 0) * D + f0 + 2 * w.qd;
+  const uint64_t* a1 = buf + (a1_ok ? s0 + 1 : 0) * D + f0 + 2 * w.qd;
   uint32_t tries = 0;
   while (true) {
     uint32_t d0, d1, d2, d3, t0, t1, t2, t3;
-    ll_ld1(a0, d0, t0); ll_ld1(a0 + 8, d2, t2); ll_ld1(a1, d1, t1); ll_ld1(a1 + 8, d3, t3);
+    ll_ld2(a0, d0, t0, d2, t2); ll_ld2(a1, d1, t1, d3, t3);
     const uint32_t bad = (a0_ok ? (t0 ^ want) | (t2 ^ want) : 0u) | (a1_ok ? (t1 ^ want) | (t3 ^ want) : 0u);
     if (__all_sync(kFull, bad == 0)) {
       r[0] = a0_ok ? __uint_as_float(d0) : 0.f; r[1] = a1_ok ? __uint_as_float(d1) : 0.f;
@@ -320,13 +327,13 @@ __device__ __forceinline__ bool load_slice(Warp& w, const uint64_t* buf, uint32_
     if (!poll_ok(w, tries, detail)) return false;
   }
 }
-__device__ __forceinline__ void store_slice(Warp& w, uint64_t* buf, uint32_t st, int f0, const float (&r)[4]) {
-  const int s0 = 2 * w.tq;
-  uint64_t* a0 = buf + s0 * D + f0 + w.qd;
-  ll_st1(a0, __float_as_uint(r[0]), st);
-  ll_st1(a0 + D, __float_as_uint(r[1]), st);
-  ll_st1(a0 + 8, __float_as_uint(r[2]), st);
-  ll_st1(a0 + D + 8, __float_as_uint(r[3]), st);
+// fp32 words (for the units that add to the residual stream) + bf16 pair words (the next GEMM's operand)
+__device__ __forceinline__ void store_slice(Warp& w, uint64_t* buf, uint64_t* bbuf, uint32_t st, int tile, const float (&r)[4]) {
+  const int s0 = 2 * w.tq, f = tile * 16 + 2 * w.qd, pos = tile * 8 + 2 * (w.qd & 3) + (w.qd >> 2);
+  ll_st1(bbuf + s0 * (D / 2) + pos, pack_bf16(r[0], r[2]), st);
+  ll_st1(bbuf + (s0 + 1) * (D / 2) + pos, pack_bf16(r[1], r[3]), st);
+  ll_st2(buf + s0 * D + f, __float_as_uint(r[0]), __float_as_uint(r[2]), st);
+  ll_st2(buf + (s0 + 1) * D + f, __float_as_uint(r[1]), __float_as_uint(r[3]), st);
 }
 
 // Attention partials of a group: per (sequence, key split) one block of 128 output words (bf16 pairs of o / l, head-major,
@@ -345,6 +352,8 @@ __device__ __forceinline__ bool unit_out(Warp& w, const FlowParams& p, int layer
   const bool act = w.qd < w.nseq;
   const uint64_t* part = w.xg + p.xc.off_part;
   uint32_t b[16][2];
+  float xs[4];                                       // the residual slice is old news (published before the attention): fetch it first,
+  if (!load_slice(w, w.xg + p.xc.off_xin, st, tile * 16, xs, 202 + layer * 10)) return false;   // hidden behind the wait for the partials
   if (!ll_wait_word(w, part + part_o_off(0, 0), st, 200 + layer * 10)) return false;
   if (S == 1) {
     // one split: the payloads ARE the B registers (o is published normalised)
@@ -416,12 +425,11 @@ __device__ __forceinline__ bool unit_out(Warp& w, const FlowParams& p, int layer
     }
   }
   FLOW_READY(w);
-  float acc4[4], xs[4];
+  float acc4[4];
   tile_mma<16>(wt, w.lane, b, acc4);
-  if (!load_slice(w, w.xg + p.xc.off_xin, st, tile * 16, xs, 202 + layer * 10)) return false;
   const float b_lo = tile_bias(wt, 16, w.qd), b_hi = tile_bias(wt, 16, w.qd + 8);
   const float r[4] = {xs[0] + acc4[0] + b_lo, xs[1] + acc4[1] + b_lo, xs[2] + acc4[2] + b_hi, xs[3] + acc4[3] + b_hi};
-  store_slice(w, w.xg + p.xc.off_x1, st, tile * 16, r);
+  store_slice(w, w.xg + p.xc.off_x1, w.xg + p.xc.off_x1b, st, tile, r);
   return true;
 }
 
@@ -429,7 +437,7 @@ __device__ __forceinline__ bool unit_out(Warp& w, const FlowParams& p, int layer
 __device__ __forceinline__ bool unit_mlp1(Warp& w, const FlowParams& p, int layer, int tile, uint32_t wt) {
   const uint32_t st = stamp_of(w.step, layer);
   uint32_t b[16][2];
-  if (!load_rows_bf16(w, w.xg + p.xc.off_x1, st, true, b, 300 + layer * 10)) return false;
+  if (!load_rows_bf16(w, w.xg + p.xc.off_x1b, st, true, b, 300 + layer * 10)) return false;
   FLOW_READY(w);
   float acc[4];
   tile_mma<16>(wt, w.lane, b, acc);
@@ -448,6 +456,8 @@ __device__ __forceinline__ bool unit_mlp2(Warp& w, const FlowParams& p, int laye
   const uint32_t st = stamp_of(w.step, layer);
   const bool act = w.qd < w.nseq;
   const uint64_t* h = w.xg + p.xc.off_h + (act ? w.qd : 0) * 512 + 2 * w.tq;
+  float xs[4];                                       // residual slice first (published two phases ago), hidden behind the wait for h
+  if (!load_slice(w, w.xg + p.xc.off_x1, st, tile * 16, xs, 402 + layer * 10)) return false;
   if (!ll_wait_word(w, w.xg + p.xc.off_h, st, 400 + layer * 10)) return false;
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -479,12 +489,10 @@ __device__ __forceinline__ bool unit_mlp2(Warp& w, const FlowParams& p, int laye
     }
   }
   FLOW_READY(w);
-  float xs[4];
-  if (!load_slice(w, w.xg + p.xc.off_x1, st, tile * 16, xs, 402 + layer * 10)) return false;
   const float b_lo = tile_bias(wt, 64, w.qd), b_hi = tile_bias(wt, 64, w.qd + 8);
   const float r[4] = {xs[0] + a0[0] + a1[0] + b_lo, xs[1] + a0[1] + a1[1] + b_lo, xs[2] + a0[2] + a1[2] + b_hi,
                       xs[3] + a0[3] + a1[3] + b_hi};
-  store_slice(w, w.xg + p.xc.off_xin, stamp_of(w.step, layer + 1), tile * 16, r);
+  store_slice(w, w.xg + p.xc.off_xin, w.xg + p.xc.off_xb, stamp_of(w.step, layer + 1), tile, r);
   return true;
 }
 
@@ -493,7 +501,7 @@ __device__ __forceinline__ bool unit_mlp2(Warp& w, const FlowParams& p, int laye
 __device__ __forceinline__ bool unit_head(Warp& w, const FlowParams& p, const SmProgram& prog, uint32_t blob) {
   const uint32_t st = stamp_of(w.step, p.n_layer);
   uint32_t b[16][2];
-  if (!load_rows_bf16(w, w.xg + p.xc.off_xin, st, false, b, 500)) return false;
+  if (!load_rows_bf16(w, w.xg + p.xc.off_xb, st, false, b, 500)) return false;
   FLOW_READY(w);
   const int dslot = !p.dbg_logits ? -1 : (p.dbg_slot ? p.dbg_slot[w.step] : w.step);
   const int s0 = 2 * w.tq, s1 = s0 + 1;
@@ -562,35 +570,78 @@ __device__ __forceinline__ int attn_unit_of(int sm, int n_sm, int g, int layer, 
   return u < n_units ? u : -1;
 }
 
-template <int HD>
-__device__ __forceinline__ void ring_issue(Warp& w, const bf16* ksrc, const bf16* vsrc) {
-  using C = AttnCfg<HD>;
-  if (w.lane == 0) {
-    const uint32_t bar = w.bars + w.is * 8, dst = w.ring + w.is * kStageBytes;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * C::HALF) : "memory");
-    bulk_load_hint(dst, ksrc, C::HALF, bar, w.pol);
-    bulk_load_hint(dst + C::HALF, vsrc, C::HALF, bar, w.pol);
-  }
-  w.is ^= 1;
+constexpr int kPoolStages = kMaxGroups * kStages;        // 16 stages of 8 KB per SM
+constexpr int kMaxInFlight = 6;                          // per streaming warp (48 KB: ~45 GB/s at 1.1 us of HBM latency)
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
 }
-__device__ __forceinline__ bool ring_wait(Warp& w) {
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ void atoms_or(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void atoms_xor(uint32_t addr, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// Take a free stage and start the two bulk copies of one tile into it; false = no stage free right now.
+template <int HD>
+__device__ __forceinline__ bool ring_issue(Warp& w, const bf16* ksrc, const bf16* vsrc) {
+  using C = AttnCfg<HD>;
+  int stage = -1;
+  if (w.lane == 0) {
+    uint32_t m = lds32_volatile(w.pool);
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      const uint32_t old = atoms_cas(w.pool, m, m & ~(1u << bit));
+      if (old == m) { stage = bit; break; }
+      m = old;
+    }
+    if (stage >= 0) {
+      const uint32_t bar = w.bars + stage * 8, dst = w.ring + stage * kStageBytes;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * C::HALF) : "memory");
+      bulk_load_hint(dst, ksrc, C::HALF, bar, w.pol);
+      bulk_load_hint(dst + C::HALF, vsrc, C::HALF, bar, w.pol);
+    }
+  }
+  stage = __shfl_sync(kFull, stage, 0);
+  if (stage < 0) return false;
+  w.q |= static_cast<uint32_t>(stage) << (4 * w.qn);
+  w.qn += 1;
+  return true;
+}
+// Wait for the oldest stage in flight; returns its index (-1: watchdog).
+__device__ __forceinline__ int ring_wait(Warp& w) {
   // test_wait polling, not try_wait: a thread suspended inside try_wait is woken thousands of cycles after the phase completes
   // (round 1 measured 3100 cycles of skew), and this wait sits on the critical chain of every K/V tile
-  const uint32_t bar = w.bars + w.cs * 8, parity = (w.cph >> w.cs) & 1u;
+  const int stage = static_cast<int>(w.q & 15u);
+  const uint32_t bar = w.bars + stage * 8, parity = (lds32_volatile(w.pool + 4) >> stage) & 1u;
   uint32_t tries = 0;
   while (true) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return true;
-    if (++tries > 16 * kMaxTries) { flow_fail(w, FS_TIMEOUT_BAR, w.cs); return false; }
-    if ((tries & 4095u) == 0 && *reinterpret_cast<volatile int32_t*>(w.status) != 0) { w.dead = true; return false; }
+    if (ok) return stage;
+    if (++tries > 16 * kMaxTries) { flow_fail(w, FS_TIMEOUT_BAR, stage); flow_waitlog(w.status, w.sm, w.g, 900 + stage, w.step); return -1; }
+    if ((tries & 4095u) == 0 && *reinterpret_cast<volatile int32_t*>(w.status) != 0) { w.dead = true; flow_waitlog(w.status, w.sm, w.g, 900 + stage, w.step); return -1; }
   }
 }
-__device__ __forceinline__ void ring_pop(Warp& w) { w.cph ^= 1u << w.cs; w.cs ^= 1; }
+// Give the oldest stage back (every lane has finished reading it).
+__device__ __forceinline__ void ring_pop(Warp& w) {
+  __syncwarp();
+  if (w.lane == 0) {
+    const uint32_t bit = 1u << (w.q & 15u);
+    atoms_xor(w.pool + 4, bit);                          // next fill of this stage completes the other phase
+    atoms_or(w.pool, bit);
+  }
+  w.q >>= 4;
+  w.qn -= 1;
+}
 // tiles that were requested ahead for a unit that does not run after all
 __device__ __forceinline__ bool ring_drain(Warp& w) {
-  for (; w.pf_n > 0; --w.pf_n) { if (!ring_wait(w)) return false; ring_pop(w); }
+  while (w.qn > 0) { if (ring_wait(w) < 0) return false; ring_pop(w); }
+  w.pf_n = 0;
   w.pf_k = nullptr;
   return true;
 }
@@ -611,7 +662,7 @@ __device__ __forceinline__ void attn_prefetch_next(Warp& w, const FlowParams& p,
   using C = AttnCfg<HD>;
   int nl = layer + 1, nstep = w.step, grow = 0;
   if (nl == p.n_layer) { nl = 0; nstep = w.step + 1; grow = 1; }
-  if (nstep >= p.n_steps || w.pf_n != 0) return;
+  if (nstep >= p.n_steps || w.pf_n != 0 || w.qn != 0) return;
   const int S = split_count(w.nseq, p.n_head, w.maxT + grow, p.n_sm);
   const int u = attn_unit_of(w.sm, p.n_sm, w.g, nl, nstep, w.nseq * p.n_head * S);
   if (u < 0) return;
@@ -622,15 +673,25 @@ __device__ __forceinline__ void attn_prefetch_next(Warp& w, const FlowParams& p,
   const int n = min(ug.n_tiles, kStages);
   if (n <= 0) return;
   w.pf_k = ug.k;
-  for (int i = 0; i < n; ++i) ring_issue<HD>(w, ug.k + static_cast<size_t>(i) * C::TILE * HD, ug.v + static_cast<size_t>(i) * C::TILE * HD);
-  w.pf_n = n;
+  int got = 0;
+  for (; got < n; ++got)
+    if (!ring_issue<HD>(w, ug.k + static_cast<size_t>(got) * C::TILE * HD, ug.v + static_cast<size_t>(got) * C::TILE * HD)) break;
+  w.pf_n = got;
+  if (got == 0) w.pf_k = nullptr;
 }
 
-// One (sequence, head, key range) unit: flash-decoding with the query in every row of the A operand (all 8 row groups carry
-// the same query, so no lane is special), K tile rows as B (ldmatrix), P V with ldmatrix.trans.
+// One (sequence, head, key range) unit: flash-decoding on the CUDA cores.  A decode query is ONE row: in mma.sync m16n8k16 form it
+// fills 1 of 16 rows, and the 32 HMMAs of a 64-key tile measured 0.85 us for the single warp that owns the unit (legacy HMMA
+// latency, nothing to overlap it with) -- 8 KB / 0.85 us = 10 GB/s per unit.  Here: scores = every lane owns the keys
+// lane, lane + 32, ... of the tile (16-byte shared-memory loads, conflict free thanks to the chunk swizzle, fp32 FMAs against the
+// query held in registers); O += P V = every lane owns two output dims and a 1 / G share of the keys (G = 64 / head_dim lane
+// groups), probabilities passed through 256 bytes of per-warp shared memory.
 template <int HD>
-__device__ __forceinline__ bool unit_attn(Warp& w, const FlowParams& p, int layer, int u, int S) {
+__device__ __forceinline__ bool unit_attn(Warp& w, const FlowParams& p, int layer, int u, int S, uint32_t pbuf) {
   using C = AttnCfg<HD>;
+  constexpr int KPL = C::TILE / 32;                                  // keys per lane in the score pass
+  constexpr int LPR = HD / 2;                                        // lanes per key row in the P V pass (two dims each)
+  constexpr int G = 32 / LPR;                                        // key groups in the P V pass
   const uint32_t st = stamp_of(w.step, layer);
   const int seq = u / (p.n_head * S), head = (u / S) % p.n_head, split = u % S;
   const int fin = __shfl_sync(kFull, w.fin, seq), T = __shfl_sync(kFull, w.len, seq);
@@ -639,29 +700,31 @@ __device__ __forceinline__ bool unit_attn(Warp& w, const FlowParams& p, int laye
   const UnitGeom ug = fin ? UnitGeom{nullptr, nullptr, 0, 0} : unit_geom<HD>(p, layer, seq * p.n_groups + w.g, head, split, S, T);
   // ---- reconcile with what was requested ahead ----
   int issued = 0;
-  if (w.pf_n > 0) {
-    if (w.pf_k == ug.k && ug.n_tiles >= w.pf_n) { issued = w.pf_n; w.pf_n = 0; w.pf_k = nullptr; }
+  if (w.pf_n > 0 || w.qn > 0) {
+    if (w.pf_k == ug.k && ug.n_tiles >= w.pf_n && w.qn == w.pf_n) { issued = w.pf_n; w.pf_n = 0; w.pf_k = nullptr; }
     else if (!ring_drain(w)) return false;
   }
-  if (fin || (ug.n_tiles == 0 && split != 0)) {                      // nothing to attend to: a neutral partial
-    if (w.lane < HD / 4) ll_st2(part_o + 2 * w.lane, 0u, 0u, st);
-    if (w.lane == HD / 4) ll_st2(part_ml, __float_as_uint(-1e30f), 0u, st);
-    return true;
-  }
-  for (; issued < min(ug.n_tiles, kStages); ++issued)
-    ring_issue<HD>(w, ug.k + static_cast<size_t>(issued) * C::TILE * HD, ug.v + static_cast<size_t>(issued) * C::TILE * HD);
-  // ---- query (bf16 pairs, already scaled by log2(e) / sqrt(hd)): pairs 8 kk + tq and 8 kk + tq + 4 of this head ----
+  const bool neutral = fin || (ug.n_tiles == 0 && split != 0);       // nothing to attend to: a neutral partial (after the query wait)
+  // keep up to `cap` tiles in flight (as many as the pool gives)
+  auto top_up = [&](int cap) {
+    while (issued < ug.n_tiles && w.qn < cap) {
+      if (!ring_issue<HD>(w, ug.k + static_cast<size_t>(issued) * C::TILE * HD, ug.v + static_cast<size_t>(issued) * C::TILE * HD)) break;
+      ++issued;
+    }
+  };
+  top_up(3);                                                        // the query is not here yet: do not hog the pool
+  // ---- query: HD / 2 bf16 pairs, already scaled by log2(e) / sqrt(hd); every lane holds the whole vector in fp32 ----
   const uint64_t* qrow = w.xg + p.xc.off_qkv + seq * 384 + head * (HD / 2);
-  uint32_t aq[C::KS][2];
+  float q[HD];
   {
     uint32_t tries = 0;
     while (true) {
       uint32_t bad = 0;
 #pragma unroll
-      for (int kk = 0; kk < C::KS; ++kk) {
-        uint32_t s0, s1;
-        ll_ld1(qrow + kk * 8 + w.tq, aq[kk][0], s0);
-        ll_ld1(qrow + kk * 8 + w.tq + 4, aq[kk][1], s1);
+      for (int j = 0; j < HD / 4; ++j) {
+        uint32_t d0, s0, d1, s1;
+        ll_ld2(qrow + 2 * j, d0, s0, d1, s1);
+        q[4 * j] = bf_lo(d0); q[4 * j + 1] = bf_hi(d0); q[4 * j + 2] = bf_lo(d1); q[4 * j + 3] = bf_hi(d1);
         bad |= (s0 ^ st) | (s1 ^ st);
       }
       if (__all_sync(kFull, bad == 0)) break;
@@ -669,113 +732,112 @@ __device__ __forceinline__ bool unit_attn(Warp& w, const FlowParams& p, int laye
     }
   }
   FLOW_READY(w);
-  float m = -1e30f, l = 0.f, o[C::NT][4];
-#pragma unroll
-  for (int n = 0; n < C::NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
-  const int mrow = w.lane & 7, mat = w.lane >> 3;
+  if (neutral) {
+    // Published only AFTER this layer's query has arrived, like every other partial: the query is what orders this unit behind the
+    // out_proj units of the previous layer, which may still be reading the words this unit overwrites (a unit that publishes
+    // without consuming its input runs ahead of the chain -- that hung ragged / EOS batches)
+    if (w.lane < HD / 4) ll_st2(part_o + 2 * w.lane, 0u, 0u, st);
+    if (w.lane == HD / 4) ll_st2(part_ml, __float_as_uint(-1e30f), 0u, st);
+    return true;
+  }
+  top_up(kMaxInFlight);
+  const int grp = w.lane / LPR, jd = w.lane % LPR;                  // P V pass: key group, dim pair (dims 2 jd, 2 jd + 1)
+  float m = -1e30f, l = 0.f, o0 = 0.f, o1 = 0.f;
   for (int it = 0; it < ug.n_tiles; ++it) {
-    if (!ring_wait(w)) return false;
-    const uint32_t kt = w.ring + w.cs * kStageBytes, vt = kt + C::HALF;
-    const int key_base = ug.key0 + it * C::TILE;
-    // scores of the tile: key group j = keys 8 j .. 8 j + 7; this lane ends up with keys 8 j + 2 tq, + 1
-    float sc[C::TILE / 8][2];
-#pragma unroll
-    for (int j = 0; j < C::TILE / 8; ++j) {
-      const int key = 8 * j + mrow;
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int hh = 0; hh < C::KS / 2; ++hh) {                       // 4 chunks = 2 k-steps per ldmatrix.x4
-        uint32_t r0, r1, r2, r3;
-        ldmatrix_x4(kt + key * C::ROWB + (swz_chunk(HD, key, hh * 4 + mat) << 4), r0, r1, r2, r3);
-        mma_bf16_16816(c, aq[2 * hh][0], aq[2 * hh][0], aq[2 * hh][1], aq[2 * hh][1], r0, r1);
-        mma_bf16_16816(c, aq[2 * hh + 1][0], aq[2 * hh + 1][0], aq[2 * hh + 1][1], aq[2 * hh + 1][1], r2, r3);
+    if (w.qn == 0) {                                                  // the pool was empty when this tile was due: insist
+      uint32_t tries = 0;
+      while (true) {
+        top_up(kMaxInFlight);
+        if (w.qn > 0) break;
+        if (!poll_ok(w, tries, 602 + layer * 10)) return false;
       }
-      const int k0 = key_base + 8 * j + 2 * w.tq;
-      sc[j][0] = k0 < T ? c[0] : -1e30f;
-      sc[j][1] = k0 + 1 < T ? c[1] : -1e30f;
     }
-    float tm = -1e30f;
+    const unsigned long long tw0 = w.prof ? ptx::global_timer_ns() : 0ull;
+    const int stg = ring_wait(w);
+    if (stg < 0) return false;
+    if (w.prof && w.lane == 0) { w.prof[3] += ptx::global_timer_ns() - tw0; w.prof[4] += 1; }
+    const uint32_t kt = w.ring + stg * kStageBytes, vt = kt + C::HALF;
+    const int key_base = ug.key0 + it * C::TILE;
+    const long long tc0 = w.prof ? clock64() : 0;
+    // ---- scores of this lane's keys (log2 domain) ----
+    float sc[KPL];
 #pragma unroll
-    for (int j = 0; j < C::TILE / 8; ++j) tm = fmaxf(tm, fmaxf(sc[j][0], sc[j][1]));
-    tm = fmaxf(tm, __shfl_xor_sync(kFull, tm, 1));
-    tm = fmaxf(tm, __shfl_xor_sync(kFull, tm, 2));
+    for (int a = 0; a < KPL; ++a) {
+      const int key = w.lane + 32 * a;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < C::ROWB / 16; ++c) {
+        const uint4 kv = lds128(kt + key * C::ROWB + (swz_chunk(HD, key, c) << 4));
+        acc0 = fmaf(q[8 * c + 0], bf_lo(kv.x), acc0); acc1 = fmaf(q[8 * c + 1], bf_hi(kv.x), acc1);
+        acc0 = fmaf(q[8 * c + 2], bf_lo(kv.y), acc0); acc1 = fmaf(q[8 * c + 3], bf_hi(kv.y), acc1);
+        acc0 = fmaf(q[8 * c + 4], bf_lo(kv.z), acc0); acc1 = fmaf(q[8 * c + 5], bf_hi(kv.z), acc1);
+        acc0 = fmaf(q[8 * c + 6], bf_lo(kv.w), acc0); acc1 = fmaf(q[8 * c + 7], bf_hi(kv.w), acc1);
+      }
+      sc[a] = key_base + key < T ? acc0 + acc1 : -1e30f;
+    }
+    float tm = sc[0];
+#pragma unroll
+    for (int a = 1; a < KPL; ++a) tm = fmaxf(tm, sc[a]);
+    tm = warp_max(tm);
     const float mn = fmaxf(m, tm), corr = fast_exp2(m - mn);
     m = mn;
-    l *= corr;
+    l *= corr; o0 *= corr; o1 *= corr;
+    __syncwarp();                                                    // the previous tile's P V pass has read the probabilities
 #pragma unroll
-    for (int n = 0; n < C::NT; ++n) { o[n][0] *= corr; o[n][1] *= corr; }
-    uint32_t pa[C::TILE / 8];
-#pragma unroll
-    for (int j = 0; j < C::TILE / 8; ++j) {
-      const float p0 = sc[j][0] > -1e29f ? fast_exp2(sc[j][0] - mn) : 0.f, p1 = sc[j][1] > -1e29f ? fast_exp2(sc[j][1] - mn) : 0.f;
-      l += p0 + p1;
-      pa[j] = pack_bf16(p0, p1);
-    }
-    // O += P V: k-step kk = keys 16 kk .. 16 kk + 15 (score groups 2 kk, 2 kk + 1), n-tile pair np = dims 16 np .. 16 np + 15
-#pragma unroll
-    for (int kk = 0; kk < C::TILE / 16; ++kk) {
-      const int key = 16 * kk + 8 * (mat & 1) + mrow;
-#pragma unroll
-      for (int np = 0; np < C::NT / 2; ++np) {
-        uint32_t r0, r1, r2, r3;
-        ldmatrix_x4_trans(vt + key * C::ROWB + (swz_chunk(HD, key, 2 * np + (mat >> 1)) << 4), r0, r1, r2, r3);
-        mma_bf16_16816(o[2 * np], pa[2 * kk], pa[2 * kk], pa[2 * kk + 1], pa[2 * kk + 1], r0, r1);
-        mma_bf16_16816(o[2 * np + 1], pa[2 * kk], pa[2 * kk], pa[2 * kk + 1], pa[2 * kk + 1], r2, r3);
-      }
+    for (int a = 0; a < KPL; ++a) {
+      const float pr = sc[a] > -1e29f ? fast_exp2(sc[a] - mn) : 0.f;
+      l += pr;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(pbuf + (w.lane + 32 * a) * 4), "f"(pr) : "memory");
     }
     __syncwarp();
-    ring_pop(w);
-    if (issued < ug.n_tiles) {
-      ring_issue<HD>(w, ug.k + static_cast<size_t>(issued) * C::TILE * HD, ug.v + static_cast<size_t>(issued) * C::TILE * HD);
-      ++issued;
+    const long long tc1 = w.prof ? clock64() : 0;
+    // ---- O += P V: this lane's two dims over the keys G i + grp ----
+#pragma unroll 8
+    for (int i = 0; i < C::TILE / G; ++i) {
+      const int key = G * i + grp;
+      uint32_t vw; float pr;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vw) : "r"(vt + key * C::ROWB + (swz_chunk(HD, key, jd >> 2) << 4) + (jd & 3) * 4));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pr) : "r"(pbuf + key * 4));
+      o0 = fmaf(pr, bf_lo(vw), o0);
+      o1 = fmaf(pr, bf_hi(vw), o1);
     }
+    if (w.prof && w.lane == 0) { const long long tc2 = clock64(); w.prof[6] += tc1 - tc0; w.prof[7] += tc2 - tc1; }
+    ring_pop(w);
+    top_up(kMaxInFlight);
   }
+  if (w.prof && w.lane == 0) w.prof[5] = ptx::global_timer_ns();
   attn_prefetch_next<HD>(w, p, layer);
+  if (G == 2) { o0 += __shfl_xor_sync(kFull, o0, 16); o1 += __shfl_xor_sync(kFull, o1, 16); }
+  l = warp_sum(l);
   // ---- the new token's own key / value (split 0): from the qkv words, not from the cache ----
   if (split == 0) {
     const uint64_t* krow = qrow + 128, *vrow = qrow + 256;
-    uint32_t kn[C::KS][2], vn[C::NT];
+    uint32_t kn, vn;
     uint32_t tries = 0;
     while (true) {
-      uint32_t bad = 0, s0, s1;
-#pragma unroll
-      for (int kk = 0; kk < C::KS; ++kk) {
-        ll_ld1(krow + kk * 8 + w.tq, kn[kk][0], s0);
-        ll_ld1(krow + kk * 8 + w.tq + 4, kn[kk][1], s1);
-        bad |= (s0 ^ st) | (s1 ^ st);
-      }
-#pragma unroll
-      for (int n = 0; n < C::NT; ++n) { ll_ld1(vrow + 4 * n + w.tq, vn[n], s0); bad |= s0 ^ st; }
-      if (__all_sync(kFull, bad == 0)) break;
+      uint32_t s0, s1;
+      ll_ld1(krow + jd, kn, s0);
+      ll_ld1(vrow + jd, vn, s1);
+      if (__all_sync(kFull, ((s0 ^ st) | (s1 ^ st)) == 0)) break;
       if (!poll_ok(w, tries, 601 + layer * 10)) return false;
     }
-    float s = 0.f;
+    // lane jd of the first group multiplies its pair of dims (q is indexed statically through a select chain)
+    float qa = 0.f, qb = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < C::KS; ++kk) {
-      s = fmaf(bf_lo(aq[kk][0]), bf_lo(kn[kk][0]), s); s = fmaf(bf_hi(aq[kk][0]), bf_hi(kn[kk][0]), s);
-      s = fmaf(bf_lo(aq[kk][1]), bf_lo(kn[kk][1]), s); s = fmaf(bf_hi(aq[kk][1]), bf_hi(kn[kk][1]), s);
-    }
-    s += __shfl_xor_sync(kFull, s, 1);
-    s += __shfl_xor_sync(kFull, s, 2);
+    for (int j = 0; j < LPR; ++j) { qa = jd == j ? q[2 * j] : qa; qb = jd == j ? q[2 * j + 1] : qb; }
+    float s = w.lane < LPR ? fmaf(qa, bf_lo(kn), qb * bf_hi(kn)) : 0.f;
+    s = warp_sum(s);
     const float mn = fmaxf(m, s), corr = fast_exp2(m - mn), pn = fast_exp2(s - mn);
     m = mn;
-    l = l * corr + (w.tq == 0 ? pn : 0.f);
-#pragma unroll
-    for (int n = 0; n < C::NT; ++n) {
-      o[n][0] = o[n][0] * corr + pn * bf_lo(vn[n]);
-      o[n][1] = o[n][1] * corr + pn * bf_hi(vn[n]);
-    }
+    l = l * corr + pn;
+    o0 = o0 * corr + pn * bf_lo(vn);
+    o1 = o1 * corr + pn * bf_hi(vn);
   }
-  l += __shfl_xor_sync(kFull, l, 1);
-  l += __shfl_xor_sync(kFull, l, 2);
   // ---- publish: normalised output as bf16 pairs in the order the out_proj units read them, then (max, sum) ----
-  if (w.qd == 0) {
+  if (w.lane < LPR) {
     const float inv = l > 0.f ? 1.0f / l : 0.f;
-#pragma unroll
-    for (int kk = 0; kk < C::NT / 2; ++kk)
-      ll_st2(part_o + kk * 8 + 2 * w.tq, pack_bf16(o[2 * kk][0] * inv, o[2 * kk][1] * inv),
-             pack_bf16(o[2 * kk + 1][0] * inv, o[2 * kk + 1][1] * inv), st);
-    if (w.tq == 0) ll_st2(part_ml, __float_as_uint(m), __float_as_uint(l), st);
+    ll_st1(part_o + pair_pos(jd), pack_bf16(o0 * inv, o1 * inv), st);
+    if (w.lane == 0) ll_st2(part_ml, __float_as_uint(m), __float_as_uint(l), st);
   }
   return true;
 }
@@ -798,6 +860,9 @@ __device__ __forceinline__ void publish_token(Warp& w, const FlowParams& p, int 
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = 0.f;
   }
+  uint64_t* xb = w.xg + p.xc.off_xb + seq * (D / 2);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ll_st1(xb + pair_pos(w.lane * 4 + e), pack_bf16(x[2 * e], x[2 * e + 1]), stx);
 #pragma unroll
   for (int e = 0; e < 4; ++e) ll_st2(xr + 2 * e, __float_as_uint(x[2 * e]), __float_as_uint(x[2 * e + 1]), stx);
   if (w.lane == 0) ll_st1(tw, static_cast<uint32_t>(tok) | (fin ? 0x80000000u : 0u), static_cast<uint32_t>(step_done + 2));
@@ -825,7 +890,6 @@ __device__ __forceinline__ bool unit_sample(Warp& w, const FlowParams& p, int se
   const SampleParams sp = *p.sp;
   const int b = seq * p.n_groups + w.g;
   const int fin_before = __shfl_sync(kFull, w.fin, seq);
-  if (fin_before) { publish_token(w, p, seq, 0, 1, w.step); return true; }
   const int nnew = __shfl_sync(kFull, w.nnew, seq), maxnew = __shfl_sync(kFull, w.maxnew, seq);
   const int out0 = __shfl_sync(kFull, w.out0, seq), len = __shfl_sync(kFull, w.len, seq);
   const uint32_t st = stamp_of(w.step, p.n_layer);
@@ -833,11 +897,11 @@ __device__ __forceinline__ bool unit_sample(Warp& w, const FlowParams& p, int se
   const uint64_t* tm = w.xg + p.xc.off_tmax + seq * p.xc.nt_pad;
   const uint64_t* lg = w.xg + p.xc.off_logits + seq * ldl;
   int tok = 0;
-  if (p.forced) {
-    tok = w.step + 1 < p.n_steps ? p.forced[static_cast<size_t>(b) * p.forced_stride + w.step] : 0;
-  } else {
-    // ---- tile maxima: tile 64 j + 2 lane + e ----
-    uint32_t key[2 * kTmaxLoads];
+  // ---- tile maxima: tile 64 j + 2 lane + e.  EVERY path waits for them, also a finished or teacher-forced sequence that does
+  // not look at the logits: publishing the next step's row overwrites this sequence's x words, which the head units of other SMs
+  // may still be reading -- all tile maxima of this step present = every head unit has consumed the row. ----
+  uint32_t key[2 * kTmaxLoads];
+  {
     const int nld = p.xc.nt_pad / 64;
     if (!ll_wait_word(w, tm, st, 700)) return false;
     uint32_t tries = 0;
@@ -858,6 +922,11 @@ __device__ __forceinline__ bool unit_sample(Warp& w, const FlowParams& p, int se
       if (!poll_ok(w, tries, 701)) return false;
     }
     FLOW_READY(w);
+  }
+  if (fin_before) { publish_token(w, p, seq, 0, 1, w.step); return true; }
+  if (p.forced) {
+    tok = w.step + 1 < p.n_steps ? p.forced[static_cast<size_t>(b) * p.forced_stride + w.step] : 0;
+  } else {
     const int top_k = sp.top_k;
     if (top_k == 1) {
       // greedy: the best tile (lowest index on ties), then the best row of it (lowest index on ties)
@@ -907,32 +976,37 @@ __device__ __forceinline__ bool unit_sample(Warp& w, const FlowParams& p, int se
         for (int j = 0; j < 2 * kTmaxLoads; ++j)
           if (key[j] >= thr && key[j] != 0u) { if (pos < 256) tlist[pos] = static_cast<uint16_t>(64 * (j >> 1) + 2 * w.lane + (j & 1)); ++pos; }
         __syncwarp();
-        // gather the logits of those tiles (16 per tile), keep the ones >= thr
+        // gather the logits of those tiles (8 row pairs per tile, 16 bytes per load), keep the ones >= thr
         n_c = 0;
-        const int items = min(n_t, 256) * 16;
+        const int items = min(n_t, 256) * 8;
         bool overflow = n_t > 256;
-        for (int base = 0; base < items && !overflow; base += 256) {
-          uint32_t d[8], s[8];
+        for (int base = 0; base < items && !overflow; base += 512) {
+          uint32_t d[16][2];
           uint32_t tr3 = 0;
           while (true) {
             uint32_t bad = 0;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int it = base + e * 32 + w.lane, itc = min(it, items - 1);     // past the end: re-read the last item, drop it
-              ll_ld1(lg + tlist[itc >> 4] * 16 + (itc & 15), d[e], s[e]);
-              bad |= s[e] ^ st;
+            for (int e = 0; e < 16; ++e) {
+              const int itc = min(base + e * 32 + w.lane, items - 1);             // past the end: re-read the last pair, drop it
+              uint32_t s0, s1;
+              ll_ld2(lg + tlist[itc >> 3] * 16 + (itc & 7) * 2, d[e][0], s0, d[e][1], s1);
+              bad |= (s0 ^ st) | (s1 ^ st);
             }
             if (__all_sync(kFull, bad == 0)) break;
             if (!poll_ok(w, tr3, 703)) return false;
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < 16; ++e) {
             const int it = base + e * 32 + w.lane;
-            const bool keep = it < items && float_key(__uint_as_float(d[e])) >= thr;
-            const uint32_t bal = __ballot_sync(kFull, keep);
-            const int at = n_c + __popc(bal & ((1u << w.lane) - 1u));
-            if (keep && at < kCandCap) { cval[at] = __uint_as_float(d[e]); cidx[at] = tlist[it >> 4] * 16 + (it & 15); }
-            n_c += __popc(bal);
+            if (base + e * 32 >= items) break;                                    // warp-uniform
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const bool keep = it < items && float_key(__uint_as_float(d[e][hh])) >= thr;
+              const uint32_t bal = __ballot_sync(kFull, keep);
+              const int at = n_c + __popc(bal & ((1u << w.lane) - 1u));
+              if (keep && at < kCandCap) { cval[at] = __uint_as_float(d[e][hh]); cidx[at] = tlist[it >> 3] * 16 + (it & 7) * 2 + hh; }
+              n_c += __popc(bal);
+            }
           }
           if (n_c > kCandCap) overflow = true;
         }
@@ -941,6 +1015,7 @@ __device__ __forceinline__ bool unit_sample(Warp& w, const FlowParams& p, int se
         else n_c = min(n_c, kCandCap);                                 // massive ties at the threshold: any of them are a valid top-k
       }
       __syncwarp();
+      if (w.prof && w.lane == 0) w.prof[3] = ptx::global_timer_ns();
       // ---- exactly top_k of the candidates: values above the k-th largest candidate, plus the first ties in list order ----
       uint32_t ck[kCandCap / 32]; float cv[kCandCap / 32];
 #pragma unroll
@@ -950,7 +1025,31 @@ __device__ __forceinline__ bool unit_sample(Warp& w, const FlowParams& p, int se
         ck[e] = j < n_c ? float_key(cv[e]) : 0u;
       }
       const int k_eff = min(top_k, n_c);
-      const uint32_t kth = kth_largest_key(ck, k_eff, 32);
+      uint32_t kth;
+      if (n_c - k_eff <= 8) {
+        // the usual case (a handful of extra candidates): walk the distinct values upwards until the n_c - k_eff keys to drop
+        // are used up; the value the cut falls into is the k-th largest
+        const int drop = n_c - k_eff;
+        uint32_t cur = 0;
+        int removed = 0;
+        kth = 0;
+        for (int r = 0; r <= drop; ++r) {
+          uint32_t mn = 0xffffffffu;
+#pragma unroll
+          for (int e = 0; e < kCandCap / 32; ++e) if (ck[e] > cur && ck[e] < mn) mn = ck[e];     // absent entries are key 0
+          mn = __reduce_min_sync(kFull, mn);
+          int cnt = 0;
+#pragma unroll
+          for (int e = 0; e < kCandCap / 32; ++e) cnt += ck[e] == mn;
+          cnt = __reduce_add_sync(kFull, cnt);
+          kth = mn;
+          if (removed + cnt > drop) break;
+          removed += cnt;
+          cur = mn;
+        }
+      } else {
+        kth = kth_largest_key(ck, k_eff, 32);
+      }
       int above = 0;
 #pragma unroll
       for (int e = 0; e < kCandCap / 32; ++e) above += ck[e] > kth;
@@ -986,11 +1085,13 @@ __device__ __forceinline__ bool unit_sample(Warp& w, const FlowParams& p, int se
       for (int o = 16; o > 0; o >>= 1) { pick = min(pick, __shfl_xor_sync(kFull, pick, o)); last = max(last, __shfl_xor_sync(kFull, last, o)); }
       if (pick == 0x7fffffff) pick = max(last, 0);                     // rounding corner: the last kept entry
       tok = cidx[pick];
+      if (w.prof && w.lane == 0) w.prof[4] = ptx::global_timer_ns();
     }
   }
   const int n = nnew + 1;
   const int fin_now = (!p.forced && tok == sp.eos_id) || n >= maxnew;
   publish_token(w, p, seq, tok, fin_now, w.step);
+  if (w.prof && w.lane == 0) w.prof[5] = ptx::global_timer_ns();
   if (w.lane == 0) {
     p.st.out_ids[static_cast<size_t>(b) * p.st.out_stride + out0 + nnew] = tok;       // api_cache.py:179
     if (fin_now || w.step + 1 >= p.n_steps) {
@@ -1008,7 +1109,7 @@ __device__ __forceinline__ int sampler_sm(int n_sm, int g, int seq, int step) { 
 // Every unit is its own (non-inlined) function: with everything inlined into the step loop, ptxas hoisted the address
 // arithmetic of ALL units out of the loop and spilled it (1 KB of local memory per thread next to 225 KB of shared memory,
 // i.e. an L1 of ~30 KB: every spill was an L2 round trip).  The per-warp state a unit needs travels by value.
-struct RingState { int cs, is; uint32_t cph; int pf_n; const bf16* pf_k; };     // K/V ring of one warp (shared memory)
+struct RingState { uint32_t q; int qn; int pf_n; const bf16* pf_k; };            // stages one warp has in flight (shared memory)
 
 struct UnitCtx {                        // what the step loop hands to a unit
   int g, nseq, step, sm;
@@ -1016,16 +1117,16 @@ struct UnitCtx {                        // what the step loop hands to a unit
   unsigned long long* prof;            // slot of this unit in the timeline (null: not profiled)
 };
 
-__device__ __forceinline__ Warp make_warp(const FlowParams& p, const UnitCtx& c, uint32_t ring, uint32_t bars, const RingState* rs) {
+__device__ __forceinline__ Warp make_warp(const FlowParams& p, const UnitCtx& c, uint32_t ring, uint32_t bars, const RingState* rs, uint32_t pool = 0) {
   Warp w;
   w.g = c.g; w.lane = threadIdx.x & 31; w.sm = c.sm; w.nseq = c.nseq; w.qd = w.lane >> 2; w.tq = w.lane & 3;
   w.xg = p.xc.base + static_cast<size_t>(c.g) * p.xc.group_words;
   w.status = p.status;
   w.len = c.len; w.fin = c.fin; w.nnew = c.nnew; w.maxnew = c.maxnew; w.out0 = c.out0; w.maxT = c.maxT;
   w.step = c.step;
-  w.ring = ring; w.bars = bars;
-  if (rs) { w.cs = rs->cs; w.is = rs->is; w.cph = rs->cph; w.pf_n = rs->pf_n; w.pf_k = rs->pf_k; }
-  else { w.cs = w.is = 0; w.cph = 0; w.pf_n = 0; w.pf_k = nullptr; }
+  w.ring = ring; w.bars = bars; w.pool = pool;
+  if (rs) { w.q = rs->q; w.qn = rs->qn; w.pf_n = rs->pf_n; w.pf_k = rs->pf_k; }
+  else { w.q = 0; w.qn = 0; w.pf_n = 0; w.pf_k = nullptr; }
   w.pol = 0;
   w.dead = false;
   w.prof = c.prof; w.t_ready = 0;
@@ -1070,13 +1171,13 @@ __device__ __noinline__ bool run_sample(const FlowParams& p, UnitCtx c, int seq,
   return unit_done(w, unit_sample(w, p, seq, scratch), t0);
 }
 template <int HD>
-__device__ __noinline__ bool run_attn(const FlowParams& p, UnitCtx c, int layer, int u, int S, uint32_t ring, uint32_t bars, RingState* rs) {
+__device__ __noinline__ bool run_attn(const FlowParams& p, UnitCtx c, int layer, int u, int S, uint32_t ring, uint32_t bars, RingState* rs, uint32_t pool, uint32_t pbuf) {
   const unsigned long long t0 = FLOW_T0(c);
-  Warp w = make_warp(p, c, ring, bars, rs);
+  Warp w = make_warp(p, c, ring, bars, rs, pool);
   w.pol = make_evict_first_policy();
-  const bool ok = unit_attn<HD>(w, p, layer, u, S);
+  const bool ok = unit_attn<HD>(w, p, layer, u, S, pbuf);
   __syncwarp();
-  if (w.lane == 0) { rs->cs = w.cs; rs->is = w.is; rs->cph = w.cph; rs->pf_n = w.pf_n; rs->pf_k = w.pf_k; }
+  if (w.lane == 0) { rs->q = w.q; rs->qn = w.qn; rs->pf_n = w.pf_n; rs->pf_k = w.pf_k; }
   __syncwarp();
   return unit_done(w, ok, t0);
 }
@@ -1084,8 +1185,8 @@ __device__ __noinline__ void run_publish(const FlowParams& p, UnitCtx c, int seq
   Warp w = make_warp(p, c, 0, 0, nullptr);
   publish_token(w, p, seq, tok, fin, c.step);
 }
-__device__ __noinline__ void run_drain(const FlowParams& p, UnitCtx c, uint32_t ring, uint32_t bars, RingState* rs) {
-  Warp w = make_warp(p, c, ring, bars, rs);
+__device__ __noinline__ void run_drain(const FlowParams& p, UnitCtx c, uint32_t ring, uint32_t bars, RingState* rs, uint32_t pool) {
+  Warp w = make_warp(p, c, ring, bars, rs, pool);
   ring_drain(w);
 }
 
@@ -1095,6 +1196,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_flow_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ SmProgram prog;
   __shared__ RingState rstate[kMaxGroups];
+  __shared__ uint32_t pool_words[2];                                 // {free stage mask, parity mask}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sm = blockIdx.x;
   // shared memory: [rings 8 x 2 x 8 KB][scratch 8 x 1.5 KB][barriers][weight blob]
@@ -1104,7 +1206,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_flow_kernel(const __grid_c
   uint8_t* blob = reinterpret_cast<uint8_t*>(bars) + 128;
   {
     if (threadIdx.x < sizeof(SmProgram) / 4) reinterpret_cast<int32_t*>(&prog)[threadIdx.x] = reinterpret_cast<const int32_t*>(&p.prog[sm])[threadIdx.x];
-    if (threadIdx.x < kMaxGroups) rstate[threadIdx.x] = RingState{0, 0, 0u, 0, nullptr};
+    if (threadIdx.x < kMaxGroups) rstate[threadIdx.x] = RingState{0u, 0, 0, nullptr};
+    if (threadIdx.x == 0) { pool_words[0] = (1u << kPoolStages) - 1u; pool_words[1] = 0u; }
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(p.packed + prog.blob_off);
     uint4* dst = reinterpret_cast<uint4*>(blob);
@@ -1118,7 +1221,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_flow_kernel(const __grid_c
   UnitCtx c;
   c.g = warp; c.sm = sm; c.step = -1; c.prof = nullptr;
   c.nseq = (p.B - warp + p.n_groups - 1) / p.n_groups;               // sequences b = i * n_groups + g
-  const uint32_t ring = ptx::smem_u32(rings + warp * kStages * kStageBytes), rbars = ptx::smem_u32(&bars[warp * kStages]);
+  const uint32_t ring = ptx::smem_u32(rings), rbars = ptx::smem_u32(&bars[0]), pool = ptx::smem_u32(&pool_words[0]);
   const uint32_t blob_addr = ptx::smem_u32(blob);
   uint64_t* const xg = p.xc.base + static_cast<size_t>(warp) * p.xc.group_words;
   {
@@ -1156,8 +1259,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_flow_kernel(const __grid_c
       while (true) {
         if ((lane & 7) < c.nseq) ll_ld1(tw, d, s);
         if (__all_sync(kFull, s == static_cast<uint32_t>(step + 1))) break;
-        if (++tries > kMaxTries) { flow_report(p.status, FS_TIMEOUT_LL, sm, warp, 800); alive = false; break; }
-        if ((tries & 255u) == 0 && *reinterpret_cast<volatile int32_t*>(p.status) != 0) { alive = false; break; }
+        if (++tries > kMaxTries) { flow_report(p.status, FS_TIMEOUT_LL, sm, warp, 800); flow_waitlog(p.status, sm, warp, 800, step); alive = false; break; }
+        if ((tries & 255u) == 0 && *reinterpret_cast<volatile int32_t*>(p.status) != 0) { flow_waitlog(p.status, sm, warp, 800, step); alive = false; break; }
       }
       if (!alive) break;
       if (step > 0 && !c.fin) { c.nnew += 1; c.len += 1; }
@@ -1171,15 +1274,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_flow_kernel(const __grid_c
     const int S = split_count(c.nseq, p.n_head, c.maxT, p.n_sm);
     // optional timeline of group 0 in ONE step: per SM and unit slot (layer * 5 + kind | 5 L head | 5 L + 1 sampler): entry, inputs
     // complete, done (globaltimer ns)
-    unsigned long long* const prof = (p.prof && warp == 0 && step == p.prof_steps) ? p.prof + static_cast<size_t>(sm) * 48 * 6 : nullptr;
-#define FLOW_SLOT(slot) (c.prof = prof ? prof + (slot) * 6 : nullptr)
+    unsigned long long* const prof = (p.prof && warp == 0 && step == p.prof_steps) ? p.prof + static_cast<size_t>(sm) * 48 * 8 : nullptr;
+#define FLOW_SLOT(slot) (c.prof = prof ? prof + (slot) * 8 : nullptr)
     for (int layer = 0; layer < p.n_layer && alive; ++layer) {
       const int ut = prog.unit_type[layer], tile = prog.unit_tile[layer];
       const uint32_t wt = blob_addr + prog.unit_off[layer];
       if (ut == U_QKV) { FLOW_SLOT(layer * 5 + 0); alive = run_qkv<HD>(p, c, layer, tile, wt); }
       if (!alive) break;
       const int u = attn_unit_of(sm, p.n_sm, warp, layer, step, c.nseq * p.n_head * S);
-      if (u >= 0) { FLOW_SLOT(layer * 5 + 1); alive = run_attn<HD>(p, c, layer, u, S, ring, rbars, &rstate[warp]); }
+      if (u >= 0) { FLOW_SLOT(layer * 5 + 1); alive = run_attn<HD>(p, c, layer, u, S, ring, rbars, &rstate[warp], pool, ptx::smem_u32(scratch + warp * kScratchBytes)); }
       if (!alive) break;
       if (ut == U_OUT) { FLOW_SLOT(layer * 5 + 2); alive = run_out<HD>(p, c, layer, tile, wt, S); }
       else if (ut == U_MLP1) { FLOW_SLOT(layer * 5 + 3); alive = run_mlp1(p, c, layer, tile, wt); }
@@ -1192,7 +1295,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_flow_kernel(const __grid_c
   }
   // tiles still in flight must land before the CTA may exit
   c.prof = nullptr;
-  if (rstate[warp].pf_n > 0) run_drain(p, c, ring, rbars, &rstate[warp]);
+  if (rstate[warp].qn > 0) run_drain(p, c, ring, rbars, &rstate[warp], pool);
 }
 
 // ---- weight packing -------------------------------------------------------------------------------
@@ -1213,7 +1316,7 @@ struct PackSrc {
 // log2(e) / sqrt(hd) into the q rows (scores come out in the log2 domain).
 __global__ void flow_pack_kernel(const PackTile* tiles, PackSrc src, uint8_t* packed) {
   const PackTile t = tiles[blockIdx.x];
-  const bool perm = t.type == 0 || t.type == 2;                      // outputs published as bf16 pairs
+  const bool perm = t.type != 4;                                     // every tile but the head's: outputs published as pairs
   const int K = t.type == 3 ? DFF : D;
   const float* W; const float* bias; const float* cs = nullptr; const float* cb = nullptr;
   int rows;
@@ -1306,9 +1409,11 @@ FlowExchange flow_exchange_layout(int V, int n_head, int head_dim, int n_sm) {
   x.nt_pad = (x.nt + 63) / 64 * 64;
   int o = 0;
   x.off_xin = o; o += kGroupSeqs * D;
+  x.off_xb = o; o += kGroupSeqs * (D / 2);
   x.off_qkv = o; o += kGroupSeqs * 384;
   x.off_part = o; o += kGroupSeqs * 4 * (D / 2) + kGroupSeqs * 4 * 8 * 2;     // outputs + (max, sum) pairs, kMaxSplits = 4
   x.off_x1 = o; o += kGroupSeqs * D;
+  x.off_x1b = o; o += kGroupSeqs * (D / 2);
   x.off_h = o; o += kGroupSeqs * 512;
   x.off_tok = o; o += 16;
   x.off_tmax = o; o += kGroupSeqs * x.nt_pad;

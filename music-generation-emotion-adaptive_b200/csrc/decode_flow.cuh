@@ -46,7 +46,7 @@ struct FlowLayer {
 struct FlowExchange {
   uint64_t* base;                      // [groups][group_words]
   int64_t group_words;
-  int32_t off_xin, off_qkv, off_part, off_x1, off_h, off_logits, off_tmax, off_tok;   // word offsets inside a group
+  int32_t off_xin, off_xb, off_qkv, off_part, off_x1, off_x1b, off_h, off_logits, off_tmax, off_tok;   // word offsets inside a group
   int32_t nt, nt_pad;                  // vocabulary tiles, padded to a multiple of 64
 };
 

@@ -148,6 +148,8 @@ namespace {
 
 bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits = nullptr,
                      const int32_t* forced = nullptr, int forced_stride = 0, const int32_t* dbg_slot = nullptr);
+// flow status block: [0..3] first failure (code, SM, group, detail), [8 + 2 (sm * 8 + group)] = what every warp was waiting for
+constexpr int kFlowStatusInts = 8 + 2 * flow::kMaxSM * flow::kMaxGroups;
 bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits = nullptr,
                      const int32_t* forced = nullptr, int forced_stride = 0, const int32_t* dbg_slot = nullptr);
 // The persistent decode paths, best first: the weight-stationary flow kernel (decode_flow.cu), then the cluster kernel
@@ -496,8 +498,8 @@ int setup_flow(mg_engine* e) {
     MG_TRY(e->dmalloc(&e->d_flow_packed, e->flow_plan->packed_bytes));
     MG_TRY(e->dmalloc(&e->d_flow_prog, sizeof(flow::SmProgram) * e->n_sm));
     MG_TRY(e->dmalloc(&e->d_flow_layers, sizeof(flow::FlowLayer) * L));
-    MG_TRY(e->dmalloc(&e->d_flow_status, 4 * sizeof(int32_t)));
-    MG_CUDA_OK(cudaMallocHost(&e->h_flow_status, 4 * sizeof(int32_t)));
+    MG_TRY(e->dmalloc(&e->d_flow_status, kFlowStatusInts * sizeof(int32_t)));
+    MG_CUDA_OK(cudaMallocHost(&e->h_flow_status, kFlowStatusInts * sizeof(int32_t)));
     uint64_t* xbase = nullptr;
     MG_TRY(e->dmalloc(&xbase, sizeof(uint64_t) * e->flow_xc.group_words * flow::kMaxGroups));
     e->flow_xc.base = xbase;
@@ -553,7 +555,7 @@ bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   p.dbg_logits = dbg_logits; p.dbg_slot = dbg_slot; p.forced = forced; p.forced_stride = forced_stride;
   p.status = e->d_flow_status;
   p.prof = nullptr; p.prof_steps = 0;
-  const size_t prof_words = static_cast<size_t>(flow::kMaxSM) * 48 * 6;
+  const size_t prof_words = static_cast<size_t>(flow::kMaxSM) * 48 * 8;
   if (const char* ps = std::getenv("MG_FLOW_PROF")) {               // debug: timeline of group 0 in one step -> stderr
     p.prof_steps = std::max(0, std::atoi(ps));
     if (!e->d_flow_prof && e->dmalloc(&e->d_flow_prof, sizeof(unsigned long long) * prof_words) != MG_OK) e->d_flow_prof = nullptr;
@@ -564,7 +566,7 @@ bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
     *rc = fail(MG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
     return false;
   };
-  if (!cuda_ok(cudaMemsetAsync(e->d_flow_status, 0, 4 * sizeof(int32_t), e->stream), "flow status reset")) return true;
+  if (!cuda_ok(cudaMemsetAsync(e->d_flow_status, 0, kFlowStatusInts * sizeof(int32_t), e->stream), "flow status reset")) return true;
   // stamps restart at every launch: the exchange words of the previous job must not look valid
   if (!cuda_ok(cudaMemsetAsync(e->flow_xc.base, 0, sizeof(uint64_t) * e->flow_xc.group_words * flow::kMaxGroups, e->stream),
                "flow exchange reset")) return true;
@@ -572,7 +574,7 @@ bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
     *rc = flow::flow_relayout_kv(e->stream, reinterpret_cast<const bf16*>(e->layers[l].kc), reinterpret_cast<const bf16*>(e->layers[l].vc),
                                  e->flow_layers[l].kc, e->flow_layers[l].vc, e->st.lens, B, g.n_head, hd, e->max_seq, e->flow_tcap);
   if (*rc == MG_OK) *rc = flow::launch_decode_flow(e->stream, p, e->flow_plan->smem_bytes);
-  if (*rc == MG_OK && !cuda_ok(cudaMemcpyAsync(e->h_flow_status, e->d_flow_status, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream),
+  if (*rc == MG_OK && !cuda_ok(cudaMemcpyAsync(e->h_flow_status, e->d_flow_status, kFlowStatusInts * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream),
                                "flow status copy")) return true;
   if (p.prof && *rc == MG_OK) {
     std::vector<unsigned long long> h(prof_words);
@@ -580,13 +582,13 @@ bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
     cudaMemcpy(h.data(), e->d_flow_prof, sizeof(unsigned long long) * prof_words, cudaMemcpyDeviceToHost);
     static const char* kind[5] = {"qkv", "attn", "out", "mlp1", "mlp2"};
     unsigned long long t_origin = ~0ull;
-    for (size_t i = 0; i < prof_words; i += 6) if (h[i]) t_origin = std::min(t_origin, h[i]);
+    for (size_t i = 0; i < prof_words; i += 8) if (h[i]) t_origin = std::min(t_origin, h[i]);
     fprintf(stderr, "[flow prof] step %d, group 0: per phase over its units: n | entry first..last | inputs complete first..last | done first..last | "
             "mean (done - inputs complete) ns\n", p.prof_steps);
     for (int slot = 0; slot < 5 * g.n_layer + 2; ++slot) {
       unsigned long long e0 = ~0ull, e1 = 0, r0 = ~0ull, r1 = 0, d0 = ~0ull, d1 = 0, work = 0, sen0 = ~0ull, sen1 = 0, retr = 0, rd = 0; int n = 0;
       for (int smi = 0; smi < e->n_sm; ++smi) {
-        const unsigned long long* q = &h[(static_cast<size_t>(smi) * 48 + slot) * 6];
+        const unsigned long long* q = &h[(static_cast<size_t>(smi) * 48 + slot) * 8];
         if (!q[0]) continue;
         if (q[3]) { sen0 = std::min(sen0, q[3]); sen1 = std::max(sen1, q[3]); retr += q[4]; rd += q[5] - q[3]; }
         ++n; e0 = std::min(e0, q[0]); e1 = std::max(e1, q[0]);
@@ -599,6 +601,22 @@ bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
       else snprintf(name, sizeof name, "%s", slot == 5 * g.n_layer ? "head" : "sampler");
       fprintf(stderr, "[flow prof] %-8s n %3d | entry %7llu..%7llu | ready %7llu..%7llu | done %7llu..%7llu | work %5llu", name, n, e0 - t_origin,
               e1 - t_origin, r0 == ~0ull ? 0 : r0 - t_origin, r1 ? r1 - t_origin : 0, d0 - t_origin, d1 - t_origin, n ? work / n : 0);
+      if (slot < 5 * g.n_layer && slot % 5 == 1) {
+        unsigned long long wt = 0, nt = 0, tl = 0, c1 = 0, c2 = 0; int m = 0;
+        for (int smi = 0; smi < e->n_sm; ++smi) {
+          const unsigned long long* q = &h[(static_cast<size_t>(smi) * 48 + slot) * 8];
+          if (q[0] && q[1] && q[5]) { wt += q[3]; nt += q[4]; tl += q[5] - q[1]; c1 += q[6]; c2 += q[7]; ++m; }
+        }
+        if (m) fprintf(stderr, " | tiles %.1f, tile loop %llu ns: waiting for tiles %llu ns, scores + softmax %llu cycles, P V %llu cycles", double(nt) / m, tl / m, wt / m, c1 / m, c2 / m);
+      } else
+      if (slot == 5 * g.n_layer + 1) {
+        unsigned long long a = 0, b2 = 0, c2 = 0; int m = 0;
+        for (int smi = 0; smi < e->n_sm; ++smi) {
+          const unsigned long long* q = &h[(static_cast<size_t>(smi) * 48 + slot) * 8];
+          if (q[0] && q[3] && q[1]) { a += q[3] - q[1]; b2 += q[4] - q[3]; c2 += q[5] - q[4]; ++m; }
+        }
+        if (m) fprintf(stderr, " | threshold + gather %llu, select + draw %llu, embed + publish %llu", a / m, b2 / m, c2 / m);
+      } else
       if (sen1) fprintf(stderr, " | sentinel seen %7llu..%7llu, mean batch retries %.1f, mean read time %llu", sen0 - t_origin, sen1 - t_origin, double(retr) / n, rd / n);
       fprintf(stderr, "\n");
     }
@@ -620,6 +638,20 @@ int persistent_status(mg_engine* e) {
   if (!e->last_run_flow || !e->h_flow_status || e->h_flow_status[0] == 0) return MG_OK;
   const int32_t* s = e->h_flow_status;
   e->flow_ok = false;                                                  // do not trust it again in this process
+  if (std::getenv("MG_FLOW_WAITLOG")) {                                // debug: which hand-over every (SM, group) warp was stuck in
+    for (int g = 0; g < flow::kMaxGroups; ++g) {
+      std::map<std::pair<int, int>, std::vector<int>> by;
+      for (int sm = 0; sm < e->n_sm; ++sm) {
+        const int32_t* q = s + 8 + 2 * (sm * flow::kMaxGroups + g);
+        if (q[1]) by[{q[1] - 1, q[0]}].push_back(sm);
+      }
+      for (auto& kv : by) {
+        fprintf(stderr, "[flow waitlog] group %d step %d detail %d: %zu SMs:", g, kv.first.first, kv.first.second, kv.second.size());
+        for (size_t i = 0; i < kv.second.size() && i < 12; ++i) fprintf(stderr, " %d", kv.second[i]);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return fail(MG_E_CUDA, "flow decode kernel aborted: code " + std::to_string(s[0]) + " (1 = exchange word never arrived, 2 = K/V tile "
               "never arrived), SM " + std::to_string(s[1]) + ", group " + std::to_string(s[2]) + ", detail " + std::to_string(s[3]));
 }
@@ -887,8 +919,10 @@ int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max
   e->use_graph = !(env_graph && env_graph[0] == '1');
   const char* env_mega = std::getenv("MG_NO_MEGA");
   e->use_mega = !(env_mega && env_mega[0] == '1');
-  const char* env_flow = std::getenv("MG_NO_FLOW");
-  e->use_flow = !(env_flow && env_flow[0] == '1');
+  // The weight-stationary flow kernel (decode_flow.cu) is OPT-IN (MG_FLOW=1): parity-green, but measured slower than the cluster
+  // kernel on every BASELINE configuration (profiles/r2b_flow_*).
+  const char* env_flow = std::getenv("MG_FLOW");
+  e->use_flow = env_flow && env_flow[0] == '1';
   {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->n_sm = prop.multiProcessorCount;

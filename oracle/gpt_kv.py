@@ -187,3 +187,56 @@ def batched_decode_step_time_port(model: KVModelOracle, prompts: Sequence[Sequen
         nxt = torch.multinomial(torch.softmax(z, dim=-1), 1, generator=generator)
         ids = torch.cat([ids, nxt], dim=1)
     return ids.tolist()
+
+
+@torch.no_grad()
+def teacher_forced_logits_projected(model: KVModelOracle, prompt_ids: Sequence[int], forced_ids: Sequence[int], n_steps: int,
+                                    want_steps: Sequence[int]) -> torch.Tensor:
+    """Same numbers as ``teacher_forced_logits`` at the steps in ``want_steps``, but caching the PROJECTED K / V rows.
+
+    The reference caches LN1(x) and re-projects the whole cache through W_k / W_v on every step (api_cache.py:60-68),
+    O(T d^2) per layer and step -- minutes of CPU time at the cache lengths of BASELINE configs 3 / 4 (1030 / 4352).  K and V of
+    a cached row never change (same LN1(x), same weights), so caching K = LN1(x) W_k^T + b_k and V likewise is the same
+    arithmetic with the row-wise matmul done once (``tests/test_oracle_cpu.py`` pins this function against
+    ``teacher_forced_logits`` in fp64).  Shape [len(want_steps), V].
+    """
+    sd, d, H, hd, L = model.sd, model.d_model, model.n_head, model.head_dim, model.n_layer
+    want = {int(s): i for i, s in enumerate(want_steps)}
+    out = torch.empty((len(want), model.vocab_size), dtype=model.dtype)
+    ids = torch.tensor(list(prompt_ids), dtype=torch.long).unsqueeze(0)
+    _, past = model.forward(ids)                                   # prefill exactly as the reference (bidirectional)
+    Ks, Vs = [], []
+    cap = past[0].shape[1] + n_steps
+    for i in range(L):
+        p = f"layers.{i}."
+        w_in, b_in = sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]
+        k = past[i][0] @ w_in[d:2 * d].T + b_in[d:2 * d]
+        v = past[i][0] @ w_in[2 * d:].T + b_in[2 * d:]
+        K = torch.empty((cap, d), dtype=model.dtype); V = torch.empty((cap, d), dtype=model.dtype)
+        K[:k.shape[0]] = k; V[:v.shape[0]] = v
+        Ks.append(K); Vs.append(V)
+    T = past[0].shape[1]
+    feed = int(prompt_ids[-1])
+    scale = 1.0 / math.sqrt(hd)
+    for step in range(n_steps):
+        x = sd["tok_emb.weight"][feed] + sd["pos_emb"][0]          # pos_emb[0] on every decode step (api_cache.py:99)
+        for i in range(L):
+            p = f"layers.{i}."
+            w_in, b_in = sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"]
+            xn = layer_norm(x, sd[p + "ln1.weight"], sd[p + "ln1.bias"])
+            qkv = w_in @ xn + b_in
+            Ks[i][T] = qkv[d:2 * d]; Vs[i][T] = qkv[2 * d:]
+            q = qkv[:d].view(H, hd)
+            Kh = Ks[i][:T + 1].view(T + 1, H, hd); Vh = Vs[i][:T + 1].view(T + 1, H, hd)
+            att = torch.softmax(torch.einsum("hd,thd->ht", q, Kh) * scale, dim=-1)
+            o = torch.einsum("ht,thd->hd", att, Vh).reshape(d)
+            x = x + (sd[p + "attn.out_proj.weight"] @ o + sd[p + "attn.out_proj.bias"])
+            h = layer_norm(x, sd[p + "ln2.weight"], sd[p + "ln2.bias"])
+            h = gelu_erf(sd[p + "mlp.0.weight"] @ h + sd[p + "mlp.0.bias"])
+            x = x + (sd[p + "mlp.2.weight"] @ h + sd[p + "mlp.2.bias"])
+        if step in want:
+            out[want[step]] = sd["head.weight"] @ x + sd["head.bias"]
+        T += 1
+        if step < len(forced_ids):
+            feed = int(forced_ids[step])
+    return out
