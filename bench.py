@@ -137,6 +137,16 @@ def host_threads():
     return max(1, min(n, 32))
 
 
+def config_dict(geo, prompt_lens, world):
+    """The `config` object both arms print (the reference arm measures a bounded sample of the SAME workload)."""
+    return {"workload": WORKLOAD, "geometry": GEOMETRY, "d_model": geo.d_model, "n_head": geo.n_head,
+            "n_layer": geo.n_layer, "vocab": geo.vocab_size, "batch_per_gpu": BATCH, "new_tokens": NEW_TOKENS,
+            "top_k": TOP_K, "temperature": TEMPERATURE, "prompt_tokens": f"{min(prompt_lens)}-{max(prompt_lens)}",
+            "parallelism": f"replicas x{world} (batch sharded, no decode-path collective)",
+            "weights": "random-init (seed 0), synthetic 8324-token vocab",
+            "l2": "KV working set grows to 270 MB per GPU (> 126 MB L2), rewritten every step: inputs larger than L2, no flush"}
+
+
 def build_workload(mg):
     geo = mg.GEOMETRIES[GEOMETRY]
     ck = mg.make_checkpoint(geo, 0)
@@ -162,30 +172,30 @@ def cpu_reference_sample(ck, geo, prompt, n_new, threads):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU path (batch-1 loop, api_cache.py:159-184) on host cores."""
+    """--impl reference: the reference's own CPU path (batch-1 loop, api_cache.py:159-184) on host cores.  One step = ONE of
+    the 64 prompts of the workload run for all 1024 new tokens (the reference sampler is batch-1 only: a whole job is 64 such
+    runs back to back, so tokens/s of one run IS the job's tokens/s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import mgea_b200 as mg
     geo, ck, prompts = build_workload(mg)
     threads = host_threads()
-    n_new = 192                                   # bounded sample per step: one prompt, 192 new tokens
-    for _ in range(args.warmup):
-        cpu_reference_sample(ck, geo, prompts[0], 32, threads)
-    rates, t_all = [], 0.0
+    n_new = NEW_TOKENS
+    for _ in range(min(args.warmup, 2)):
+        cpu_reference_sample(ck, geo, prompts[0], 64, threads)
+    t_all = 0.0
     for i in range(args.steps):
-        r, dt = cpu_reference_sample(ck, geo, prompts[i % len(prompts)], n_new, threads)
-        rates.append(r)
+        _, dt = cpu_reference_sample(ck, geo, prompts[i % len(prompts)], n_new, threads)
         t_all += dt
     value = args.steps * n_new / t_all
-    sample = (f"oracle port of the reference batch-1 sample_kvcache loop (the reference is batch-1 only): 1 of the 64 "
-              f"prompts, {n_new} new tokens per step (cache length <= {6 + n_new}; the full workload runs to 1030, where "
-              f"the reference's per-token cost is higher), fp32, torch CPU, {threads} threads")
+    sample = (f"oracle port of the reference batch-1 sample_kvcache loop: 1 of the 64 prompts per step, all {n_new} new tokens "
+              f"(cache length to 1030), top-k 40, fp32, torch CPU, {threads} threads")
     line = {
         "impl": "reference", "metric": "midi_decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "geometry": GEOMETRY, "batch": 1, "new_tokens": n_new, "top_k": TOP_K},
+        "config": config_dict(geo, [len(p) for p in prompts], max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -286,13 +296,7 @@ def main():
         "metric": "midi_decode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "geometry": GEOMETRY, "d_model": geo.d_model, "n_head": geo.n_head,
-                   "n_layer": geo.n_layer, "vocab": geo.vocab_size, "batch_per_gpu": BATCH, "new_tokens": NEW_TOKENS,
-                   "top_k": TOP_K, "temperature": TEMPERATURE, "prompt_tokens": f"{min(prompt_lens)}-{max(prompt_lens)}",
-                   "parallelism": f"replicas x{world} (batch sharded, no decode-path collective)",
-                   "weights": "random-init (seed 0), synthetic 8324-token vocab",
-                   "l2": "KV working set grows to 270 MB per GPU (> 126 MB L2) and is rewritten every step: inputs "
-                         "larger than L2, no explicit flush"},
+        "config": config_dict(geo, prompt_lens, world),
         "e2e": {"value": e2e_value, "unit": "tokens/s",
                 "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // args.steps,
                 "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // args.steps},
@@ -309,11 +313,25 @@ def main():
         "wall_s_timed_region": wall,
     }
 
-    if rank == 0 and world == 1 and not args.no_extras:
-        line["batch1"] = batch1_latency(mg)
-        line["classifier"] = classifier_throughput(mg, tf_peak, peak_src)
-        line["long_context"] = long_context(mg, hbm_peak)
-        line["pipeline"] = pipeline_512(mg)
+    secondary = {}
+    if not args.no_extras:
+        if world == 1:
+            line["batch1"] = batch1_latency(mg)
+            line["classifier"] = classifier_throughput(mg, tf_peak, peak_src)
+            line["long_context"] = long_context(mg, hbm_peak)
+            secondary.update({"batch1_p50_ms_per_token_bf16": line["batch1"]["bf16"]["p50_ms_per_token"],
+                              "batch1_p50_ms_per_token_fp32": line["batch1"]["fp32"]["p50_ms_per_token"],
+                              "classifier_ms": line["classifier"]["ms"], "classifier_tflops": line["classifier"]["tflops"],
+                              "classifier_frac_of_tensor_peak": line["classifier"]["frac_of_tensor_peak"],
+                              "long_context_us_per_step": line["long_context"]["decode_us_per_step"],
+                              "long_context_frac_of_measured_hbm": line["long_context"]["frac_of_measured_hbm"]})
+        eng.close()
+        eng = None
+        pipe = pipeline_512(mg, rank, world, local_rank, dist)          # every rank: 512 / N requests (strong scaling)
+        if rank == 0:
+            line["pipeline"] = pipe
+            secondary.update({"pipeline_requests": pipe["requests"], "pipeline_wall_s": pipe["wall_s"],
+                              "pipeline_tokens_per_s": pipe["tokens_per_s"]})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         n_new = 1024
@@ -325,41 +343,49 @@ def main():
                                              TEMPERATURE, TOP_K, torch.Generator().manual_seed(0))
         batched = len(eq) * 96 / (time.perf_counter() - bt0)
         line["cpu_baseline"] = {
-            "batched_restatement_tokens_per_s": batched,
-            "batched_restatement_note": (f"NOT the reference's loop: GPTWithKV.forward fed idx [{len(eq)},1] with the .item() "
-                                         "stop removed (SURVEY 8d), 96 steps, same host threads"),
             "value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
             "sample": (f"oracle port of the reference batch-1 sample_kvcache loop on 1 of the 64 prompts, all {n_new} new "
-                       f"tokens, top-k 40, fp32 torch CPU ({dt:.1f} s); the reference sampler is batch-1 only, so a "
-                       f"64-prompt job costs 64 such runs")}
+                       f"tokens, top-k 40, fp32 torch CPU ({dt:.1f} s); batch-1 only: a 64-prompt job = 64 such runs"),
+            "batched_restatement_tokens_per_s": batched,
+            "batched_restatement_note": (f"NOT the reference's loop: GPTWithKV.forward fed idx [{len(eq)},1], .item() stop "
+                                         "removed (SURVEY 8d), 96 steps"),
+            "config1": config1_cpu(mg, threads), "distilbert_cpu": distilbert_cpu(mg, threads)}
     elif rank == 0:
         line["cpu_baseline"] = None
+    if rank == 0 and secondary:
+        line["roofline"]["secondary"] = secondary                      # compact mirror of the side measurements
     if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def batch1_latency(mg):
-    """BASELINE metric part 2: p50 ms/token @ batch 1 (config 1 shape: train_mini, 5-token prompt, 507 new tokens)."""
+    """BASELINE metric part 2: p50 ms/token @ batch 1 (config 1 shape: train_mini, 5-token prompt, 507 new tokens, greedy).
+    p50 over the PER-TOKEN latencies (device %globaltimer stamp of every token, mg_last_step_times), all timed runs pooled."""
     geo = mg.GEOMETRIES["train_mini"]
     ck = mg.make_checkpoint(geo, 0)
     prompt = mg.encode(ck["vocab"], mg.synthetic_prompts(ck["vocab"], 1, seed=1)[0])
     out = {}
     for dtype in ("fp32", "bf16"):
         eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype=dtype, max_batch=1, max_seq=1088)
-        per_tok = []
+        per_tok, run_means = [], []
         n_new = 512 - len(prompt)
-        for i in range(9):
+        for i in range(7):
             eng.upload([prompt], n_new)
             eng.run(1.0, 1, eos_id=-1)
             eng.synchronize()
             t = eng.last_timing()
             if i >= 2:
-                per_tok.append(t["decode_ms"] / max(t["steps"], 1))
-        out[dtype] = {"p50_ms_per_token": statistics.median(per_tok), "runs": len(per_tok), "new_tokens": n_new,
-                      "note": "median over runs of (decode-loop device time / tokens); greedy (top_k=1)"}
+                per_tok.append(eng.last_step_times_us())
+                run_means.append(t["decode_ms"] / max(t["steps"], 1))
+        lat = np.concatenate(per_tok) * 1e-3
+        out[dtype] = {"p50_ms_per_token": float(np.percentile(lat, 50)), "p99_ms_per_token": float(np.percentile(lat, 99)),
+                      "mean_ms_per_token": float(statistics.mean(run_means)), "tokens_timed": int(lat.size), "new_tokens": n_new,
+                      "path": eng.last_decode_path(),
+                      "note": "percentiles over per-token latencies (device-stamped), 5 runs pooled; greedy (top_k=1)"}
         eng.close()
     return out
 
@@ -386,28 +412,101 @@ def long_context(mg, hbm_peak):
             "note": "16 sequences -> 16 clusters x 4 CTAs = 64 of 148 SMs busy (one sequence per cluster)"}
 
 
-def pipeline_512(mg):
-    """BASELINE config 5 on ONE replica: 512 requests, classify -> prompt -> generate (1024 tokens total each, top-k 40)."""
+def pipeline_512(mg, rank, world, local_rank, dist):
+    """BASELINE config 5: 512 requests classify -> emotion -> music parameters -> prompt -> generate (1024 tokens total each,
+    top-k 40), batch-sharded over the replicas: every rank serves 512 / N requests (strong scaling); wall time = max over ranks.
+    The emotion -> parameter mapping is the reference's own (EATS.py table via tests/golden/eats_table.json, random.seed(0))."""
+    import random
     geo = mg.GEOMETRIES["train_large_pos512"]
     ck = mg.make_checkpoint(geo, 0)
     vocab = {t: i for t, i in ck["vocab"].items() if t != "[END_SEQUENCE]"}       # EOS disabled: every request runs to max_len
     vocab["[EOS_DISABLED]"] = ck["vocab"]["[END_SEQUENCE]"]
-    gen = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=128, max_seq=1088)
-    clf = mg.Classifier(mg.make_bert_state_dict(mg.DISTILBERT_BASE, 0), n_heads=12, max_tokens=16384)
+    gen = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=128, max_seq=1088, device=local_rank)
+    clf = mg.Classifier(mg.make_bert_state_dict(mg.DISTILBERT_BASE, 0), n_heads=12, max_tokens=16384, device=local_rank)
+    params_fn = mg.eats_music_params(mg.load_eats_table(os.path.join(ROOT, "tests", "golden", "eats_table.json")))
     g = torch.Generator().manual_seed(0)
     ids = torch.randint(1000, 30000, (512, 64), generator=g)
     ids[:, 0], ids[:, 63] = 101, 102
-    mg.classify_prompt_generate(clf, gen, vocab, ids.numpy()[:128], max_len=64, top_k=40)      # warm-up
+    lo, hi = mg.shard_range(512, rank, world)
+    mine = ids.numpy()[lo:hi]
+    random.seed(0)
+    mg.classify_prompt_generate(clf, gen, vocab, mine[:min(128, len(mine))], params_fn=params_fn, max_len=64, top_k=40)   # warm-up
+    random.seed(0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out = mg.classify_prompt_generate(clf, gen, vocab, ids.numpy(), max_len=1024, temperature=1.0, top_k=40, batch=128)
+    out = mg.classify_prompt_generate(clf, gen, vocab, mine, params_fn=params_fn, max_len=1024, temperature=1.0, top_k=40,
+                                      batch=128, seq_index_base=lo)
     dt = time.perf_counter() - t0
-    assert len(out) == 512 and all(len(o) == 1024 for o in out)
-    n_new = sum(len(o) for o in out) - sum(3 for _ in out)
+    assert len(out) == hi - lo and all(len(o) == 1024 for o in out)
+    prompt_toks = sum(len(o) for o in out)
+    t_dev = torch.tensor([dt, float(prompt_toks)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        t_max = t_dev.clone()
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_dev, op=dist.ReduceOp.SUM)
+        dt, total = float(t_max[0]), float(t_dev[1])
+    else:
+        total = float(prompt_toks)
     gen.close()
     clf.close()
-    return {"workload": "config5 on one replica: 512 requests classify -> prompt -> generate to 1024 tokens, top-k 40, batches of 128",
-            "wall_s": dt, "requests_per_s": 512 / dt, "tokens_per_s": n_new / dt,
-            "note": "host wall clock incl. tokenised-text H2D, synthetic emotion -> music mapping, prompt building, D2H of tokens"}
+    return {"workload": "config5: 512 requests classify -> EATS mapping -> prompt -> generate to 1024 tokens, top-k 40",
+            "requests": 512, "replicas": world, "requests_per_replica": hi - lo, "wall_s": dt, "requests_per_s": 512 / dt,
+            "tokens_per_s": total / dt, "scaling": "strong",
+            "note": "host wall clock, max over ranks: tokenised-text H2D, classifier, reference EATS table, prompt building, "
+                    "generation in batches of 128, D2H of tokens (prompt tokens included in the count)"}
+
+
+def config1_cpu(mg, threads):
+    """BASELINE config 1 on the host cores: train_mini, greedy, 507 new tokens from one 5-token prompt, fp32 -- BOTH reference
+    loops (KV-cache sample_kvcache, api_cache.py:159-184; no-cache sample, generate.py:46-61) as oracle ports, at all host
+    threads and at 1 thread (the no-cache loop is O(T^2): bounded to 192 new tokens at 1 thread)."""
+    from oracle import gpt_kv, gpt_nocache
+    geo = mg.GEOMETRIES["train_mini"]
+    ck = mg.make_checkpoint(geo, 0)
+    prompt = mg.encode(ck["vocab"], mg.synthetic_prompts(ck["vocab"], 1, seed=1)[0])
+    sd = mg.remap_state_dict(ck["model"])
+    kv, nc = gpt_kv.KVModelOracle(sd, geo.n_head), gpt_nocache.NoCacheModelOracle(sd, geo.n_head)
+    out = {"workload": "config1: train_mini greedy, 5-token prompt, fp32, batch 1, CPU"}
+    for th in (threads, 1):
+        torch.set_num_threads(th)
+        n_kv, n_nc = 512 - len(prompt), (512 - len(prompt) if th > 1 else 192)
+        t0 = time.perf_counter()
+        gpt_kv.sample_ids(kv, prompt, max_len=len(prompt) + n_kv, temperature=1.0, top_k=1)
+        t_kv = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        gpt_nocache.sample_ids(nc, prompt, max_len=len(prompt) + n_nc, temperature=1.0, top_k=1)
+        t_nc = time.perf_counter() - t0
+        out[f"threads_{th}"] = {"kv_loop_ms_per_token": 1e3 * t_kv / n_kv, "kv_new_tokens": n_kv,
+                                "nocache_loop_ms_per_token": 1e3 * t_nc / n_nc, "nocache_new_tokens": n_nc}
+    torch.set_num_threads(threads)
+    return out
+
+
+def distilbert_cpu(mg, threads):
+    """BASELINE config 2 on the host cores: the installed HF DistilBertForSequenceClassification (the third-party class the
+    reference calls, emotion_analysis/modeling.py:14-21), fp32, ids [256, 64], random-init weights; None if transformers is absent."""
+    try:
+        from transformers import DistilBertConfig, DistilBertForSequenceClassification
+    except Exception:
+        return None
+    geo = mg.DISTILBERT_BASE
+    torch.set_num_threads(threads)
+    cfg = DistilBertConfig(vocab_size=geo.vocab_size, max_position_embeddings=geo.max_pos, dim=geo.dim, n_heads=geo.n_heads,
+                           n_layers=geo.n_layers, hidden_dim=geo.hidden_dim, num_labels=geo.num_labels)
+    torch.manual_seed(0)
+    model = DistilBertForSequenceClassification(cfg).eval()
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(1000, 30000, (256, 64), generator=g)
+    ids[:, 0], ids[:, 63] = 101, 102
+    with torch.no_grad():
+        model(input_ids=ids[:32])
+        t0 = time.perf_counter()
+        model(input_ids=ids)
+        dt = time.perf_counter() - t0
+    return {"workload": "config2: HF DistilBertForSequenceClassification fp32, 256 x 64, torch CPU", "seconds": dt,
+            "texts_per_s": 256 / dt, "threads": threads}
 
 
 def classifier_throughput(mg, tf_peak, peak_src):

@@ -143,6 +143,12 @@ int mg_engine_stats(mg_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes
  * (total, prefill part, decode part) and the number of decode steps it executed. */
 int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* decode_ms, int* steps);
 
+/* Per-token latency of the last run: us_out[i] = time between the tokens of decode steps i and i + 1 of sequence 0
+ * (%globaltimer stamps written on the device by whichever kernel finalised the token), at most cap values; *n = how many.
+ * The reference has no counterpart (its loop is timed around api_cache.py:166-182 from Python); BASELINE's
+ * "p50 ms/token @ batch 1" is the median of these. */
+int mg_last_step_times(mg_engine* e, float* us_out, int cap, int* n);
+
 /* Which decode path served the last mg_run / mg_generate / mg_step_logits of this engine: 0 = step graph (one launch per
  * kernel and step), 1 = persistent cluster kernel (decode_mega.cu), 2 = weight-stationary flow kernel (decode_flow.cu).
  * Tests assert that parity was checked on the path the benchmark runs. */

@@ -15,12 +15,13 @@ from .bert_checkpoint import (DISTILBERT_BASE, ID2LABEL, TINY_BERT, BertGeometry
                               merge_lora_state_dict)
 from .engine import (Classifier, Generator, KVModel, load_library, sample, sample_kvcache, tc_gemm)  # noqa: F401
 from .batcher import RequestBatcher  # noqa: F401
-from .pipeline import classify_prompt_generate, clf_capacity, synthetic_music_params  # noqa: F401
+from .pipeline import (classify_prompt_generate, clf_capacity, eats_music_params, load_eats_table,  # noqa: F401
+                       synthetic_music_params)
 from .replicas import gather_token_lists, shard, shard_range  # noqa: F401
 
 __all__ = [
     "Classifier", "Generator", "KVModel", "RequestBatcher", "load_library", "sample", "sample_kvcache", "tc_gemm", "gather_token_lists",
-    "shard", "shard_range", "classify_prompt_generate", "clf_capacity", "synthetic_music_params", "DISTILBERT_BASE", "ID2LABEL", "TINY_BERT", "BertGeometry", "make_bert_state_dict",
+    "shard", "shard_range", "classify_prompt_generate", "clf_capacity", "synthetic_music_params", "eats_music_params", "load_eats_table", "DISTILBERT_BASE", "ID2LABEL", "TINY_BERT", "BertGeometry", "make_bert_state_dict",
     "merge_lora_state_dict",
     "GEOMETRIES", "Geometry", "expected_keys", "infer_geometry", "make_checkpoint", "make_state_dict",
     "remap_state_dict", "state_dict_digest", "build_prompt", "build_synthetic_vocab",

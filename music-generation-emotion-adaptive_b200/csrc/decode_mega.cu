@@ -1450,6 +1450,7 @@ decode_mega_kernel(const MegaParams p) {
                 const int b = b0 + s;
                 const int pos = misc.outlen[s];
                 p.st.out_ids[static_cast<size_t>(b) * p.st.out_stride + pos] = tok;      // api_cache.py:179
+                if (p.st.step_ns && b == 0) p.st.step_ns[step] = ptx::global_timer_ns();   // per-token latency read-out
                 misc.outlen[s] = pos + 1;
               }
             }

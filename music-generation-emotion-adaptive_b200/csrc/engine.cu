@@ -87,6 +87,7 @@ struct mg_engine {
           *d_seq_len = nullptr, *d_last_rows = nullptr;
   DecodeState st{};
   int32_t* d_out_block = nullptr;      // [out_len (B) | out_ids (B * stride)] contiguous for one D2H
+  unsigned long long* d_step_ns = nullptr;   // [max_seq + 1] %globaltimer per decode step of sequence 0 (mg_last_step_times)
   int32_t* h_out_block = nullptr;      // pinned
   size_t out_cap = 0;
   SampleParams* d_sp = nullptr;
@@ -803,6 +804,8 @@ int upload_impl(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, in
   }
   e->st.cur_tok = new_cur; e->st.lens = new_lens; e->st.n_new = new_nnew; e->st.finished = new_fin;
   e->st.out_len = new_outlen; e->st.out_ids = new_outids; e->st.max_new = da + o_maxnew; e->st.out_stride = stride;
+  if (!e->d_step_ns) MG_TRY(e->dmalloc(&e->d_step_ns, sizeof(unsigned long long) * (e->max_seq + 1)));
+  e->st.step_ns = e->d_step_ns;
   e->cur_B = B; e->cur_M = M; e->cur_max_tp = max_tp; e->cur_steps = steps;
   MG_TRY(ensure_rows(e, std::max(M, B)));
   e->uploaded = true;
@@ -1325,6 +1328,20 @@ int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* 
   if (prefill_ms) *prefill_ms = e->t_prefill;
   if (decode_ms) *decode_ms = e->t_decode;
   if (steps) *steps = e->t_steps;
+  return MG_OK;
+}
+
+int mg_last_step_times(mg_engine* e, float* us_out, int cap, int* n_out) {
+  if (!e || !n_out || (cap > 0 && !us_out)) return fail(MG_E_ARG, "null argument");
+  *n_out = 0;
+  const int steps = std::min(e->t_steps, e->max_seq + 1);
+  if (!e->d_step_ns || steps < 2) return MG_OK;
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  std::vector<unsigned long long> h(steps);
+  MG_CUDA_OK(cudaMemcpy(h.data(), e->d_step_ns, sizeof(unsigned long long) * steps, cudaMemcpyDeviceToHost));
+  const int n = std::min(cap, steps - 1);
+  for (int i = 0; i < n; ++i) us_out[i] = static_cast<float>(h[i + 1] - h[i]) * 1e-3f;
+  *n_out = n;
   return MG_OK;
 }
 

@@ -1074,6 +1074,11 @@ sample_step_kernel(const float* __restrict__ logits, int ld, int V, const Sample
   if (threadIdx.x == 0) {
     const int pos = st.out_len[b];
     st.out_ids[static_cast<size_t>(b) * st.out_stride + pos] = tok;     // api_cache.py:179
+    if (st.step_ns && b == 0) {                                          // per-token latency read-out (mg_last_step_times)
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      st.step_ns[step] = t;
+    }
     st.out_len[b] = pos + 1;
     st.cur_tok[b] = tok;
     st.lens[b] += 1;

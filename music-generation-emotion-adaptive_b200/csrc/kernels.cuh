@@ -32,6 +32,7 @@ struct DecodeState {
   int32_t* max_new;
   uint8_t* finished;
   int32_t out_stride;
+  unsigned long long* step_ns;   // optional [max steps]: %globaltimer when the token of sequence 0 in decode step i was written
 };
 
 // x[r] = tok_emb[tok[r]] + pos_emb[pos ? pos[r] : 0]   (fp32 residual stream, optional)

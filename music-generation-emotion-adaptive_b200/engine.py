@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "mg_abi_version", "mg_last_error", "mg_device_count", "mg_engine_create", "mg_engine_destroy", "mg_load_weight",
     "mg_engine_finalize", "mg_generate", "mg_upload_prompts", "mg_run", "mg_download", "mg_synchronize",
     "mg_engine_stream", "mg_step_logits", "mg_step_logits_at", "mg_generate_nocache", "mg_forward_nocache", "mg_sample_logits",
-    "mg_engine_stats", "mg_last_run_timing", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
+    "mg_engine_stats", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
     "mg_bert_finalize", "mg_classify", "mg_bert_upload", "mg_bert_run", "mg_bert_download", "mg_bert_synchronize",
     "mg_bert_stream", "mg_bert_stats", "mg_test_gemm_bf16",
 ]
@@ -92,6 +92,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mg_sample_logits": (c.c_int, [vp, f32p, c.c_int, c.c_int, c.c_float, c.c_int, u64, u64, c.c_uint32, i32p]),
         "mg_engine_stats": (c.c_int, [vp, u64p, u64p, u64p]),
         "mg_last_run_timing": (c.c_int, [vp, f32p, f32p, f32p, c.POINTER(c.c_int)]),
+        "mg_last_step_times": (c.c_int, [vp, f32p, c.c_int, c.POINTER(c.c_int)]),
         "mg_last_decode_path": (c.c_int, [vp]),
         "mg_bert_create": (c.c_int, [c.POINTER(_BertGeometry), c.c_int, c.c_int, c.POINTER(vp)]),
         "mg_bert_destroy": (None, [vp]),
@@ -343,6 +344,14 @@ class Generator:
     def last_decode_path(self) -> str:
         """Which CUDA decode path served the last run: step_graph / cluster_kernel (decode_mega.cu) / flow_kernel (decode_flow.cu)."""
         return self.DECODE_PATHS[int(self.lib.mg_last_decode_path(self._h))]
+
+    def last_step_times_us(self) -> np.ndarray:
+        """Per-token latencies (microseconds between consecutive tokens of sequence 0) of the last run, device-stamped."""
+        cap = 1 << 16
+        buf = np.empty(cap, np.float32)
+        n = ctypes.c_int()
+        _check(self.lib, self.lib.mg_last_step_times(self._h, _ptr(buf, ctypes.c_float), cap, ctypes.byref(n)))
+        return buf[:n.value].copy()
 
     def last_timing(self) -> Dict[str, float]:
         t, p, d, s = ctypes.c_float(), ctypes.c_float(), ctypes.c_float(), ctypes.c_int()

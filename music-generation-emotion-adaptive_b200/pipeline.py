@@ -29,6 +29,37 @@ def synthetic_music_params(label: str, rng: Optional[random.Random] = None) -> D
             "inst_family": rng.choice(all_fams), "all_families": all_fams}
 
 
+def load_eats_table(path: str) -> Dict[str, Dict]:
+    """The reference's emotion table, from its own ``lookup_table.csv`` (emotion_analysis/EATS.py:7-19: emotion, bpm_min,
+    bpm_max, key, scale_type, JSON list of instrument families) or from the JSON dump of it (tests/golden/eats_table.json)."""
+    import csv
+    import json
+    if path.endswith(".json"):
+        with open(path) as f:
+            j = json.load(f)
+        return j.get("table", j)
+    with open(path, newline="") as f:
+        return {r["emotion"]: {"bpm_min": int(r["bpm_min"]), "bpm_max": int(r["bpm_max"]), "key": r["key"],
+                               "scale_type": r["scale_type"], "instrument_families": json.loads(r["instrument_families"])}
+                for r in csv.DictReader(f)}
+
+
+def eats_music_params(table: Dict[str, Dict]) -> Callable[[str], Dict]:
+    """``get_music_params`` of the reference for one label (emotion_analysis/EATS.py:21-42) over a loaded table: same keys, same
+    ValueError for an unknown emotion, and the same two draws from the module-level ``random`` in the same order (bpm first,
+    family second), so ``random.seed(0)`` reproduces the reference's choices (pinned by tests/golden/eats_table.json)."""
+    def params(label: str) -> Dict:
+        lc = label.lower()
+        if lc not in table:
+            raise ValueError(f"Emotion '{label}' not in lookup table")
+        e = table[lc]
+        bpm = random.randint(e["bpm_min"], e["bpm_max"])
+        fam = random.choice(e["instrument_families"])
+        return {"emotion": lc, "bpm": bpm, "key": e["key"], "scale_type": e["scale_type"], "inst_family": fam,
+                "all_families": e["instrument_families"]}
+    return params
+
+
 def classify_prompt_generate(clf, gen, tok2id: Dict[str, int], input_ids, attention_mask=None,
                              params_fn: Callable[[str], Dict] = synthetic_music_params, max_len: int = 512,
                              temperature: float = 1.0, top_k: Optional[int] = 50, seed: Optional[int] = None, batch: int = 128,

@@ -203,6 +203,51 @@ def distilbert():
     np.savez_compressed(os.path.join(OUT, "distilbert.npz"), meta=json.dumps(meta), **out)
 
 
+@torch.no_grad()
+def distilbert_margin():
+    """tests/golden/distilbert_margin.npz: 48 inputs whose top-2 logit margin under the installed transformers
+    DistilBertForSequenceClassification (fp32, LoRA merged) is the largest of a pool of 384 random rows -- every one of them far
+    above the bf16 engine's logit error, so the parity test can demand label identity on ALL rows."""
+    from transformers import DistilBertConfig, DistilBertForSequenceClassification
+
+    geo, seed, N, T, keep = bc.DISTILBERT_BASE, 0, 384, 32, 48
+    sd = bc.make_bert_state_dict(geo, seed)
+    cfg = DistilBertConfig(vocab_size=geo.vocab_size, max_position_embeddings=geo.max_pos, dim=geo.dim,
+                           n_heads=geo.n_heads, n_layers=geo.n_layers, hidden_dim=geo.hidden_dim,
+                           num_labels=geo.num_labels, dropout=0.0, attention_dropout=0.0, seq_classif_dropout=0.0)
+    model = DistilBertForSequenceClassification(cfg).eval()
+    model.load_state_dict(bc.merge_lora_state_dict(sd), strict=True)
+    g = torch.Generator().manual_seed(23)
+    ids = torch.randint(1000, 30000, (N, T), generator=g)
+    ids[:, 0], ids[:, T - 1] = 101, 102
+    logits = torch.cat([model(input_ids=ids[i:i + 64]).logits for i in range(0, N, 64)])
+    top2 = torch.topk(logits, 2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    sel = torch.argsort(margin, descending=True)[:keep]
+    meta = {"seed": seed, "N": keep, "T": T, "pool": N, "digest": mg.state_dict_digest(sd), "min_margin": float(margin[sel].min())}
+    np.savez_compressed(os.path.join(OUT, "distilbert_margin.npz"), meta=json.dumps(meta), ids=ids[sel].numpy().astype(np.int32),
+                        logits=logits[sel].numpy(), margin=margin[sel].numpy())
+    print("distilbert margin fixture ok", meta)
+
+
+def eats_table():
+    """tests/golden/eats_table.json: the emotion -> music-parameter table the REFERENCE builds at import
+    (emotion_analysis/EATS.py:7-19 from its lookup_table.csv) and the outputs of its get_music_params for all 28 labels under
+    random.seed(0) -- the pin for pipeline.eats_music_params (BASELINE config 5 uses the reference's own mapping)."""
+    import importlib.util
+    import random
+    path = os.path.join(refload.REFERENCE_ROOT, "emotion_analysis", "EATS.py")
+    spec = importlib.util.spec_from_file_location("ref_eats", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                              # reads lookup_table.csv next to it (pandas)
+    random.seed(0)
+    labels = list(bc.ID2LABEL.values())
+    calls = [mod.get_music_params(lab) for lab in labels]
+    with open(os.path.join(OUT, "eats_table.json"), "w") as f:
+        json.dump({"table": mod.EATS, "labels": labels, "seed": 0, "get_music_params": calls}, f, indent=1, sort_keys=True)
+    print("eats table ok", len(mod.EATS))
+
+
 if __name__ == "__main__":
     if not refload.reference_available():
         sys.exit("reference tree not found; golden fixtures can only be generated in the build container")
@@ -214,3 +259,5 @@ if __name__ == "__main__":
     nocache_greedy()
     topk_distribution()
     distilbert()
+    distilbert_margin()
+    eats_table()

@@ -347,3 +347,25 @@ def test_generate_with_no_room_returns_the_prompt_like_the_reference():
     with pytest.raises(RuntimeError):
         Generator.generate(g, [list(range(g.geometry.pos_rows + 1))], 0)
     assert mg.clf_capacity(type("C", (), {"max_tokens": 4096})()) == 4096
+
+
+def test_eats_music_params_reproduce_the_reference_mapping():
+    """pipeline.eats_music_params over the reference's own table (tests/golden/eats_table.json, dumped from
+    emotion_analysis/EATS.py by oracle/make_golden.py) returns what the reference's get_music_params returned for all 28
+    labels under random.seed(0); every prompt it leads to is encodable in the synthetic vocabulary (api_cache.py:194-203)."""
+    import json
+    import os
+    import random
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eats_table.json")
+    with open(path) as f:
+        gold = json.load(f)
+    fn = mg.eats_music_params(mg.load_eats_table(path))
+    random.seed(gold["seed"])
+    got = [fn(lab) for lab in gold["labels"]]
+    assert got == gold["get_music_params"]
+    with pytest.raises(ValueError):
+        fn("not-an-emotion")
+    tok2id = mg.build_synthetic_vocab(8324)
+    for prm in got:
+        ids = mg.encode(tok2id, mg.build_prompt(tok2id, prm["bpm"], prm["key"], prm["all_families"]))
+        assert 3 <= len(ids) <= 6
