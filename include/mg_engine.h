@@ -143,6 +143,20 @@ int mg_engine_stats(mg_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes
  * (total, prefill part, decode part) and the number of decode steps it executed. */
 int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* decode_ms, int* steps);
 
+/* Device-side detokenisation to note events: replaces the per-token regex / float() / pretty_midi look-ups of the reference's
+ * MIDI assembly loop (api_cache.py:157 note_re, :208-221) by a gather.  mg_set_note_table uploads ONE record per vocabulary entry,
+ * built on the host once per checkpoint: kind 0 = any other token, 1 = "[INSTRUMENT] <name>" (value = GM program,
+ * pretty_midi.instrument_name_to_program or 0, api_cache.py:211-212), 2 = a whole-line "[NOTE] [PITCH:p] [START:s] [END:e]
+ * [DURATION:d]" token (value = pretty_midi.note_name_to_number(p), start / end = float(s) / float(e), api_cache.py:216-217).
+ * mg_note_events walks the token ids of the LAST generation where they lie in HBM (prompt included, like the reference, which
+ * iterates over all returned tokens): every instrument token opens a new instrument, a note goes to the most recent one and is
+ * dropped while there is none.  Per sequence b: n_inst[b] / n_notes[b] events found (entries beyond max_inst / max_notes are
+ * counted but not stored), inst_program / inst_token [B][max_inst], note_inst (index into that list) / note_pitch / note_start /
+ * note_end [B][max_notes].  Caller-owned host buffers. */
+int mg_set_note_table(mg_engine* e, const int32_t* kind, const int32_t* value, const float* start, const float* end, int V);
+int mg_note_events(mg_engine* e, int max_inst, int max_notes, int32_t* n_inst, int32_t* inst_program, int32_t* inst_token,
+                   int32_t* n_notes, int32_t* note_inst, int32_t* note_pitch, float* note_start, float* note_end);
+
 /* Per-token latency of the last run: us_out[i] = time between the tokens of decode steps i and i + 1 of sequence 0
  * (%globaltimer stamps written on the device by whichever kernel finalised the token), at most cap values; *n = how many.
  * The reference has no counterpart (its loop is timed around api_cache.py:166-182 from Python); BASELINE's

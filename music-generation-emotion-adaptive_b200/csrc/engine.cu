@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "decode_flow.cuh"
+#include "detok.cuh"
 #include "decode_mega.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -87,6 +88,10 @@ struct mg_engine {
           *d_seq_len = nullptr, *d_last_rows = nullptr;
   DecodeState st{};
   int32_t* d_out_block = nullptr;      // [out_len (B) | out_ids (B * stride)] contiguous for one D2H
+  int4* d_note_table = nullptr;         // device-side detokenisation: one record per vocabulary entry (detok.cu)
+  int32_t* d_detok = nullptr;            // result block of mg_note_events
+  int32_t* h_detok = nullptr;            // pinned
+  size_t detok_cap = 0;
   unsigned long long* d_step_ns = nullptr;   // [max_seq + 1] %globaltimer per decode step of sequence 0 (mg_last_step_times)
   int32_t* h_out_block = nullptr;      // pinned
   size_t out_cap = 0;
@@ -1328,6 +1333,73 @@ int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* 
   if (prefill_ms) *prefill_ms = e->t_prefill;
   if (decode_ms) *decode_ms = e->t_decode;
   if (steps) *steps = e->t_steps;
+  return MG_OK;
+}
+
+// ---- device-side detokenisation (reference api_cache.py:157,208-221) ------------------------------------------------
+int mg_set_note_table(mg_engine* e, const int32_t* kind, const int32_t* value, const float* start, const float* end, int V) {
+  if (!e || !kind || !value || !start || !end) return fail(MG_E_ARG, "null argument");
+  if (V != e->geo.vocab_size) return fail(MG_E_SHAPE, "note table must have one record per vocabulary entry");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  std::vector<int4> h(V);
+  for (int i = 0; i < V; ++i) {
+    if (kind[i] < DETOK_OTHER || kind[i] > DETOK_NOTE) return fail(MG_E_ARG, "note table kind must be 0 (other), 1 (instrument) or 2 (note)");
+    int zs, ze;
+    std::memcpy(&zs, &start[i], 4); std::memcpy(&ze, &end[i], 4);
+    h[i] = make_int4(kind[i], value[i], zs, ze);
+  }
+  if (!e->d_note_table) MG_TRY(e->dmalloc(&e->d_note_table, sizeof(int4) * V));
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_note_table, h.data(), sizeof(int4) * V, cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));                       // `h` is pageable
+  e->h2d += sizeof(int4) * V;
+  return MG_OK;
+}
+
+int mg_note_events(mg_engine* e, int max_inst, int max_notes, int32_t* n_inst, int32_t* inst_program, int32_t* inst_token,
+                   int32_t* n_notes, int32_t* note_inst, int32_t* note_pitch, float* note_start, float* note_end) {
+  if (!e || !n_inst || !n_notes) return fail(MG_E_ARG, "null argument");
+  if (max_inst < 0 || max_notes < 0) return fail(MG_E_ARG, "negative capacity");
+  if ((max_inst > 0 && (!inst_program || !inst_token)) || (max_notes > 0 && (!note_inst || !note_pitch || !note_start || !note_end)))
+    return fail(MG_E_ARG, "null event array");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  if (!e->d_note_table) return fail(MG_E_STATE, "no note table (call mg_set_note_table first)");
+  if (!e->uploaded) return fail(MG_E_STATE, "nothing generated yet (call mg_generate or mg_upload_prompts + mg_run first)");
+  const int B = e->cur_B;
+  const size_t per = 2 + 2 * static_cast<size_t>(max_inst) + 4 * static_cast<size_t>(max_notes), ints = per * B;
+  if (ints > e->detok_cap) {
+    MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->dfree(e->d_detok); e->d_detok = nullptr;
+    if (e->h_detok) { cudaFreeHost(e->h_detok); e->h_detok = nullptr; }
+    MG_TRY(e->dmalloc(&e->d_detok, ints * sizeof(int32_t)));
+    MG_CUDA_OK(cudaMallocHost(&e->h_detok, ints * sizeof(int32_t)));
+    e->detok_cap = ints;
+  }
+  // block layout: n_inst [B] | n_notes [B] | inst_program [B][mi] | inst_token [B][mi] | note_inst, note_pitch, note_start, note_end [B][mn]
+  int32_t* d = e->d_detok;
+  DetokOut o{};
+  o.max_inst = max_inst; o.max_notes = max_notes;
+  o.n_inst = d; o.n_notes = d + B;
+  o.inst_program = d + 2 * B; o.inst_token = o.inst_program + static_cast<size_t>(B) * max_inst;
+  o.note_inst = o.inst_token + static_cast<size_t>(B) * max_inst; o.note_pitch = o.note_inst + static_cast<size_t>(B) * max_notes;
+  o.note_start = reinterpret_cast<float*>(o.note_pitch + static_cast<size_t>(B) * max_notes);
+  o.note_end = o.note_start + static_cast<size_t>(B) * max_notes;
+  MG_TRY(launch_detok(e->stream, e->st.out_ids, e->st.out_len, e->st.out_stride, e->d_note_table, e->geo.vocab_size, B, o));
+  MG_CUDA_OK(cudaMemcpyAsync(e->h_detok, d, ints * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  MG_TRY(persistent_status(e));
+  e->d2h += ints * sizeof(int32_t);
+  const int32_t* h = e->h_detok;
+  std::memcpy(n_inst, h, sizeof(int32_t) * B);
+  std::memcpy(n_notes, h + B, sizeof(int32_t) * B);
+  const size_t bi = static_cast<size_t>(B) * max_inst, bn = static_cast<size_t>(B) * max_notes;
+  if (bi) { std::memcpy(inst_program, h + 2 * B, 4 * bi); std::memcpy(inst_token, h + 2 * B + bi, 4 * bi); }
+  if (bn) {
+    const int32_t* q = h + 2 * B + 2 * bi;
+    std::memcpy(note_inst, q, 4 * bn); std::memcpy(note_pitch, q + bn, 4 * bn);
+    std::memcpy(note_start, q + 2 * bn, 4 * bn); std::memcpy(note_end, q + 3 * bn, 4 * bn);
+  }
   return MG_OK;
 }
 

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "mg_abi_version", "mg_last_error", "mg_device_count", "mg_engine_create", "mg_engine_destroy", "mg_load_weight",
     "mg_engine_finalize", "mg_generate", "mg_upload_prompts", "mg_run", "mg_download", "mg_synchronize",
     "mg_engine_stream", "mg_step_logits", "mg_step_logits_at", "mg_generate_nocache", "mg_forward_nocache", "mg_sample_logits",
-    "mg_engine_stats", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
+    "mg_engine_stats", "mg_set_note_table", "mg_note_events", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
     "mg_bert_finalize", "mg_classify", "mg_bert_upload", "mg_bert_run", "mg_bert_download", "mg_bert_synchronize",
     "mg_bert_stream", "mg_bert_stats", "mg_test_gemm_bf16",
 ]
@@ -93,6 +93,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mg_engine_stats": (c.c_int, [vp, u64p, u64p, u64p]),
         "mg_last_run_timing": (c.c_int, [vp, f32p, f32p, f32p, c.POINTER(c.c_int)]),
         "mg_last_step_times": (c.c_int, [vp, f32p, c.c_int, c.POINTER(c.c_int)]),
+        "mg_set_note_table": (c.c_int, [vp, i32p, i32p, f32p, f32p, c.c_int]),
+        "mg_note_events": (c.c_int, [vp, c.c_int, c.c_int, i32p, i32p, i32p, i32p, i32p, i32p, f32p, f32p]),
         "mg_last_decode_path": (c.c_int, [vp]),
         "mg_bert_create": (c.c_int, [c.POINTER(_BertGeometry), c.c_int, c.c_int, c.POINTER(vp)]),
         "mg_bert_destroy": (None, [vp]),
@@ -240,6 +242,7 @@ class Generator:
         stride = int(max(len(p) for p in prompt_tokens)) + max(mx, 0)
         out = np.zeros((B, max(stride, 1)), np.int32)
         lens = np.zeros(B, np.int32)
+        self._last_B = B
         _check(self.lib, self.lib.mg_generate(self._h, _ptr(flat, ctypes.c_int32), _ptr(offs, ctypes.c_int32), B, mx,
                                               _ptr(per, ctypes.c_int32), float(temperature), 0 if top_k is None else int(top_k),
                                               int(eos_id), _seed(seed), int(seq_index_base), _ptr(out, ctypes.c_int32),
@@ -344,6 +347,39 @@ class Generator:
     def last_decode_path(self) -> str:
         """Which CUDA decode path served the last run: step_graph / cluster_kernel (decode_mega.cu) / flow_kernel (decode_flow.cu)."""
         return self.DECODE_PATHS[int(self.lib.mg_last_decode_path(self._h))]
+
+    # -- device-side detokenisation (api_cache.py:157,208-221) -------------------------------------
+    def set_note_table(self, tok2id: Dict[str, int], instrument_program=None, note_number=None) -> None:
+        """Upload the token-id -> (instrument | note) table built by ``vocab.note_table``; pass pretty_midi's
+        ``instrument_name_to_program`` / ``note_name_to_number`` where it is installed (the service box)."""
+        from .vocab import note_table
+        kind, value, start, end = note_table(tok2id, self.geometry.vocab_size, instrument_program, note_number)
+        _check(self.lib, self.lib.mg_set_note_table(self._h, _ptr(kind, ctypes.c_int32), _ptr(value, ctypes.c_int32),
+                                                    _ptr(start, ctypes.c_float), _ptr(end, ctypes.c_float), len(kind)))
+        self._id2tok = {i: t for t, i in tok2id.items()}
+
+    def note_events(self, max_inst: int = 16, max_notes: int = 1088) -> List[List[Dict]]:
+        """Note events of the last generation, assembled on the device from the token ids in HBM: per sequence the list of
+        instruments in order of appearance, ``{"name", "program", "notes": [(pitch, start, end), ...]}`` -- what the loop of
+        api_cache.py:208-221 feeds into pretty_midi (velocity is the constant 100 there)."""
+        B = int(self._last_B)
+        n_inst, n_notes = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        ip, it = np.zeros((B, max_inst), np.int32), np.zeros((B, max_inst), np.int32)
+        ni, npit = np.zeros((B, max_notes), np.int32), np.zeros((B, max_notes), np.int32)
+        ns, ne = np.zeros((B, max_notes), np.float32), np.zeros((B, max_notes), np.float32)
+        i32, f32 = ctypes.c_int32, ctypes.c_float
+        _check(self.lib, self.lib.mg_note_events(self._h, max_inst, max_notes, _ptr(n_inst, i32), _ptr(ip, i32), _ptr(it, i32),
+                                                 _ptr(n_notes, i32), _ptr(ni, i32), _ptr(npit, i32), _ptr(ns, f32), _ptr(ne, f32)))
+        if (n_inst > max_inst).any() or (n_notes > max_notes).any():
+            raise ValueError("note_events: more instruments / notes than the given capacity")
+        out = []
+        for b in range(B):
+            insts = [{"name": self._id2tok[int(it[b, i])].split("]", 1)[1].strip(), "program": int(ip[b, i]), "notes": []}
+                     for i in range(int(n_inst[b]))]
+            for j in range(int(n_notes[b])):
+                insts[int(ni[b, j])]["notes"].append((int(npit[b, j]), float(ns[b, j]), float(ne[b, j])))
+            out.append(insts)
+        return out
 
     def last_step_times_us(self) -> np.ndarray:
         """Per-token latencies (microseconds between consecutive tokens of sequence 0) of the last run, device-stamped."""

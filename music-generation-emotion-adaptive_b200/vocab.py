@@ -9,6 +9,7 @@ the 24 ``[KEY_SIGNATURE]`` names of reference dataparsing/analysis_output.txt:2-
 """
 from __future__ import annotations
 
+import re
 from typing import Dict, List, Sequence
 
 KEY_NAMES = [
@@ -99,3 +100,48 @@ def synthetic_prompts(tok2id: Dict[str, int], n: int, seed: int = 0) -> List[Lis
         # lookup_table.csv writes keys as "D Major"; title() reproduces that spelling
         out.append(build_prompt(tok2id, rng.randint(20, 250), rng.choice(KEY_NAMES).title(), chosen))
     return out
+
+
+# ---- device-side detokenisation table (reference api_cache.py:157,208-221) ------------------------------------------
+NOTE_RE = re.compile(r"\[NOTE\] \[PITCH:(.+?)\] \[START:(.+?)\] \[END:(.+?)\] \[DURATION:(.+?)\]")   # api_cache.py:157
+_NOTE_NAME_RE = re.compile(r"^(?P<n>[A-Ga-g])(?P<off>[#b!]?)(?P<oct>[+-]?\d+)$")
+_PITCH_CLASS = {"C": 0, "D": 2, "E": 4, "F": 5, "G": 7, "A": 9, "B": 11}
+# General MIDI programs of the instruments the service can ask for (api_cache.py:152-156); any other name goes through the
+# caller's ``instrument_program`` (pretty_midi.instrument_name_to_program on the service box) or falls to 0 like api_cache.py:212
+GM_PROGRAMS = {"Acoustic Grand Piano": 0, "Violin": 40, "Flute": 73}
+
+
+def note_name_to_number(name: str) -> int:
+    """pretty_midi.note_name_to_number (third-party, pinned by the reference's requirements.txt): letter, optional # / b / !,
+    signed octave; ``12 * (octave + 1) + pitch class + accidental``; ValueError for anything else."""
+    m = _NOTE_NAME_RE.match(name)
+    if not m:
+        raise ValueError(f"Improper note format: {name}")
+    return 12 * (int(m.group("oct")) + 1) + _PITCH_CLASS[m.group("n").upper()] + {"#": 1, "": 0, "b": -1, "!": -1}[m.group("off")]
+
+
+def note_table(tok2id: Dict[str, int], vocab_size: int, instrument_program=None, note_number=None):
+    """One record per token id for ``mg_set_note_table``: (kind, value, start, end) as int32 / int32 / float32 / float32 arrays.
+
+    Everything the reference's loop does per generated token -- ``startswith("[INSTRUMENT]")``, the name -> program look-up
+    (0 when the name is unknown), ``note_re.match``, ``note_name_to_number``, two ``float()`` -- is done here once per vocabulary
+    entry.  A NOTE token whose pitch or times do not parse would raise inside the reference's loop (HTTP 500 when it is ever
+    generated): the table builder raises the same ValueError up front."""
+    import numpy as np
+    prog = instrument_program or (lambda name: GM_PROGRAMS.get(name, 0))
+    num = note_number or note_name_to_number
+    kind = np.zeros(vocab_size, np.int32)
+    value = np.zeros(vocab_size, np.int32)
+    start = np.zeros(vocab_size, np.float32)
+    end = np.zeros(vocab_size, np.float32)
+    for tok, i in tok2id.items():
+        if not 0 <= i < vocab_size:
+            continue
+        if tok.startswith("[INSTRUMENT]"):                              # api_cache.py:209-214
+            kind[i], value[i] = 1, int(prog(tok.split("]", 1)[1].strip()))
+        else:
+            m = NOTE_RE.match(tok)                                      # api_cache.py:215-220
+            if m:
+                kind[i], value[i] = 2, int(num(m.group(1)))
+                start[i], end[i] = float(m.group(2)), float(m.group(3))
+    return kind, value, start, end

@@ -614,3 +614,59 @@ def test_flow_kernel_sampler_distribution_chi_square():
     assert counts[probs == 0].sum() == 0                            # never a token outside the top-k set
     assert _chi_square_p(counts, probs / probs.sum()) > 1e-3
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-side detokenisation: api_cache.py:157,208-221 as a gather over the token ids in HBM
+# ---------------------------------------------------------------------------------------------------
+def _note_line_vocab(V, seed=0):
+    """A train_mini-style vocabulary (whole-line NOTE tokens, train/train_mini.py:22-32) of exactly V entries."""
+    rng = np.random.default_rng(seed)
+    toks = ["[START_SEQUENCE]", "[END_SEQUENCE]", "[BPM] 120.0", "[KEY_SIGNATURE] C major", "[INSTRUMENT] Violin",
+            "[INSTRUMENT] Acoustic Grand Piano", "[INSTRUMENT] Flute", "[INSTRUMENT] Theremin", "[PAD]"]
+    names = ["C", "C#", "D", "Eb", "E", "F", "F#", "G", "Ab", "A", "Bb", "B"]
+    seen = set(toks)
+    while len(toks) < V:
+        s = round(float(rng.uniform(0, 30)), 3)
+        d = round(float(rng.uniform(0.05, 2)), 3)
+        t = f"[NOTE] [PITCH:{names[rng.integers(12)]}{rng.integers(1, 7)}] [START:{s}] [END:{round(s + d, 3)}] [DURATION:{d}]"
+        if t not in seen:
+            seen.add(t)
+            toks.append(t)
+    return {t: i for i, t in enumerate(sorted(toks))}                   # ids by sorted() like the trainers
+
+
+def test_device_detokenisation_equals_the_reference_loop():
+    from oracle import detok as odetok
+    geo = mg.GEOMETRIES["tiny_hd64"]
+    ck = checkpoint("tiny_hd64", 0)
+    tok2id = _note_line_vocab(geo.vocab_size)
+    id2tok = {i: t for t, i in tok2id.items()}
+    e = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=8, max_seq=160)
+    e.set_note_table(tok2id)
+    inst_ids = [tok2id[f"[INSTRUMENT] {n}"] for n in ("Violin", "Acoustic Grand Piano", "Flute", "Theremin")]
+    rng = np.random.default_rng(3)
+    prompts = []
+    for b in range(8):
+        p = [tok2id["[START_SEQUENCE]"], tok2id["[BPM] 120.0"]]
+        if b != 5:                                                      # row 5: notes before any instrument are dropped
+            p += [inst_ids[b % 4]]
+        p += rng.integers(0, geo.vocab_size, 3 + b).tolist()
+        if b % 3 == 0:
+            p += [inst_ids[(b + 1) % 4]] + rng.integers(0, geo.vocab_size, 2).tolist()   # a second instrument takes over
+        prompts.append(p)
+    out = e.generate(prompts, 120, 1.0, 50, seed=5)
+    got = e.note_events(max_inst=64, max_notes=160)
+    program_of = lambda name: mg.vocab.GM_PROGRAMS.get(name, 0)          # noqa: E731
+    total = 0
+    for b in range(8):
+        want = odetok.tokens_to_instruments([id2tok[i] for i in out[b]], program_of, mg.vocab.note_name_to_number)
+        assert len(got[b]) == len(want)
+        for g, w in zip(got[b], want):
+            assert g["name"] == w["name"] and g["program"] == w["program"]
+            assert g["notes"] == [(p, float(np.float32(s)), float(np.float32(en))) for p, s, en in w["notes"]]
+            total += len(w["notes"])
+    assert total > 300                                                   # the vocabulary is ~99 % NOTE tokens
+    with pytest.raises(ValueError):
+        e.note_events(max_inst=64, max_notes=4)                          # capacity overflow is reported, not truncated
+    e.close()

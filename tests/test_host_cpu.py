@@ -369,3 +369,26 @@ def test_eats_music_params_reproduce_the_reference_mapping():
     for prm in got:
         ids = mg.encode(tok2id, mg.build_prompt(tok2id, prm["bpm"], prm["key"], prm["all_families"]))
         assert 3 <= len(ids) <= 6
+
+
+def test_note_table_follows_the_reference_token_rules():
+    """vocab.note_table = the per-token work of api_cache.py:208-221 done once per vocabulary entry."""
+    from mgea_b200 import vocab as V
+    tok2id = {"[START_SEQUENCE]": 0, "[INSTRUMENT] Violin": 1, "[INSTRUMENT] Kazoo": 2,
+              "[NOTE] [PITCH:C#4] [START:1.5] [END:2.25] [DURATION:0.75]": 3, "[NOTE]": 4, "[PITCH]": 5,
+              "[NOTE] [PITCH:B-3] [START:0] [END:1] [DURATION:1]": 6}
+    kind, value, start, end = V.note_table(tok2id, 8)
+    assert kind.tolist() == [0, 1, 1, 2, 0, 0, 2, 0]
+    assert value[1] == 40 and value[2] == 0                              # unknown instrument name -> program 0 (api_cache.py:212)
+    assert value[3] == 61 and (start[3], end[3]) == (1.5, 2.25)
+    assert value[6] == 12 * (-3 + 1) + 11                                # pretty_midi reads "B-3" as B, octave -3
+    assert V.note_name_to_number("A4") == 69 and V.note_name_to_number("Eb2") == 39 and V.note_name_to_number("c0") == 12
+    with pytest.raises(ValueError):
+        V.note_table({"[NOTE] [PITCH:H2] [START:0] [END:1] [DURATION:1]": 0}, 1)
+    from oracle import detok as odetok
+    toks = ["[NOTE] [PITCH:C#4] [START:1.5] [END:2.25] [DURATION:0.75]", "[INSTRUMENT] Violin", "[PITCH]",
+            "[NOTE] [PITCH:C#4] [START:1.5] [END:2.25] [DURATION:0.75]", "[INSTRUMENT] Kazoo", "[INSTRUMENT] Violin",
+            "[NOTE] [PITCH:B-3] [START:0] [END:1] [DURATION:1]"]
+    got = odetok.tokens_to_instruments(toks, lambda n: V.GM_PROGRAMS.get(n, 0), V.note_name_to_number)
+    assert [(g["name"], g["program"], g["notes"]) for g in got] == [("Violin", 40, [(61, 1.5, 2.25)]), ("Kazoo", 0, []),
+                                                                     ("Violin", 40, [(-13, 0.0, 1.0)])]
