@@ -319,12 +319,15 @@ def main():
             line["batch1"] = batch1_latency(mg)
             line["classifier"] = classifier_throughput(mg, tf_peak, peak_src)
             line["long_context"] = long_context(mg, hbm_peak)
+            line["continuous_batching"] = continuous_batching(mg)
             secondary.update({"batch1_p50_ms_per_token_bf16": line["batch1"]["bf16"]["p50_ms_per_token"],
                               "batch1_p50_ms_per_token_fp32": line["batch1"]["fp32"]["p50_ms_per_token"],
                               "classifier_ms": line["classifier"]["ms"], "classifier_tflops": line["classifier"]["tflops"],
                               "classifier_frac_of_tensor_peak": line["classifier"]["frac_of_tensor_peak"],
                               "long_context_us_per_step": line["long_context"]["decode_us_per_step"],
-                              "long_context_frac_of_measured_hbm": line["long_context"]["frac_of_measured_hbm"]})
+                              "long_context_frac_of_measured_hbm": line["long_context"]["frac_of_measured_hbm"],
+                              "continuous_batching_tokens_per_s": line["continuous_batching"]["continuous_tokens_per_s"],
+                              "static_batching_tokens_per_s": line["continuous_batching"]["static_batches_tokens_per_s"]})
         eng.close()
         eng = None
         pipe = pipeline_512(mg, rank, world, local_rank, dist)          # every rank: 512 / N requests (strong scaling)
@@ -456,6 +459,49 @@ def pipeline_512(mg, rank, world, local_rank, dist):
             "tokens_per_s": total / dt, "scaling": "strong",
             "note": "host wall clock, max over ranks: tokenised-text H2D, classifier, reference EATS table, prompt building, "
                     "generation in batches of 128, D2H of tokens (prompt tokens included in the count)"}
+
+
+def continuous_batching(mg):
+    """a stream of 256 requests with ragged budgets (128..1024 new tokens) through a 64-slot session (chunks of 32
+    decode steps, finished slots refilled between chunks) against static batches of 64 that run to their longest member."""
+    geo = mg.GEOMETRIES[GEOMETRY]
+    ck = mg.make_checkpoint(geo, 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 256, seed=3)]
+    rng = np.random.default_rng(0)
+    budgets = rng.integers(128, 1025, 256).tolist()
+    total_new = int(sum(budgets))
+    eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=BATCH, max_seq=1088)
+    out = {"workload": "256 requests, 128..1024 new tokens each (uniform, seed 0), top-k 40, train_large bf16, one GPU"}
+    for rep in range(2):                                              # first pass = warm-up
+        t0 = time.perf_counter()
+        for lo in range(0, 256, BATCH):
+            eng.generate(prompts[lo:lo + BATCH], budgets[lo:lo + BATCH], TEMPERATURE, TOP_K, eos_id=-1, seed=rep, as_arrays=True)
+        t_static = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        eng.slots_begin(BATCH, 1088, TEMPERATURE, TOP_K, eos_id=-1, seed=rep)
+        nxt, slot_req, done, chunks = 0, [None] * BATCH, 0, 0
+        while done < 256:
+            free = [b for b in range(BATCH) if slot_req[b] is None]
+            take = list(range(nxt, min(nxt + len(free), 256)))
+            if take:
+                eng.slots_admit(free[:len(take)], [prompts[r] for r in take], [budgets[r] for r in take], take)
+                for b, r in zip(free, take):
+                    slot_req[b] = r
+                nxt += len(take)
+            fin, _ = eng.slots_step(32)
+            chunks += 1
+            for b in range(BATCH):
+                if fin[b] and slot_req[b] is not None:
+                    row = eng.slots_fetch(b, 1100)
+                    assert len(row) == len(prompts[slot_req[b]]) + budgets[slot_req[b]]
+                    slot_req[b], done = None, done + 1
+        eng.slots_end()
+        t_cont = time.perf_counter() - t0
+    out.update({"static_batches_tokens_per_s": total_new / t_static, "continuous_tokens_per_s": total_new / t_cont,
+                "speedup": t_static / t_cont, "chunks": chunks, "slots": BATCH, "chunk_steps": 32,
+                "note": "host wall clock incl. admission prefills, per-chunk status D2H and per-request token D2H"})
+    eng.close()
+    return out
 
 
 def config1_cpu(mg, threads):

@@ -143,6 +143,28 @@ int mg_engine_stats(mg_engine* e, uint64_t* kernel_launches, uint64_t* h2d_bytes
  * (total, prefill part, decode part) and the number of decode steps it executed. */
 int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* decode_ms, int* steps);
 
+/* ---- slot sessions: continuous batching -------------------------------------------------------------------------------
+ * Caller side in the reference: the /generate endpoint, one batch-1 sample_kvcache call per HTTP request on a shared model
+ * (api_cache.py:186-204).  A slot session keeps n_slots independent sequences in flight on one engine: new requests are
+ * admitted into free slots BETWEEN chunks of decode steps (their prompts are prefilled into the K/V rows of the slot, nothing
+ * in flight is touched), finished ones are retired, so a stream of requests is served at batched-decode throughput.
+ * Row b of the session behaves exactly like a batch-1 reference run of its request: same prefill, same loop, own Philox
+ * stream (seed, seq_index) wherever and whenever it was admitted.
+ *   mg_slots_begin  sampling parameters are fixed for the session (the decode path -- persistent cluster kernel or step
+ *                   graph -- is chosen once); max_len = prompt + new tokens any request may reach.
+ *   mg_slots_admit  n prompts (packed like mg_generate) into the free slots `slots[j]`; max_new[j] tokens each; seq_index[j] =
+ *                   Philox sequence index of the request.  MG_E_STATE if a slot is still in flight.
+ *   mg_slots_step   up to n_steps decode steps for every slot in flight (a slot stops at EOS or at its budget); returns
+ *                   finished[b] (1 = idle or done) and out_len[b] for all slots -- ONE small D2H copy.
+ *   mg_slots_fetch  token ids (prompt included) of one slot.
+ *   mg_slots_end    leaves the session (any batch call does so implicitly). */
+int mg_slots_begin(mg_engine* e, int n_slots, int max_len, float temperature, int top_k, int eos_id, uint64_t seed);
+int mg_slots_admit(mg_engine* e, int n, const int32_t* slots, const int32_t* prompt_ids, const int32_t* prompt_offsets,
+                   const int32_t* max_new, const int32_t* seq_index);
+int mg_slots_step(mg_engine* e, int n_steps, uint8_t* finished, int32_t* out_len);
+int mg_slots_fetch(mg_engine* e, int slot, int32_t* out_ids, int cap, int* n);
+int mg_slots_end(mg_engine* e);
+
 /* Device-side detokenisation to note events: replaces the per-token regex / float() / pretty_midi look-ups of the reference's
  * MIDI assembly loop (api_cache.py:157 note_re, :208-221) by a gather.  mg_set_note_table uploads ONE record per vocabulary entry,
  * built on the host once per checkpoint: kind 0 = any other token, 1 = "[INSTRUMENT] <name>" (value = GM program,

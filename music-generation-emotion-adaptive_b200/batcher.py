@@ -140,3 +140,120 @@ def _is_device_failure(e: BaseException) -> bool:
 def stats(batcher: RequestBatcher) -> Dict[str, float]:
     n = len(batcher.batches)
     return {"engine_calls": n, "requests": sum(batcher.batches), "mean_batch": (sum(batcher.batches) / n) if n else 0.0}
+
+
+class ContinuousBatcher:
+    """Continuous batching in front of one engine (second half): a slot session of ``n_slots`` sequences.
+
+    One worker thread alternates between (1) admitting waiting requests into free slots -- their prompts are prefilled into
+    the K/V rows of the slot while everything in flight stays where it is --, (2) a chunk of ``chunk_steps`` decode steps for
+    all slots in flight (the persistent cluster kernel, or the step graph for geometries it does not take), and (3) retiring
+    the slots that hit ``[END_SEQUENCE]`` or their budget.  A request therefore waits at most one chunk (~ chunk_steps x 70 us)
+    for a free slot instead of a whole batch generation, and the GPU never idles on a half-empty batch while requests wait.
+    Sampling settings are per batcher (they are fixed for a slot session); every request has its own Philox stream
+    (``seed``, running request index), so its tokens do not depend on the slot or the moment it was admitted.
+
+        cb = ContinuousBatcher(model.engine, n_slots=64, max_len=1024, temperature=1.0, top_k=50, eos_id=eos)
+        tokens = cb.generate(prompt_ids, max_new_tokens)          # blocking, thread-safe (the /generate endpoint's call)
+        cb.close()
+    """
+
+    def __init__(self, engine, n_slots: int = 64, max_len: int = 1024, temperature: float = 1.0, top_k: Optional[int] = 50,
+                 eos_id: int = -1, chunk_steps: int = 32, seed: Optional[int] = None, first_seq_index: int = 0):
+        if n_slots < 1 or chunk_steps < 1:
+            raise ValueError("n_slots and chunk_steps must be positive")
+        self.engine, self.n_slots, self.max_len, self.chunk = engine, int(n_slots), int(max_len), int(chunk_steps)
+        self._seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+        engine.slots_begin(self.n_slots, self.max_len, temperature, top_k, eos_id, self._seed)
+        self._cv = threading.Condition()
+        self._queue: List[Tuple[List[int], int, int, Future]] = []
+        self._closed = False
+        self._seq = itertools.count(int(first_seq_index))
+        self._slot_req: List[Optional[Future]] = [None] * self.n_slots
+        self.admissions: List[Tuple[int, int]] = []      # (chunk number, requests admitted) -- observability / tests
+        self.chunks = 0
+        self._worker = threading.Thread(target=self._run, name="mgea-continuous", daemon=True)
+        self._worker.start()
+
+    def submit(self, prompt_ids: Sequence[int], max_new_tokens: int) -> "Future[List[int]]":
+        fut: "Future[List[int]]" = Future()
+        with self._cv:
+            if self._closed:
+                raise RuntimeError("ContinuousBatcher is closed")
+            self._queue.append((list(prompt_ids), max(int(max_new_tokens), 0), next(self._seq), fut))
+            self._cv.notify()
+        return fut
+
+    def generate(self, prompt_ids: Sequence[int], max_new_tokens: int) -> List[int]:
+        return self.submit(prompt_ids, max_new_tokens).result()
+
+    def close(self) -> None:
+        with self._cv:
+            self._closed = True
+            self._cv.notify()
+        self._worker.join()
+        self.engine.slots_end()
+
+    # -- worker -----------------------------------------------------------------------------------------
+    def _admit(self) -> None:
+        free = [b for b in range(self.n_slots) if self._slot_req[b] is None]
+        with self._cv:
+            take, self._queue = self._queue[:len(free)], self._queue[len(free):]
+        ok: List[Tuple[int, Tuple]] = []
+        for req in take:
+            prompt, max_new, _, fut = req
+            if max_new == 0:                                    # api_cache.py:166: empty range, the prompt comes back unchanged
+                fut.set_result(list(prompt))
+            elif len(prompt) + max_new > self.max_len:
+                fut.set_exception(ValueError(f"prompt + max_new_tokens = {len(prompt) + max_new} exceeds the batcher's max_len "
+                                             f"{self.max_len}"))
+            else:
+                ok.append((free[len(ok)], req))
+        if not ok:
+            return
+
+        def admit(items):
+            self.engine.slots_admit([s for s, _ in items], [r[0] for _, r in items], [r[1] for _, r in items],
+                                    [r[2] for _, r in items])
+            for slot, r in items:
+                self._slot_req[slot] = r[3]
+
+        n_in = 0
+        try:
+            admit(ok)                                            # admission validates every prompt before it touches a slot
+            n_in = len(ok)
+        except Exception as e:                                   # noqa: BLE001
+            for item in ok:                                      # a bad prompt fails its own request only
+                if _is_device_failure(e):
+                    item[1][3].set_exception(e)
+                    continue
+                try:
+                    admit([item])
+                    n_in += 1
+                except Exception as e1:                          # noqa: BLE001
+                    item[1][3].set_exception(e1)
+        if n_in:
+            self.admissions.append((self.chunks, n_in))
+
+    def _run(self) -> None:
+        while True:
+            with self._cv:
+                while not self._queue and not self._closed and all(f is None for f in self._slot_req):
+                    self._cv.wait()
+                if self._closed and not self._queue and all(f is None for f in self._slot_req):
+                    return
+            self._admit()
+            if all(f is None for f in self._slot_req):
+                continue
+            try:
+                fin, _ = self.engine.slots_step(self.chunk)
+                self.chunks += 1
+                for b in range(self.n_slots):
+                    if fin[b] and self._slot_req[b] is not None:
+                        self._slot_req[b].set_result(self.engine.slots_fetch(b, self.max_len + 8))
+                        self._slot_req[b] = None
+            except Exception as e:                               # noqa: BLE001 -- device failure: nothing in flight survives
+                for b in range(self.n_slots):
+                    if self._slot_req[b] is not None:
+                        self._slot_req[b].set_exception(e)
+                        self._slot_req[b] = None

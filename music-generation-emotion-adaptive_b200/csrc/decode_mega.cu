@@ -1358,7 +1358,7 @@ decode_mega_kernel(const MegaParams p) {
           if (ct == 0) ptx::mbar_arrive_expect_tx(&bars.cand, (CL - 1) * k * 8);
           // the uniform draw depends on nothing the wait delivers: ten Philox rounds hidden behind the DSMEM latency
           const float u01 = (cw == 0 && k != 1)
-                                ? philox_uniform(sp.seed, sp.seq_base + static_cast<uint64_t>(b0 + s), static_cast<uint32_t>(misc.nnew[s]))
+                                ? philox_uniform(sp.seed, sp.seq_base + static_cast<uint64_t>(p.st.seq_idx ? p.st.seq_idx[b0 + s] : b0 + s), static_cast<uint32_t>(misc.nnew[s]))
                                 : 0.f;
           // every thread observes the arrival itself (greedy: only warp 0 needs the data): no CTA barrier behind the wait --
           // the local candidates became visible at the barrier above, the remote ones through the mbarrier
@@ -1583,8 +1583,10 @@ __global__ void mega_pack_kernel(PackSrc src, uint4* __restrict__ dst, int n_lay
 // K / V cache rows written by the prefill ([B][4][Tmax][64]) -> the caches of the persistent kernel:
 //   kh [B][4][head][Tmax][hd]            (head-major rows)
 //   vt [B][4][head][Tvt / 32][hd][32]    (per 32-key block transposed, key 8j + 2t + e at position 8t + 2j + e)
-__global__ void mega_relayout_kv_kernel(const MegaLayer* __restrict__ layers, const int32_t* __restrict__ lens, int Tmax, int Tvt, int hd) {
-  const int bs = blockIdx.x, l = blockIdx.y;                 // (sequence, slice), layer
+__global__ void mega_relayout_kv_kernel(const MegaLayer* __restrict__ layers, const int32_t* __restrict__ lens,
+                                        const int32_t* __restrict__ slots, int Tmax, int Tvt, int hd) {
+  // (sequence, slice), layer; `slots` (optional) = the sequences to convert (continuous batching: the newly admitted ones)
+  const int bs = slots ? slots[blockIdx.x / CL] * CL + blockIdx.x % CL : blockIdx.x, l = blockIdx.y;
   const int len = lens[bs / CL];
   const bf16* ksrc = layers[l].kc + static_cast<size_t>(bs) * Tmax * FS;
   const bf16* vsrc = layers[l].vc + static_cast<size_t>(bs) * Tmax * FS;
@@ -1601,7 +1603,14 @@ __global__ void mega_relayout_kv_kernel(const MegaLayer* __restrict__ layers, co
 }  // namespace
 
 int mega_relayout_kv(cudaStream_t stream, const MegaLayer* layers, const int32_t* lens, int B, int n_layer, int Tmax, int Tvt, int hd) {
-  mega_relayout_kv_kernel<<<dim3(B * CL, n_layer), 256, 0, stream>>>(layers, lens, Tmax, Tvt, hd);
+  mega_relayout_kv_kernel<<<dim3(B * CL, n_layer), 256, 0, stream>>>(layers, lens, nullptr, Tmax, Tvt, hd);
+  MG_LAUNCH_CHECK();
+  return MG_OK;
+}
+
+int mega_relayout_kv_slots(cudaStream_t stream, const MegaLayer* layers, const int32_t* lens, const int32_t* slots, int n, int n_layer,
+                           int Tmax, int Tvt, int hd) {
+  mega_relayout_kv_kernel<<<dim3(n * CL, n_layer), 256, 0, stream>>>(layers, lens, slots, Tmax, Tvt, hd);
   MG_LAUNCH_CHECK();
   return MG_OK;
 }

@@ -67,6 +67,9 @@ size_t mega_packed_bytes(int n_layer, int NP, int tail);
 int mega_pack_weights(cudaStream_t stream, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1,
                       const bf16* const* w2, const bf16* head, int n_layer, int V, int VS, int NP, int tail, void* dst);
 int mega_relayout_kv(cudaStream_t stream, const MegaLayer* layers, const int32_t* lens, int B, int n_layer, int Tmax, int Tvt, int hd);
+// the same for n sequences named by a device array of slot indices (continuous batching: newly admitted sequences only)
+int mega_relayout_kv_slots(cudaStream_t stream, const MegaLayer* layers, const int32_t* lens, const int32_t* slots, int n, int n_layer,
+                           int Tmax, int Tvt, int hd);
 int mega_max_clusters(int smax);      // co-resident clusters (0 when the query fails)
 int launch_decode_mega(cudaStream_t stream, const MegaParams& p, int n_clusters);
 

@@ -88,6 +88,15 @@ struct mg_engine {
           *d_seq_len = nullptr, *d_last_rows = nullptr;
   DecodeState st{};
   int32_t* d_out_block = nullptr;      // [out_len (B) | out_ids (B * stride)] contiguous for one D2H
+  // ---- slot session (continuous batching, mg_slots_*): persistent per-slot decode state outside the per-call arena ----
+  bool slots_active = false, slots_mega = false;
+  int n_slots = 0, slots_eos = -1, slots_topk = 0;
+  int32_t* d_slot_state = nullptr;      // cur_tok | lens | n_new | max_new | seq_idx | finished (bytes) | last_rows, n_slots each
+  int32_t* d_slot_last_rows = nullptr;
+  int32_t* d_slot_out = nullptr;        // out_len [n] | out_ids [n][stride]
+  int32_t* h_slot_flags = nullptr;      // pinned: finished [n] (bytes, padded) | out_len [n]
+  size_t slot_state_cap = 0, slot_out_cap = 0;
+  std::vector<uint8_t> slot_busy;       // host mirror: admitted and not yet reported finished
   int4* d_note_table = nullptr;         // device-side detokenisation: one record per vocabulary entry (detok.cu)
   int32_t* d_detok = nullptr;            // result block of mg_note_events
   int32_t* h_detok = nullptr;            // pinned
@@ -254,16 +263,22 @@ int block_kv(mg_engine* e, int l, int M, bool decode, int B, int nsplit, bool ln
   return MG_OK;
 }
 
+// Prompt rows -> K/V caches (B packed prompts, M rows in total; the cache row of a prompt row is named by d_row_seq / d_row_pos)
 template <typename T>
-int prefill(mg_engine* e) {
+int prefill_rows(mg_engine* e, int M, int B) {
   const mg_geometry& g = e->geo;
-  const int M = e->cur_M, B = e->cur_B;
   MG_TRY(launch_embed_ln<T>(e->stream, e->d_prompt, e->d_row_pos, reinterpret_cast<const T*>(e->tok_emb),
                             reinterpret_cast<const T*>(e->pos_emb), e->layers[0].ln1w, e->layers[0].ln1b, e->x,
                             reinterpret_cast<T*>(e->y), M, g.d_model, 1e-5f, true));
   for (int l = 0; l < g.n_layer; ++l) MG_TRY(block_kv<T>(e, l, M, false, B, 1, l == 0));
   // logits of the prefill are discarded by the reference (api_cache.py:163): the head is skipped
-  MG_TRY(launch_decode_init(e->stream, e->d_prompt, e->d_offsets, e->st, B));
+  return MG_OK;
+}
+
+template <typename T>
+int prefill(mg_engine* e) {
+  MG_TRY(prefill_rows<T>(e, e->cur_M, e->cur_B));
+  MG_TRY(launch_decode_init(e->stream, e->d_prompt, e->d_offsets, e->st, e->cur_B));
   return MG_OK;
 }
 
@@ -463,7 +478,11 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
       p.prof_thread = std::getenv("MG_MEGA_PROF_THREAD") ? std::atoi(std::getenv("MG_MEGA_PROF_THREAD")) : 0;
     }
   }
-  *rc = mega::mega_relayout_kv(e->stream, e->d_mega_layers, e->st.lens, B, g.n_layer, e->max_seq, p.Tvt, p.head_dim);
+  if (e->slots_active) p.early_exit = forced == nullptr ? 1 : 0;    // a cluster whose slots are all idle stops at once
+  // slot sessions convert the caches of newly admitted sequences themselves (mg_slots_admit); the rows a previous chunk of
+  // decode steps appended exist only in the persistent layout and must not be overwritten from the prefill caches
+  if (!e->slots_active)
+    *rc = mega::mega_relayout_kv(e->stream, e->d_mega_layers, e->st.lens, B, g.n_layer, e->max_seq, p.Tvt, p.head_dim);
   if (*rc == MG_OK) *rc = mega::launch_decode_mega(e->stream, p, n_clusters);
   if (p.prof && *rc == MG_OK) {
     unsigned long long h[128];
@@ -801,7 +820,7 @@ int upload_impl(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, in
   int32_t* new_outids = e->d_out_block + B;
   const bool same = e->st.cur_tok == new_cur && e->st.lens == new_lens && e->st.n_new == new_nnew &&
                     e->st.finished == new_fin && e->st.out_len == new_outlen && e->st.out_ids == new_outids &&
-                    e->st.max_new == da + o_maxnew && e->st.out_stride == stride;
+                    e->st.max_new == da + o_maxnew && e->st.out_stride == stride && e->st.seq_idx == nullptr;
   if (!same && e->graph) {               // captured kernel arguments would be stale
     cudaGraphExecDestroy(e->graph);
     e->graph = nullptr;
@@ -809,6 +828,8 @@ int upload_impl(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, in
   }
   e->st.cur_tok = new_cur; e->st.lens = new_lens; e->st.n_new = new_nnew; e->st.finished = new_fin;
   e->st.out_len = new_outlen; e->st.out_ids = new_outids; e->st.max_new = da + o_maxnew; e->st.out_stride = stride;
+  e->st.seq_idx = nullptr;
+  e->slots_active = false;                                  // a batch call ends a slot session (mg_slots_begin)
   if (!e->d_step_ns) MG_TRY(e->dmalloc(&e->d_step_ns, sizeof(unsigned long long) * (e->max_seq + 1)));
   e->st.step_ns = e->d_step_ns;
   e->cur_B = B; e->cur_M = M; e->cur_max_tp = max_tp; e->cur_steps = steps;
@@ -1333,6 +1354,194 @@ int mg_last_run_timing(mg_engine* e, float* total_ms, float* prefill_ms, float* 
   if (prefill_ms) *prefill_ms = e->t_prefill;
   if (decode_ms) *decode_ms = e->t_decode;
   if (steps) *steps = e->t_steps;
+  return MG_OK;
+}
+
+// ---- slot sessions: continuous batching (the caller side is reference api_cache.py:186-204) ---------------------
+// The service is one request per HTTP call; a slot session keeps n_slots sequences in flight, admits new requests into free
+// slots between chunks of decode steps and retires finished ones, so that the batch-64 throughput of the decode kernels
+// serves a stream of independent requests.  Decode state and token rows live outside the per-call arena; the K/V rows of a
+// newly admitted prompt are prefilled into the caches of its slot, everything already in flight is untouched.
+int mg_slots_begin(mg_engine* e, int n_slots, int max_len, float temperature, int top_k, int eos_id, uint64_t seed) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  if (!e->ready) return fail(MG_E_STATE, "engine not finalized (mg_engine_finalize)");
+  if (n_slots <= 0 || n_slots > e->max_batch) return fail(MG_E_OOM, "n_slots must be in [1, max_batch]");
+  if (max_len <= 1 || max_len > e->max_seq) return fail(MG_E_OOM, "max_len must be in [2, max_seq]");
+  MG_TRY(check_sampling(e, temperature, top_k));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  const int stride = (max_len + 7) & ~7;
+  const size_t state_ints = static_cast<size_t>(n_slots) * 7, out_ints = static_cast<size_t>(n_slots) * (stride + 1);
+  if (state_ints > e->slot_state_cap) {
+    e->dfree(e->d_slot_state); e->d_slot_state = nullptr;
+    if (e->h_slot_flags) { cudaFreeHost(e->h_slot_flags); e->h_slot_flags = nullptr; }
+    MG_TRY(e->dmalloc(&e->d_slot_state, state_ints * sizeof(int32_t)));
+    MG_CUDA_OK(cudaMallocHost(&e->h_slot_flags, 2 * static_cast<size_t>(n_slots) * sizeof(int32_t)));
+    e->slot_state_cap = state_ints;
+  }
+  if (out_ints > e->slot_out_cap) {
+    e->dfree(e->d_slot_out); e->d_slot_out = nullptr;
+    MG_TRY(e->dmalloc(&e->d_slot_out, out_ints * sizeof(int32_t)));
+    e->slot_out_cap = out_ints;
+  }
+  int32_t* d = e->d_slot_state;
+  MG_CUDA_OK(cudaMemsetAsync(d, 0, state_ints * sizeof(int32_t), e->stream));
+  MG_CUDA_OK(cudaMemsetAsync(d + 5 * n_slots, 1, n_slots, e->stream));                 // every slot starts idle (finished)
+  MG_CUDA_OK(cudaMemsetAsync(e->d_slot_out, 0, out_ints * sizeof(int32_t), e->stream));
+  {
+    std::vector<int32_t> ident(n_slots);                              // row of the residual stream the head reads for slot b
+    for (int b = 0; b < n_slots; ++b) ident[b] = b;
+    MG_CUDA_OK(cudaMemcpyAsync(d + 6 * n_slots, ident.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, e->stream));
+    MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
+  e->d_slot_last_rows = d + 6 * n_slots;
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }                // captured state pointers change
+  e->graph_B = -1;
+  e->st.cur_tok = d; e->st.lens = d + n_slots; e->st.n_new = d + 2 * n_slots; e->st.max_new = d + 3 * n_slots;
+  e->st.seq_idx = d + 4 * n_slots; e->st.finished = reinterpret_cast<uint8_t*>(d + 5 * n_slots);
+  e->st.out_len = e->d_slot_out; e->st.out_ids = e->d_slot_out + n_slots; e->st.out_stride = stride;
+  if (!e->d_step_ns) MG_TRY(e->dmalloc(&e->d_step_ns, sizeof(unsigned long long) * (e->max_seq + 1)));
+  e->st.step_ns = nullptr;                                                              // per-token stamps are a batch-call read-out
+  e->cur_B = n_slots; e->cur_M = 0; e->cur_max_tp = 0; e->cur_steps = 0;
+  e->n_slots = n_slots; e->slots_eos = eos_id; e->slots_topk = top_k;
+  e->slot_busy.assign(n_slots, 0);
+  *e->h_sp = SampleParams{temperature, top_k, eos_id, 0, seed, 0};
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream));
+  MG_TRY(ensure_rows(e, n_slots));
+  // the decode path is fixed for the whole session: the persistent kernel appends K/V rows in its own layout only
+  e->slots_mega = false;
+  if (e->dtype == MG_DTYPE_BF16 && e->mega_ok && top_k >= 1 && top_k <= mega::kMegaMaxTopK)
+    for (int s_try = 1; s_try <= mega::kMegaMaxSeqPerCluster && !e->slots_mega; ++s_try) {
+      const int avail = s_try <= 2 ? e->mega_clusters2 : e->mega_clusters4;
+      e->slots_mega = avail > 0 && ceil_div(n_slots, s_try) <= avail;
+    }
+  e->uploaded = false;                                                                  // batch-call read-outs do not apply
+  e->slots_active = true;
+  return MG_OK;
+}
+
+int mg_slots_admit(mg_engine* e, int n, const int32_t* slots, const int32_t* ids, const int32_t* offs, const int32_t* max_new,
+                   const int32_t* seq_index) {
+  if (!e || !slots || !ids || !offs || !max_new || !seq_index) return fail(MG_E_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  if (!e->slots_active) return fail(MG_E_STATE, "no slot session (mg_slots_begin)");
+  if (n <= 0) return MG_OK;
+  const mg_geometry& g = e->geo;
+  if (offs[0] != 0) return fail(MG_E_ARG, "prompt_offsets[0] must be 0");
+  int M = 0, max_tp = 0;
+  std::vector<uint8_t> seen(e->n_slots, 0);
+  for (int j = 0; j < n; ++j) {
+    const int b = slots[j], tp = offs[j + 1] - offs[j];
+    if (b < 0 || b >= e->n_slots) return fail(MG_E_ARG, "slot index outside the session");
+    if (e->slot_busy[b] || seen[b]) return fail(MG_E_STATE, "slot " + std::to_string(b) + " is still in flight");
+    seen[b] = 1;
+    if (tp <= 0) return fail(MG_E_ARG, "empty prompt (the reference indexes generated[:, -1:], api_cache.py:167)");
+    if (tp > g.pos_rows)
+      return fail(MG_E_PROMPT_TOO_LONG, "prompt of " + std::to_string(tp) + " tokens exceeds the " + std::to_string(g.pos_rows) +
+                                            "-row position table (api_cache.py:99)");
+    if (max_new[j] < 0) return fail(MG_E_ARG, "max_new < 0");
+    if (tp + max_new[j] > e->st.out_stride || tp + max_new[j] > e->max_seq)
+      return fail(MG_E_OOM, "prompt + max_new exceeds the max_len of the slot session");
+    M += tp;
+    max_tp = std::max(max_tp, tp);
+  }
+  for (int i = 0; i < M; ++i)
+    if (ids[i] < 0 || ids[i] >= g.vocab_size) return fail(MG_E_TOKEN, "prompt token id outside [0, vocab)");
+  // arena (int32): prompt[M] offsets[n+1] row_seq[M] row_pos[M] seq_start[n] seq_len[n] slots[n] max_new[n] seq_index[n]
+  const size_t ints = static_cast<size_t>(M) * 3 + static_cast<size_t>(n) * 6 + 1;
+  MG_TRY(ensure_arena(e, ints));
+  int32_t* h = e->h_arena;
+  size_t o = 0;
+  auto take = [&](size_t k) { size_t r = o; o += k; return r; };
+  const size_t o_prompt = take(M), o_offs = take(n + 1), o_rseq = take(M), o_rpos = take(M), o_sstart = take(n), o_slen = take(n),
+               o_slots = take(n), o_maxnew = take(n), o_sidx = take(n);
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));                     // the staging buffer may still feed the previous admission
+  std::memcpy(h + o_prompt, ids, sizeof(int32_t) * M);
+  std::memcpy(h + o_offs, offs, sizeof(int32_t) * (n + 1));
+  for (int j = 0; j < n; ++j) {
+    const int tp = offs[j + 1] - offs[j];
+    for (int t = 0; t < tp; ++t) { h[o_rseq + offs[j] + t] = slots[j]; h[o_rpos + offs[j] + t] = t; }
+    h[o_sstart + j] = offs[j]; h[o_slen + j] = tp; h[o_slots + j] = slots[j]; h[o_maxnew + j] = max_new[j]; h[o_sidx + j] = seq_index[j];
+  }
+  MG_CUDA_OK(cudaMemcpyAsync(e->d_arena, h, ints * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  e->h2d += ints * sizeof(int32_t);
+  int32_t* da = e->d_arena;
+  e->d_prompt = da + o_prompt; e->d_offsets = da + o_offs; e->d_row_seq = da + o_rseq; e->d_row_pos = da + o_rpos;
+  e->d_seq_start = da + o_sstart; e->d_seq_len = da + o_slen;
+  e->d_last_rows = e->d_slot_last_rows;
+  e->cur_M = M; e->cur_max_tp = max_tp;
+  MG_TRY(ensure_rows(e, std::max(M, e->n_slots)));
+  MG_TRY(e->dtype == MG_DTYPE_BF16 ? prefill_rows<bf16>(e, M, n) : prefill_rows<float>(e, M, n));
+  MG_TRY(launch_slot_init(e->stream, e->d_prompt, e->d_offsets, da + o_slots, da + o_maxnew, da + o_sidx,
+                          const_cast<int32_t*>(e->st.seq_idx), e->st, n));
+  if (e->slots_mega)
+    MG_TRY(mega::mega_relayout_kv_slots(e->stream, e->d_mega_layers, e->st.lens, da + o_slots, n, g.n_layer, e->max_seq,
+                                        mega_tvt(e->max_seq), g.d_model / g.n_head));
+  for (int j = 0; j < n; ++j) e->slot_busy[slots[j]] = max_new[j] > 0 ? 1 : 0;
+  return MG_OK;
+}
+
+int mg_slots_step(mg_engine* e, int n_steps, uint8_t* finished_out, int32_t* out_len_out) {
+  if (!e || !finished_out || !out_len_out) return fail(MG_E_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  if (!e->slots_active) return fail(MG_E_STATE, "no slot session (mg_slots_begin)");
+  if (n_steps <= 0 || n_steps > e->max_seq) return fail(MG_E_ARG, "n_steps must be in [1, max_seq]");
+  e->cur_steps = n_steps;
+  e->d_last_rows = e->d_slot_last_rows;
+  e->last_run_mega = e->last_run_flow = false;
+  if (e->slots_mega) {
+    int rc = MG_OK;
+    if (!run_decode_mega(e, e->slots_topk, e->slots_eos, &rc, nullptr, nullptr, 0, nullptr))
+      return fail(MG_E_STATE, "slot session: the persistent kernel refused the launch");
+    MG_TRY(rc);
+    e->last_run_mega = true;
+  } else {
+    MG_TRY(e->dtype == MG_DTYPE_BF16 ? run_decode_loop<bf16>(e, e->slots_eos >= 0 ? e->slots_eos : 0)
+                                     : run_decode_loop<float>(e, e->slots_eos >= 0 ? e->slots_eos : 0));
+  }
+  const int n = e->n_slots, fin_ints = (n + 3) / 4;
+  MG_CUDA_OK(cudaMemcpyAsync(e->h_slot_flags, e->st.finished, n, cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaMemcpyAsync(e->h_slot_flags + fin_ints, e->st.out_len, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->d2h += n + n * sizeof(int32_t);
+  std::memcpy(finished_out, e->h_slot_flags, n);
+  std::memcpy(out_len_out, e->h_slot_flags + fin_ints, n * sizeof(int32_t));
+  for (int b = 0; b < n; ++b)
+    if (finished_out[b]) e->slot_busy[b] = 0;
+  return MG_OK;
+}
+
+int mg_slots_fetch(mg_engine* e, int slot, int32_t* out_ids, int cap, int* n_out) {
+  if (!e || !out_ids || !n_out) return fail(MG_E_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  if (!e->slots_active) return fail(MG_E_STATE, "no slot session (mg_slots_begin)");
+  if (slot < 0 || slot >= e->n_slots) return fail(MG_E_ARG, "slot index outside the session");
+  int32_t len = 0;
+  MG_CUDA_OK(cudaMemcpyAsync(&len, e->st.out_len + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  if (len > cap) return fail(MG_E_ARG, "out buffer smaller than the sequence");
+  MG_CUDA_OK(cudaMemcpyAsync(out_ids, e->st.out_ids + static_cast<size_t>(slot) * e->st.out_stride, sizeof(int32_t) * len,
+                             cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->d2h += sizeof(int32_t) * (len + 1);
+  *n_out = len;
+  return MG_OK;
+}
+
+int mg_slots_end(mg_engine* e) {
+  if (!e) return fail(MG_E_ARG, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+  e->graph_B = -1;
+  e->st = DecodeState{};
+  e->slots_active = false;
+  e->uploaded = false;
   return MG_OK;
 }
 

@@ -1070,7 +1070,7 @@ sample_step_kernel(const float* __restrict__ logits, int ld, int V, const Sample
   const SampleParams p = *sp;
   const uint32_t step = static_cast<uint32_t>(st.n_new[b]);
   const int tok = sample_row(logits + static_cast<size_t>(b) * ld, V, p.temperature, p.top_k, p.seed,
-                             p.seq_base + static_cast<uint64_t>(b), step, vals, ss);
+                             p.seq_base + static_cast<uint64_t>(st.seq_idx ? st.seq_idx[b] : b), step, vals, ss);
   if (threadIdx.x == 0) {
     const int pos = st.out_len[b];
     st.out_ids[static_cast<size_t>(b) * st.out_stride + pos] = tok;     // api_cache.py:179
@@ -1111,6 +1111,25 @@ __global__ void decode_init_kernel(const int32_t* __restrict__ prompt_ids, const
     st.lens[b] = n;
     st.n_new[b] = 0;
     st.finished[b] = st.max_new[b] <= 0 ? 1 : 0;
+  }
+}
+
+// continuous batching: the prompts of n newly admitted requests -> decode state of the slots they were given
+__global__ void slot_init_kernel(const int32_t* __restrict__ prompt_ids, const int32_t* __restrict__ offsets,
+                                 const int32_t* __restrict__ slots, const int32_t* __restrict__ max_new,
+                                 const int32_t* __restrict__ seq_idx, int32_t* __restrict__ seq_idx_out, DecodeState st, int n) {
+  const int j = blockIdx.x;
+  if (j >= n) return;
+  const int b = slots[j], o0 = offsets[j], len = offsets[j + 1] - o0;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) st.out_ids[static_cast<size_t>(b) * st.out_stride + i] = prompt_ids[o0 + i];
+  if (threadIdx.x == 0) {
+    st.out_len[b] = len;
+    st.cur_tok[b] = prompt_ids[o0 + len - 1];     // the last prompt token is fed again (api_cache.py:167)
+    st.lens[b] = len;
+    st.n_new[b] = 0;
+    st.max_new[b] = max_new[j];
+    seq_idx_out[b] = seq_idx[j];
+    st.finished[b] = max_new[j] <= 0 ? 1 : 0;
   }
 }
 
@@ -1360,6 +1379,14 @@ template int launch_nocache_embed<bf16>(cudaStream_t, const int32_t*, int, const
 int launch_decode_init(cudaStream_t s, const int32_t* prompt_ids, const int32_t* offsets, DecodeState st, int B) {
   if (B <= 0) return MG_OK;
   decode_init_kernel<<<B, 64, 0, s>>>(prompt_ids, offsets, st, B);
+  MG_LAUNCH_CHECK();
+  return MG_OK;
+}
+
+int launch_slot_init(cudaStream_t s, const int32_t* prompt_ids, const int32_t* offsets, const int32_t* slots, const int32_t* max_new,
+                     const int32_t* seq_idx, int32_t* seq_idx_out, DecodeState st, int n) {
+  if (n <= 0) return MG_OK;
+  slot_init_kernel<<<n, 64, 0, s>>>(prompt_ids, offsets, slots, max_new, seq_idx, seq_idx_out, st, n);
   MG_LAUNCH_CHECK();
   return MG_OK;
 }

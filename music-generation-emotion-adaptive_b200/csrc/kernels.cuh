@@ -32,6 +32,8 @@ struct DecodeState {
   int32_t* max_new;
   uint8_t* finished;
   int32_t out_stride;
+  const int32_t* seq_idx;        // optional [B]: Philox sequence index of row b relative to seq_base (null: b itself) --
+                                 // continuous batching gives every REQUEST its own stream whatever slot it lands in
   unsigned long long* step_ns;   // optional [max steps]: %globaltimer when the token of sequence 0 in decode step i was written
 };
 
@@ -88,6 +90,8 @@ int kernels_init();
 int gemm_tc_init();
 // Copy prompts into the output buffer and initialise the per-sequence decode state after prefill.
 int launch_decode_init(cudaStream_t s, const int32_t* prompt_ids, const int32_t* offsets, DecodeState st, int B);
+int launch_slot_init(cudaStream_t s, const int32_t* prompt_ids, const int32_t* offsets, const int32_t* slots, const int32_t* max_new,
+                     const int32_t* seq_idx, int32_t* seq_idx_out, DecodeState st, int n);
 // Teacher forcing (mg_step_logits): cur_tok[b] = forced[b * stride + col]; lens[b] += 1.
 int launch_force_next(cudaStream_t s, const int32_t* forced, int stride, int col, DecodeState st, int B);
 // Count sequences still running into *active (device).

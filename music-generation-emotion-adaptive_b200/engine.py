@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "mg_abi_version", "mg_last_error", "mg_device_count", "mg_engine_create", "mg_engine_destroy", "mg_load_weight",
     "mg_engine_finalize", "mg_generate", "mg_upload_prompts", "mg_run", "mg_download", "mg_synchronize",
     "mg_engine_stream", "mg_step_logits", "mg_step_logits_at", "mg_generate_nocache", "mg_forward_nocache", "mg_sample_logits",
-    "mg_engine_stats", "mg_set_note_table", "mg_note_events", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
+    "mg_engine_stats", "mg_slots_begin", "mg_slots_admit", "mg_slots_step", "mg_slots_fetch", "mg_slots_end", "mg_set_note_table", "mg_note_events", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
     "mg_bert_finalize", "mg_classify", "mg_bert_upload", "mg_bert_run", "mg_bert_download", "mg_bert_synchronize",
     "mg_bert_stream", "mg_bert_stats", "mg_test_gemm_bf16",
 ]
@@ -93,6 +93,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mg_engine_stats": (c.c_int, [vp, u64p, u64p, u64p]),
         "mg_last_run_timing": (c.c_int, [vp, f32p, f32p, f32p, c.POINTER(c.c_int)]),
         "mg_last_step_times": (c.c_int, [vp, f32p, c.c_int, c.POINTER(c.c_int)]),
+        "mg_slots_begin": (c.c_int, [vp, c.c_int, c.c_int, c.c_float, c.c_int, c.c_int, u64]),
+        "mg_slots_admit": (c.c_int, [vp, c.c_int, i32p, i32p, i32p, i32p, i32p]),
+        "mg_slots_step": (c.c_int, [vp, c.c_int, u8p, i32p]),
+        "mg_slots_fetch": (c.c_int, [vp, c.c_int, i32p, c.c_int, c.POINTER(c.c_int)]),
+        "mg_slots_end": (c.c_int, [vp]),
         "mg_set_note_table": (c.c_int, [vp, i32p, i32p, f32p, f32p, c.c_int]),
         "mg_note_events": (c.c_int, [vp, c.c_int, c.c_int, i32p, i32p, i32p, i32p, i32p, i32p, f32p, f32p]),
         "mg_last_decode_path": (c.c_int, [vp]),
@@ -347,6 +352,37 @@ class Generator:
     def last_decode_path(self) -> str:
         """Which CUDA decode path served the last run: step_graph / cluster_kernel (decode_mega.cu) / flow_kernel (decode_flow.cu)."""
         return self.DECODE_PATHS[int(self.lib.mg_last_decode_path(self._h))]
+
+    # -- slot session: continuous batching (caller side: api_cache.py:186-204) --------------------
+    def slots_begin(self, n_slots: int, max_len: int, temperature: float = 1.0, top_k: Optional[int] = 50, eos_id: int = -1,
+                    seed: Optional[int] = None) -> None:
+        self._n_slots = int(n_slots)
+        _check(self.lib, self.lib.mg_slots_begin(self._h, int(n_slots), int(max_len), float(temperature),
+                                                 0 if top_k is None else int(top_k), int(eos_id), _seed(seed)))
+
+    def slots_admit(self, slots: Sequence[int], prompt_tokens: Sequence[Sequence[int]], max_new: Sequence[int],
+                    seq_index: Sequence[int]) -> None:
+        flat, offs = _pack_prompts(prompt_tokens)
+        sl, mn, si = _i32(slots), _i32(max_new), _i32(seq_index)
+        if not (len(sl) == len(mn) == len(si) == len(prompt_tokens)):
+            raise ValueError("slots, prompts, max_new and seq_index must have the same length")
+        i32 = ctypes.c_int32
+        _check(self.lib, self.lib.mg_slots_admit(self._h, len(sl), _ptr(sl, i32), _ptr(flat, i32), _ptr(offs, i32), _ptr(mn, i32),
+                                                 _ptr(si, i32)))
+
+    def slots_step(self, n_steps: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Up to ``n_steps`` decode steps for every slot in flight -> (finished[n_slots] bool, out_len[n_slots])."""
+        fin, ln = np.zeros(self._n_slots, np.uint8), np.zeros(self._n_slots, np.int32)
+        _check(self.lib, self.lib.mg_slots_step(self._h, int(n_steps), _ptr(fin, ctypes.c_uint8), _ptr(ln, ctypes.c_int32)))
+        return fin.astype(bool), ln
+
+    def slots_fetch(self, slot: int, cap: int = 8192) -> List[int]:
+        buf, n = np.zeros(cap, np.int32), ctypes.c_int()
+        _check(self.lib, self.lib.mg_slots_fetch(self._h, int(slot), _ptr(buf, ctypes.c_int32), cap, ctypes.byref(n)))
+        return buf[:n.value].tolist()
+
+    def slots_end(self) -> None:
+        _check(self.lib, self.lib.mg_slots_end(self._h))
 
     # -- device-side detokenisation (api_cache.py:157,208-221) -------------------------------------
     def set_note_table(self, tok2id: Dict[str, int], instrument_program=None, note_number=None) -> None:

@@ -670,3 +670,115 @@ def test_device_detokenisation_equals_the_reference_loop():
     with pytest.raises(ValueError):
         e.note_events(max_inst=64, max_notes=4)                          # capacity overflow is reported, not truncated
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# continuous batching: slot sessions, late admission, slot reuse
+# ---------------------------------------------------------------------------------------------------
+def test_slot_session_fp32_late_admission_and_slot_reuse_equal_batch1_reference_runs():
+    """fp32 step-graph path: whatever slot a request gets and whenever it is admitted, its greedy tokens are the batch-1
+    reference run of its prompt (oracle port of sample_kvcache) -- also in a slot that still holds a previous request's K/V."""
+    geo = mg.GEOMETRIES["tiny_hd64"]
+    ck = checkpoint("tiny_hd64", 0)
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head)
+    rng = np.random.default_rng(5)
+    reqs = [(rng.integers(0, geo.vocab_size, 3 + i).tolist(), 9 + 4 * i) for i in range(7)]
+    want = [gpt_kv.sample_ids(ora, p, max_len=len(p) + n, temperature=1.0, top_k=1) for p, n in reqs]
+    e = mg.Generator(ck["model"], n_head=geo.n_head, dtype="fp32", max_batch=4, max_seq=96)
+    e.slots_begin(4, 64, 1.0, 1, eos_id=-1, seed=0)
+    got = {}
+    slot_of = {0: 0, 1: 2}
+    e.slots_admit([0, 2], [reqs[0][0], reqs[1][0]], [reqs[0][1], reqs[1][1]], [0, 1])
+    fin, ln = e.slots_step(5)
+    assert not fin[0] and not fin[2] and fin[1] and fin[3] and ln[0] == len(reqs[0][0]) + 5
+    with pytest.raises(RuntimeError):
+        e.slots_admit([0], [reqs[2][0]], [4], [9])                       # slot 0 is in flight
+    e.slots_admit([1, 3], [reqs[2][0], reqs[3][0]], [reqs[2][1], reqs[3][1]], [2, 3])     # late admission
+    slot_of.update({2: 1, 3: 3})
+    pending = [4, 5, 6]
+    for _ in range(40):
+        fin, ln = e.slots_step(3)
+        for r, s in list(slot_of.items()):
+            if fin[s]:
+                got[r] = e.slots_fetch(s)
+                del slot_of[r]
+                if pending:                                              # the freed slot is reused at once
+                    nr = pending.pop(0)
+                    e.slots_admit([s], [reqs[nr][0]], [reqs[nr][1]], [nr])
+                    slot_of[nr] = s
+        if not slot_of:
+            break
+    assert sorted(got) == list(range(7))
+    for r in range(7):
+        assert got[r] == want[r], r
+    e.slots_end()
+    assert e.generate([reqs[0][0]], reqs[0][1], 1.0, 1)[0] == want[0]      # batch calls work again after the session
+    e.close()
+
+
+def test_slot_session_persistent_kernel_late_admission_does_not_change_a_request():
+    """bf16 persistent cluster kernel, 64 slots, top-k 40 sampling: request R has the same tokens (a) admitted at the start and
+    (b) admitted 24 decode steps late into the same slot, and nobody else's tokens change; (c) a session decoded in chunks equals
+    the one-launch batch call with the same Philox streams."""
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 64, seed=9)]
+    e = engine("train_large", 0, "bf16", max_batch=64, max_seq=1088)
+    others = [b for b in range(64) if b != 5]
+
+    def run(late):
+        e.slots_begin(64, 256, 1.0, 40, eos_id=-1, seed=77)
+        e.slots_admit(others, [prompts[b] for b in others], [60 + b % 7 for b in others], [2000 + b for b in others])
+        if late:
+            for _ in range(3):
+                e.slots_step(8)
+        e.slots_admit([5], [prompts[5]], [48], [1005])
+        for _ in range(20):
+            fin, ln = e.slots_step(8)
+            if fin.all():
+                break
+        assert fin.all() and e.last_decode_path() == "cluster_kernel"
+        rows = [e.slots_fetch(b) for b in range(64)]
+        e.slots_end()
+        return rows
+
+    a, b = run(False), run(True)
+    assert a[5] == b[5] and len(a[5]) == len(prompts[5]) + 48
+    assert all(len(a[i]) == len(prompts[i]) + 60 + i % 7 for i in others)
+    assert all(a[i] == b[i] for i in others)                             # and nobody else notices the newcomer
+    # chunked decode == one launch: all 64 admitted in ONE call (same prefill kernels as a batch call: the tensor-core GEMMs take
+    # over at >= 32 prompt rows, so bf16 K/V rows of a prompt depend on how many rows were prefilled WITH it -- bit-identity
+    # across admission groupings is an fp32-mode property, tested above), then 6 chunks of 8 steps against one 48-step launch
+    e.slots_begin(64, 256, 1.0, 40, eos_id=-1, seed=77)
+    e.slots_admit(list(range(64)), prompts, [48] * 64, [1000 + b for b in range(64)])
+    for _ in range(6):
+        fin, ln = e.slots_step(8)
+    assert fin.all()
+    d = [e.slots_fetch(b) for b in range(64)]
+    e.slots_end()
+    c = e.generate(prompts, 48, 1.0, 40, seed=77, seq_index_base=1000)
+    assert c == d
+
+
+def test_continuous_batcher_serves_a_request_stream():
+    geo = mg.GEOMETRIES["tiny_hd64"]
+    ck = checkpoint("tiny_hd64", 0)
+    ora = gpt_kv.KVModelOracle(mg.remap_state_dict(ck["model"]), geo.n_head)
+    rng = np.random.default_rng(6)
+    reqs = [(rng.integers(0, geo.vocab_size, 2 + i % 5).tolist(), 5 + (7 * i) % 23) for i in range(21)]
+    e = mg.Generator(ck["model"], n_head=geo.n_head, dtype="fp32", max_batch=6, max_seq=96)
+    cb = mg.ContinuousBatcher(e, n_slots=6, max_len=64, temperature=1.0, top_k=1, eos_id=-1, chunk_steps=4, seed=1)
+    futs = [cb.submit(p, n) for p, n in reqs]
+    bad = cb.submit([geo.vocab_size + 3], 4)                              # an out-of-vocabulary id fails its own request only
+    too_long = cb.submit([1, 2, 3], 500)
+    res = [f.result(timeout=120) for f in futs]
+    with pytest.raises(ValueError):
+        bad.result(timeout=120)
+    with pytest.raises(ValueError):
+        too_long.result(timeout=120)
+    assert cb.generate([4, 5, 6], 0) == [4, 5, 6]
+    cb.close()
+    for (p, n), r in zip(reqs, res):
+        assert r == gpt_kv.sample_ids(ora, p, max_len=len(p) + n, temperature=1.0, top_k=1)
+    assert len(cb.admissions) > 3 and sum(n for _, n in cb.admissions) == 21       # admitted over several chunks, not as one batch
+    e.close()

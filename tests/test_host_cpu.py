@@ -392,3 +392,59 @@ def test_note_table_follows_the_reference_token_rules():
     got = odetok.tokens_to_instruments(toks, lambda n: V.GM_PROGRAMS.get(n, 0), V.note_name_to_number)
     assert [(g["name"], g["program"], g["notes"]) for g in got] == [("Violin", 40, [(61, 1.5, 2.25)]), ("Kazoo", 0, []),
                                                                      ("Violin", 40, [(-13, 0.0, 1.0)])]
+
+
+class _FakeSlotEngine:
+    """Host-logic stand-in for the slot-session calls of Generator: a slot emits prompt[-1] + 1, + 2, ... one token per step."""
+
+    def __init__(self):
+        self.rows, self.left, self.log = {}, {}, []
+
+    def slots_begin(self, n_slots, max_len, temperature, top_k, eos_id, seed):
+        self.n = n_slots
+
+    def slots_admit(self, slots, prompts, max_new, seq_index):
+        for p in prompts:
+            if any(t < 0 for t in p):
+                raise ValueError("prompt token id outside [0, vocab)")
+        for s, p, m, i in zip(slots, prompts, max_new, seq_index):
+            assert s not in self.rows
+            self.rows[s], self.left[s] = list(p), m
+            self.log.append((s, i))
+
+    def slots_step(self, n_steps):
+        import numpy as np
+        for s in self.rows:
+            k = min(n_steps, self.left[s])
+            self.rows[s] += [self.rows[s][-1] + j + 1 for j in range(k)]
+            self.left[s] -= k
+        fin = np.array([s not in self.rows or self.left[s] == 0 for s in range(self.n)])
+        return fin, np.zeros(self.n, np.int32)
+
+    def slots_fetch(self, slot, cap):
+        self.left.pop(slot)
+        return self.rows.pop(slot)
+
+    def slots_end(self):
+        self.ended = True
+
+
+def test_continuous_batcher_admits_between_chunks_reuses_slots_and_isolates_bad_requests():
+    eng = _FakeSlotEngine()
+    cb = mg.ContinuousBatcher(eng, n_slots=3, max_len=40, chunk_steps=4, seed=0, first_seq_index=100)
+    futs = [cb.submit([10 * i, 10 * i + 1], 3 + 2 * i) for i in range(8)]
+    bad = cb.submit([5, -1], 4)
+    long_one = cb.submit([1], 100)
+    res = [f.result(timeout=30) for f in futs]
+    with pytest.raises(ValueError):
+        bad.result(timeout=30)
+    with pytest.raises(ValueError):
+        long_one.result(timeout=30)
+    assert cb.generate([7, 8], 0) == [7, 8]
+    cb.close()
+    for i, r in enumerate(res):
+        n = 3 + 2 * i
+        assert r[:2] == [10 * i, 10 * i + 1] and len(r) == 2 + n
+    assert sorted(i for _, i in eng.log) == list(range(100, 108))          # one Philox stream index per admitted request
+    assert max(s for s, _ in eng.log) <= 2 and len(eng.log) == 8           # 8 requests through 3 slots
+    assert len(cb.admissions) >= 3 and eng.ended
