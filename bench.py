@@ -275,9 +275,9 @@ def main():
     barrier()
     e0 = time.perf_counter()
     for i in range(args.steps):
-        out = eng.generate(prompts, NEW_TOKENS, TEMPERATURE, TOP_K, eos_id=-1, seed=i, seq_index_base=rank * BATCH)
+        out = eng.generate(prompts, NEW_TOKENS, TEMPERATURE, TOP_K, eos_id=-1, seed=i, seq_index_base=rank * BATCH, as_arrays=True)
         if world > 1:
-            mg.gather_token_lists(out, BATCH * world, as_arrays=True)   # the only exchange of the path: final token gather
+            mg.gather_token_lists(out, BATCH * world, as_arrays=True, max_len=max(prompt_lens) + NEW_TOKENS)   # the only exchange of the path
     barrier()
     e2e_s = time.perf_counter() - e0
     st1 = eng.stats()

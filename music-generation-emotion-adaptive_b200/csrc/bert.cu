@@ -77,6 +77,8 @@ struct mg_bert {
   cudaGraphExec_t graph = nullptr;
   int graph_N = 0, graph_T = 0, shape_runs = 0;
   uint64_t graph_kernels = 0;
+  int prof_which = 0;                       // MG_PAIR_PROF (debug)
+  unsigned long long* d_prof = nullptr;
 
   template <typename P> int dmalloc(P** p, size_t bytes) {
     void* q = nullptr;
@@ -109,14 +111,19 @@ int bert_forward(mg_bert* b) {
   for (int l = 0; l < g.n_layers; ++l) {
     BertLayerW& w = b->layers[l];
     { GemmEpilogue epi; epi.bias = w.bqkv; epi.out_bf16 = b->qkv; epi.ld_out = 3 * d;
+      if (l == 2 && b->prof_which == 3) epi.prof = b->d_prof;
       MG_TRY(bgemm(b, b->hA, &b->tm_hA, w.wqkv, &w.m_qkv, M, 3 * d, d, epi)); }
     MG_TRY(launch_encoder_attn<bf16>(b->stream, b->qkv, b->d_seq_start, b->d_seq_len, b->d_mask, b->att, N, d, g.n_heads, T));
     { GemmEpilogue epi; epi.bias = w.bo; epi.resid_bf16 = b->hA; epi.out_bf16 = b->pre; epi.ld_out = d;
+      if (l == 2 && b->prof_which == 4) epi.prof = b->d_prof;
       MG_TRY(bgemm(b, b->att, &b->tm_att, w.wo, &w.m_o, M, d, d, epi)); }
     MG_TRY((launch_layernorm<bf16, bf16>(b->stream, b->pre, w.sa_w, w.sa_b, b->hB, nullptr, M, d, eps)));
+    // debug: MG_PAIR_PROF=<1 lin1 | 2 lin2 | 3 qkv | 4 out_proj> -> per-tile timeline of one CTA pair in layer 2 (see bert_prof_dump)
     { GemmEpilogue epi; epi.bias = w.b1; epi.act = ACT_GELU; epi.out_bf16 = b->h1; epi.ld_out = f;
+      if (l == 2 && b->prof_which == 1) epi.prof = b->d_prof;
       MG_TRY(bgemm(b, b->hB, &b->tm_hB, w.w1, &w.m_1, M, f, d, epi)); }
     { GemmEpilogue epi; epi.bias = w.b2; epi.resid_bf16 = b->hB; epi.out_bf16 = b->pre; epi.ld_out = d;
+      if (l == 2 && b->prof_which == 2) epi.prof = b->d_prof;
       MG_TRY(bgemm(b, b->h1, &b->tm_h1, w.w2, &w.m_2, M, d, f, epi)); }
     MG_TRY((launch_layernorm<bf16, bf16>(b->stream, b->pre, w.out_w, w.out_b, b->hA, nullptr, M, d, eps)));
   }
@@ -129,7 +136,21 @@ int bert_forward(mg_bert* b) {
   return MG_OK;
 }
 
+// debug read-out of MG_PAIR_PROF: per tile {MMA issue start, last MMA issued, epilogue start, epilogue end} in ns
+static void bert_prof_dump(mg_bert* b) {
+  unsigned long long h[128];
+  cudaStreamSynchronize(b->stream);
+  cudaMemcpy(h, b->d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+  unsigned long long t0 = ~0ull;
+  for (int i = 0; i < 128; ++i) if (h[i]) t0 = std::min(t0, h[i]);
+  fprintf(stderr, "[pair prof %d] tile: mma_start mma_issued | epi_start epi_end (ns)\n", b->prof_which);
+  for (int t = 0; t < 32 && h[4 * t]; ++t)
+    fprintf(stderr, "[pair prof] %2d: %7llu %7llu | %7llu %7llu\n", t, h[4 * t] - t0, h[4 * t + 1] - t0, h[4 * t + 2] - t0, h[4 * t + 3] - t0);
+  cudaMemset(b->d_prof, 0, sizeof(h));
+}
+
 int bert_run(mg_bert* b) {
+  if (b->prof_which) { const int rc = bert_forward(b); bert_prof_dump(b); return rc; }
   if (!b->use_graph) return bert_forward(b);
   if (b->graph_N != b->cur_N || b->graph_T != b->cur_T) {       // new shape: start counting again
     if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
@@ -254,6 +275,11 @@ int mg_bert_create(const mg_bert_geometry* geo, int device, int max_tokens, mg_b
   b->max_tokens = ceil_div(max_tokens, 128) * 128;
   const char* env_gemm = std::getenv("MG_GEMM");
   b->use_tc = !(env_gemm && std::strcmp(env_gemm, "simt") == 0);
+  if (const char* pp = std::getenv("MG_PAIR_PROF")) {
+    b->prof_which = std::atoi(pp);
+    if (b->prof_which && cudaMalloc(&b->d_prof, 128 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(b->d_prof, 0, 128 * sizeof(unsigned long long));
+    else b->prof_which = 0;
+  }
   const char* env_graph = std::getenv("MG_BERT_GRAPH");
   b->use_graph = !(env_graph && std::atoi(env_graph) == 0);
   b->launches0 = g_kernel_launches.load();

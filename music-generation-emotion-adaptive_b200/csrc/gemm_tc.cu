@@ -376,7 +376,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     __syncwarp();
   } else {
     const int quarter = warp & 3;                                   // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                               // which half of the tile's columns
+    const int half = (warp - 2) >> 2;                               // which part (1 / kParts) of the tile's columns
     const size_t ld = static_cast<size_t>(epi.ld_out);
     uint8_t* stg = smem + Cfg::kStages * Cfg::kStageBytes + 256 + (warp - 2) * kEpiWarpBytes;   // behind the barriers
     const bool coalesce = epi_can_coalesce(epi) && (ld % 8 == 0);
@@ -481,17 +481,27 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
 //               warps 2..9 = epilogue of the CTA's own 128 accumulator rows (TMEM lanes 0..127 x 256 columns x 2 buffers)
 //   leader    : warp 1 = MMA issuer (tcgen05.mma.cta_group::2, M = 256); commits are multicast to both CTAs' barriers
 // -------------------------------------------------------------------------------------------------
+#ifndef MG_PAIR_EPI_PARTS
+#define MG_PAIR_EPI_PARTS 4
+#endif
 struct PairCfg {
+  // epilogue warps per TMEM lane quarter: each takes kBN / kParts of the tile's columns.  The epilogue of a chunk is a chain of
+  // dependent latencies (tcgen05.ld -> math -> shared-memory transpose -> global store); with 2 warps per scheduler (kParts = 2)
+  // the K = 768 GEMMs of the classifier were bound by it (lin1: tensor pipe 44 % active, issue slots 49 %, ncu r1j)
+  static constexpr int kParts = MG_PAIR_EPI_PARTS;
+  static constexpr int kEpiWarps = 4 * kParts;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kBN = 256;
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;              // 128 rows of A
   static constexpr int kBBytes = (kBN / 2) * kGemmBK * 2;            // 128 of the 256 weight rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 6;
+  static constexpr int kStages = kParts > 2 ? 5 : 6;                 // 16 staging buffers of 2.5 KB take the sixth stage's room
   static constexpr int kTmemCols = 2 * kBN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 8 * kEpiWarpBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiWarps * kEpiWarpBytes;
+  static_assert(kSmemBytes <= 227 * 1024, "pair kernel: shared memory");
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg::kThreads, 1)
 gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                          int M, int N, int K, GemmEpilogue epi) {
   using Cfg = PairCfg;
@@ -517,11 +527,11 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 16); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 2 * Cfg::kEpiWarps); }
     ptx::fence_mbar_init();
   }
-  // the peer's barriers must exist before anything of this CTA can signal them
-  ptx::cluster_arrive();
+  // the peer's barriers must exist before anything of this CTA can signal them (fence.mbarrier_init publishes them)
+  ptx::cluster_arrive_relaxed();
   ptx::cluster_wait();
   if (warp == 1) ptx::tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
   ptx::tc_fence_before_sync();
@@ -556,6 +566,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t buf = it & 1;
         ptx::mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);      // both CTAs' epilogues drained this accumulator buffer
         ptx::tc_fence_after_sync();
+        if (epi.prof && pair == 0 && it < 32) epi.prof[it * 4 + 0] = ptx::global_timer_ns();
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
@@ -569,6 +580,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit_pair(&tmem_full[buf]);
+        if (epi.prof && pair == 0 && it < 32) epi.prof[it * 4 + 1] = ptx::global_timer_ns();
       }
     }
     __syncwarp();
@@ -585,10 +597,12 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t buf = it & 1;
       ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after_sync();
+      const bool prof_on = epi.prof && pair == 0 && rank == 0 && warp == 2 && lane == 0 && it < 32;
+      if (prof_on) epi.prof[it * 4 + 2] = ptx::global_timer_ns();
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < M;
 #pragma unroll 1
-      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+      for (int c = half * (BN / (32 * Cfg::kParts)); c < (half + 1) * (BN / (32 * Cfg::kParts)); ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c * 32, r);
         const int col0 = n0 + c * 32;
@@ -662,6 +676,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
+      if (prof_on) epi.prof[it * 4 + 3] = ptx::global_timer_ns();
       if (lane == 0) ptx::mbar_arrive_cluster_relaxed(lead_empty0 + buf * 8);   // the leader's tmem_empty[buf]
     }
   }
@@ -669,7 +684,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   // nobody leaves (or frees TMEM) while the peer can still signal this CTA's barriers or read its shared memory
   ptx::tc_fence_before_sync();
   __syncthreads();
-  ptx::cluster_arrive();
+  ptx::cluster_arrive_relaxed();                                    // lifetime only: no data is handed over here
   ptx::cluster_wait();
   if (warp == 1) ptx::tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
 }
@@ -677,7 +692,7 @@ gemm_bf16_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 int launch_pair(cudaStream_t stream, const CUtensorMap* ta, const CUtensorMap* tw_half, int M, int N, int K,
                 const GemmEpilogue& epi) {
   const int total = ceil_div(M, 2 * kGemmBM) * ceil_div(N, PairCfg::kBN);
-  gemm_bf16_tc_pair_kernel<<<2 * std::min(total, 74), kPThreads, PairCfg::kSmemBytes, stream>>>(*ta, *tw_half, M, N, K, epi);
+  gemm_bf16_tc_pair_kernel<<<2 * std::min(total, 74), PairCfg::kThreads, PairCfg::kSmemBytes, stream>>>(*ta, *tw_half, M, N, K, epi);
   MG_LAUNCH_CHECK();
   return MG_OK;
 }

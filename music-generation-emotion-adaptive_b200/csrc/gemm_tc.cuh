@@ -20,6 +20,9 @@ struct GemmEpilogue {
   float* out_f32 = nullptr;
   bf16* out_bf16 = nullptr;
   int ld_out = 0;     // row stride (elements) of out_* and resid_*
+  // debug (MG_PAIR_PROF): per-tile %globaltimer stamps of cluster 0 / CTA 0 of the CTA-pair kernel: [tile][4] =
+  // {MMA issue starts (accumulator buffer free), last MMA issued, epilogue starts (accumulator complete), epilogue done}
+  unsigned long long* prof = nullptr;
 };
 
 // Tensor map over a row-major bf16 matrix [rows, cols] (cols contiguous) with a {64 x box_rows} box

@@ -210,6 +210,9 @@ __device__ __forceinline__ uint32_t cluster_id_x() {
   return r;
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// no memory ordering implied (CUTLASS: fence_barrier_init + cluster_arrive_relaxed + cluster_wait): for hand-shakes that only
+// order barrier initialisation / lifetime, where the release form costs a MEMBAR.ALL.GPU
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // shared::cta address of this CTA -> shared::cluster address of the same location in CTA `rank`
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {

@@ -29,6 +29,9 @@ def shard(items: Sequence, rank: int, world_size: int) -> List:
     return list(items[lo:hi])
 
 
+_GATHER_BUFFERS: dict = {}
+
+
 def gather_token_lists(local: Sequence[Sequence[int]], n_total: int, group=None,
                        device: Optional[torch.device] = None, as_arrays: bool = False, max_len: Optional[int] = None):
     """All ranks receive the token lists of all ``n_total`` requests in request order.
@@ -60,17 +63,32 @@ def gather_token_lists(local: Sequence[Sequence[int]], n_total: int, group=None,
         max_len = int(t.item())
     elif my_max > max_len:
         raise ValueError(f"a result of {my_max} tokens exceeds max_len={max_len}")
-    stage = torch.empty((max_local, 1 + max_len), dtype=torch.int32, pin_memory=on_gpu)
+    # staging buffers are reused across calls (a pinned allocation costs milliseconds -- more than the exchange itself)
+    key = (max_local, max_len, world, str(dev), on_gpu)
+    bufs = _GATHER_BUFFERS.get(key)
+    if bufs is None:
+        if len(_GATHER_BUFFERS) > 8:
+            _GATHER_BUFFERS.clear()
+        stage = torch.empty((max_local, 1 + max_len), dtype=torch.int32, pin_memory=on_gpu)
+        allo_t = torch.empty((world, max_local, 1 + max_len), dtype=torch.int32, device=dev)
+        host = torch.empty((world, max_local, 1 + max_len), dtype=torch.int32, pin_memory=on_gpu)
+        bufs = _GATHER_BUFFERS[key] = (stage, allo_t, host)
+    stage, allo_t, host = bufs
     nbuf = stage.numpy()
-    nbuf.fill(-1)
     for i, x in enumerate(local):
-        nbuf[i, 0] = len(x)
-        if len(x):
-            nbuf[i, 1:1 + len(x)] = x
+        n = len(x)
+        nbuf[i, 0] = n
+        nbuf[i, 1:1 + n] = x
+        nbuf[i, 1 + n:] = -1
+    nbuf[len(local):] = -1
     buf = stage.to(dev, non_blocking=True) if on_gpu else stage
-    allo_t = torch.empty((world,) + tuple(buf.shape), dtype=torch.int32, device=dev)
     dist.all_gather(list(allo_t.unbind(0)), buf, group=group)   # views of ONE buffer: NCCL gathers in place, no copy-out
-    allo = allo_t.cpu().numpy()                            # one device -> host copy for all ranks' rows
+    if on_gpu:
+        host.copy_(allo_t, non_blocking=True)               # one device -> host copy for all ranks' rows
+        torch.cuda.current_stream(dev).synchronize()
+        allo = host.numpy().copy() if as_arrays else host.numpy()   # as_arrays hands out views: detach them from the reused buffer
+    else:
+        allo = allo_t.numpy().copy() if as_arrays else allo_t.numpy()
     result = []
     for r in range(world):
         o = allo[r]
