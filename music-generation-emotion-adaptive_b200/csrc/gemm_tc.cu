@@ -482,7 +482,7 @@ gemm_bf16_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
 //   leader    : warp 1 = MMA issuer (tcgen05.mma.cta_group::2, M = 256); commits are multicast to both CTAs' barriers
 // -------------------------------------------------------------------------------------------------
 #ifndef MG_PAIR_EPI_PARTS
-#define MG_PAIR_EPI_PARTS 4
+#define MG_PAIR_EPI_PARTS 2
 #endif
 struct PairCfg {
   // epilogue warps per TMEM lane quarter: each takes kBN / kParts of the tile's columns.  The epilogue of a chunk is a chain of
