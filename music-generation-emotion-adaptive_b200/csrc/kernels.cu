@@ -137,8 +137,11 @@ layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ w, const fl
 
 
 // bf16 -> bf16 LayerNorm with 16-byte accesses: lane owns chunks lane, lane + 32, ... of 8 elements (d = 256 * NCH).
+#ifndef MG_LN_MIN_BLOCKS
+#define MG_LN_MIN_BLOCKS 1
+#endif
 template <int NCH>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, MG_LN_MIN_BLOCKS)
 layernorm_bf16_vec_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                           bf16* __restrict__ y, int M, float eps) {
   constexpr int d = 256 * NCH;
@@ -839,6 +842,157 @@ encoder_attn_tc_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Pipelined variant for sequences of at most 64 tokens (the classifier's shape, BASELINE config 2: 256 texts x 64 tokens x 12
+// heads = 3072 independent 64 x 64 attentions).  The one-tile-per-CTA kernel above spends its life waiting for ONE global round
+// trip (24 KB per CTA: 3.2 TB/s over the pass); here a persistent CTA walks over (sequence, head) items with the Q / K / V tiles
+// of item i + 1 in flight (cp.async, 16-byte, zero-fill for rows past the end) while item i is computed.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+encoder_attn_tc_pipe_kernel(const bf16* __restrict__ qkv, const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
+                            const uint8_t* __restrict__ key_mask, bf16* __restrict__ out, int d, int H, int n_items, float scale_log2) {
+  constexpr int P = HD + 8;                          // padded pitch: ldmatrix rows land in distinct banks
+  constexpr int CPR = HD / 8;                        // 16-byte chunks per row
+  constexpr int TILE = 64 * P;                       // elements of one staged matrix
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  bf16* stage0 = reinterpret_cast<bf16*>(attn_smem);                 // [2 stages][Q | K | V][64][P]
+  float* kbias = reinterpret_cast<float*>(attn_smem + 2 * 3 * TILE * sizeof(bf16));   // [2][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t ld = static_cast<size_t>(3) * d;
+
+  auto issue = [&](int item, int st) {
+    const int b = item / H, h = item - b * H;
+    const int len = seq_len[b], start = seq_start[b];
+    const bf16* base = qkv + static_cast<size_t>(start) * ld + h * HD;
+    bf16* Qs = stage0 + st * 3 * TILE;
+    const uint32_t q_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Qs));
+#pragma unroll
+    for (int j = 0; j < 64 * CPR / 128; ++j) {
+      const int i = threadIdx.x + j * 128, r = i / CPR, c = i - r * CPR;
+      const bool ok = r < len;
+      const bf16* src = base + static_cast<size_t>(ok ? r : 0) * ld + c * 8;
+      const uint32_t dst = q_addr + (r * P + c * 8) * 2;
+      cp_async16_zfill(dst, src, ok);
+      cp_async16_zfill(dst + TILE * 2, src + d, ok);
+      cp_async16_zfill(dst + 2 * TILE * 2, src + 2 * d, ok);
+    }
+    if (threadIdx.x < 64) {
+      const int kr = threadIdx.x;
+      kbias[st * 64 + kr] = (kr < len && (key_mask == nullptr || key_mask[start + kr] != 0)) ? 0.f : -INFINITY;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int item = blockIdx.x, st = 0;
+  if (item < n_items) issue(item, 0);
+  for (; item < n_items; item += gridDim.x, st ^= 1) {
+    const int next = item + gridDim.x;
+    if (next < n_items) {
+      issue(next, st ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int b = item / H, h = item - b * H;
+    const int len = seq_len[b], start = seq_start[b];
+    const bf16* Qs = stage0 + st * 3 * TILE;
+    const bf16* Ks = Qs + TILE;
+    const bf16* Vs = Ks + TILE;
+    const float* Kb = kbias + st * 64;
+    const int mi = lane >> 3;
+    if (warp * 16 < len) {                            // warp-uniform: this warp's 16 query rows exist
+      uint32_t qf[HD / 16][4];
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Qs + (warp * 16 + (lane & 7) + (mi & 1) * 8) * P + ks * 16 + (mi >> 1) * 8)), qf[ks]);
+      float s[8][4];
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[t][e] = 0.f;
+#pragma unroll
+      for (int nt2 = 0; nt2 < 4; ++nt2) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          uint32_t kf[4];
+          ldsm_x4(static_cast<uint32_t>(__cvta_generic_to_shared(Ks + (nt2 * 16 + (lane & 7) + (mi >> 1) * 8) * P + ks * 16 + (mi & 1) * 8)), kf);
+          mma_16816(s[2 * nt2], qf[ks], kf[0], kf[1]);
+          mma_16816(s[2 * nt2 + 1], qf[ks], kf[2], kf[3]);
+        }
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float b0 = Kb[t * 8 + (lane & 3) * 2], b1 = Kb[t * 8 + (lane & 3) * 2 + 1];
+        s[t][0] = s[t][0] * scale_log2 + b0;
+        s[t][1] = s[t][1] * scale_log2 + b1;
+        s[t][2] = s[t][2] * scale_log2 + b0;
+        s[t][3] = s[t][3] * scale_log2 + b1;
+        mx[0] = fmaxf(mx[0], fmaxf(s[t][0], s[t][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[t][2], s[t][3]));
+      }
+      float l_run[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        mx[r] = (mx[r] == -INFINITY) ? 0.f : mx[r];      // every key masked: keep everything at zero
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        s[t][0] = fast_exp2(s[t][0] - mx[0]); s[t][1] = fast_exp2(s[t][1] - mx[0]);
+        s[t][2] = fast_exp2(s[t][2] - mx[1]); s[t][3] = fast_exp2(s[t][3] - mx[1]);
+        l_run[0] += s[t][0] + s[t][1];
+        l_run[1] += s[t][2] + s[t][3];
+      }
+      float o[HD / 8][4];
+#pragma unroll
+      for (int t = 0; t < HD / 8; ++t)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[t][e] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack2_bf16(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack2_bf16(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack2_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack2_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dn2 = 0; dn2 < HD / 16; ++dn2) {
+          uint32_t vf[4];
+          ldsm_x4_trans(static_cast<uint32_t>(__cvta_generic_to_shared(Vs + (kk * 16 + (lane & 7) + (mi & 1) * 8) * P + dn2 * 16 + (mi >> 1) * 8)), vf);
+          mma_16816(o[2 * dn2], pa, vf[0], vf[1]);
+          mma_16816(o[2 * dn2 + 1], pa, vf[2], vf[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int qrow = warp * 16 + (lane >> 2) + r * 8;
+        if (qrow < len) {
+          const float inv = 1.0f / l_run[r];
+          bf16* op = out + static_cast<size_t>(start + qrow) * d + h * HD + (lane & 3) * 2;
+#pragma unroll
+          for (int t = 0; t < HD / 8; ++t)
+            *reinterpret_cast<uint32_t*>(op + t * 8) = pack2_bf16(o[t][2 * r] * inv, o[t][2 * r + 1] * inv);
+        }
+      }
+    }
+    __syncthreads();                                  // this stage is refilled by the NEXT iteration's issue()
+  }
+}
+
 // =================================================================================================
 // Sampler: /temperature -> top-k (radix select) -> softmax over the kept set -> Philox multinomial
 // =================================================================================================
@@ -1315,6 +1469,19 @@ int launch_encoder_attn(cudaStream_t s, const T* qkv, const int32_t* seq_start, 
     dim3 grid_tc(B * H, ceil_div(max_len, 64));
     const bf16* q16 = reinterpret_cast<const bf16*>(qkv);
     bf16* o16 = reinterpret_cast<bf16*>(out);
+    static const bool pipe_off = std::getenv("MG_ATTN_PIPE") && std::atoi(std::getenv("MG_ATTN_PIPE")) == 0;
+    if (max_len <= 64 && B * H >= 1024 && !pipe_off) {
+      // many short sequences (the classifier): persistent CTAs, next item's tiles in flight while this one is computed
+      static int sms = 0;
+      if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int per_sm = hd == 64 ? 4 : 6;
+      const size_t smem = static_cast<size_t>(2) * 3 * 64 * (hd + 8) * sizeof(bf16) + 2 * 64 * sizeof(float);
+      const int grid_p = std::min(B * H, sms * per_sm);
+      if (hd == 64) encoder_attn_tc_pipe_kernel<64><<<grid_p, 128, smem, s>>>(q16, seq_start, seq_len, key_mask, o16, d, H, B * H, scale_log2);
+      else encoder_attn_tc_pipe_kernel<32><<<grid_p, 128, smem, s>>>(q16, seq_start, seq_len, key_mask, o16, d, H, B * H, scale_log2);
+      MG_LAUNCH_CHECK();
+      return MG_OK;
+    }
     if (hd == 64) encoder_attn_tc_kernel<64><<<grid_tc, 128, 0, s>>>(q16, seq_start, seq_len, key_mask, o16, d, H, scale_log2);
     else encoder_attn_tc_kernel<32><<<grid_tc, 128, 0, s>>>(q16, seq_start, seq_len, key_mask, o16, d, H, scale_log2);
     MG_LAUNCH_CHECK();
@@ -1337,6 +1504,8 @@ static int sample_smem_ok(int V, size_t* bytes) {
 }
 
 int kernels_init() {
+  MG_CUDA_OK(cudaFuncSetAttribute(encoder_attn_tc_pipe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  MG_CUDA_OK(cudaFuncSetAttribute(encoder_attn_tc_pipe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   MG_CUDA_OK(cudaFuncSetAttribute(sample_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   MG_CUDA_OK(cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return MG_OK;
