@@ -75,6 +75,9 @@ enum { BAR_COMPUTE = 1, BAR_STAGE_FREE = 8 };
 // per-layer parameter block kept in shared memory for the whole generation (floats):
 //   ln1w 256 | ln1b 256 | ln2w 256 | ln2b 256 | b_q 64 | b_k 64 | b_v 64 | b_out 256 | b1 slice 256 | b2 256
 constexpr int kLayerParamFloats = 4 * 256 + 3 * 64 + 3 * 256;
+#ifndef MG_MEGA_KVSLOT
+#define MG_MEGA_KVSLOT 0
+#endif
 enum { P_LN1W = 0, P_LN1B = 256, P_LN2W = 512, P_LN2B = 768, P_BQKV = 1024, P_BOUT = 1216, P_B1 = 1472, P_B2 = 1728 };
 
 template <int SMAX, int NSTAGE>
@@ -96,7 +99,11 @@ struct Smem {
   static constexpr int kParams = kHist + SMAX * 1024;                // per-layer LN / bias slices (fp32)
   static constexpr int kMisc = kParams + kMegaMaxLayersSmem * kLayerParamFloats * 4;                  // small scalars
   static constexpr int kBars = kMisc + 512;
-  static constexpr int kTotal = kBars + 512;
+  // K/V staging slots (MG_MEGA_KVSLOT): one 4 KB slot per compute warp = one 32-key block of one head (K 2 KB | V^T 2 KB), filled by
+  // cp.async.bulk and tracked by an mbarrier -- a third block in flight per warp next to the two register sets
+  static constexpr int kKvSlot = kBars + 512;
+  static constexpr bool kHasKvSlot = MG_MEGA_KVSLOT && SMAX <= 2;    // no room next to the wider buffers of 3..4 sequences
+  static constexpr int kTotal = kKvSlot + (kHasKvSlot ? NCW * 4096 : 0);
 };
 
 struct MiscSmem {
@@ -126,6 +133,7 @@ struct Bars {
   uint64_t cand;
   uint64_t tok;
   uint64_t step_go;                   // compute warps -> producer: the next step will run (early-exit mode)
+  uint64_t kvslot[8];                 // per compute warp: "the block in my staging slot has landed" (MG_MEGA_KVSLOT)
 };
 
 __device__ __forceinline__ uint32_t float_key(float f) {
@@ -385,11 +393,24 @@ __device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, con
 
 // kq0 / vq0: block `wi` of this worker, loaded by the caller ahead of time (before the QKV GEMM, whose result the loads do not
 // depend on) when PRE is set.
+// One 32-key block of one head into this warp's staging slot: two bulk copies (K rows 2 KB, V^T block 2 KB) counted on the
+// warp's own mbarrier.  Lane 0 issues; callers make sure every lane has finished reading the slot (__syncwarp).
+template <int HD>
+__device__ __forceinline__ void kvslot_issue(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int b, int lane, uint8_t* slot,
+                                             uint64_t* bar) {
+  if (lane == 0) {
+    ptx::mbar_arrive_expect_tx(bar, 2 * 32 * HD * 2);
+    ptx::bulk_load_1d(slot, kh + static_cast<size_t>(b) * 32 * HD, 32 * HD * 2, bar);
+    ptx::bulk_load_1d(slot + 32 * HD * 2, vt + static_cast<size_t>(b) * (HD * 32), 32 * HD * 2, bar);
+  }
+}
+
 template <int HD, bool PRE>
 __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int wi, int nws,
                                         int lane, const float* __restrict__ q, const bf16* __restrict__ knew,
                                         const bf16* __restrict__ vnew, bool fold_new, float* __restrict__ out,
-                                        uint4 (&kq0)[4][HD / 32], uint4 (&vq0)[HD / 8]) {
+                                        uint4 (&kq0)[4][HD / 32], uint4 (&vq0)[HD / 8], uint8_t* slot = nullptr,
+                                        uint64_t* slot_bar = nullptr, uint32_t* slot_phase = nullptr, bool slot_issued = false) {
   constexpr int KS = HD / 16;              // k-steps of the score MMAs
   constexpr int NT = HD / 8;               // n-tiles (8 dims) of the output MMAs
   constexpr int KL = HD / 32;              // 16-byte K loads per lane per key row
@@ -469,7 +490,44 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
       mma_bf16_16816(oacc[n], a1, vq[n].z, vq[n].w);
     }
   };
-  if (HD == 32) {
+  if (HD == 32 && MG_MEGA_KVSLOT && slot != nullptr) {
+    // Three blocks in flight per warp: register sets A (kq0 / vq0) and B by 16-byte global loads, the staging slot S by bulk copy.
+    // Block k of this warp (wi + k nws) lives in storage k % 3; after a block is consumed its storage is refilled with block k + 3.
+    uint4 kqb[4][KL], vqb[NT];
+    int b = wi;
+    if (!PRE && b < nblk) load_block(b, kq0, vq0);
+    if (b + nws < nblk) load_block(b + nws, kqb, vqb);
+    if (!slot_issued && b + 2 * nws < nblk) kvslot_issue<HD>(kh, vt, b + 2 * nws, lane, slot, slot_bar);
+    uint32_t ph = *slot_phase;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t sa = ptx::smem_u32(slot) + g * 64 + t * 16;
+    while (b < nblk) {
+      compute_block(b, kq0, vq0);
+      if (b + 3 * nws < nblk) load_block(b + 3 * nws, kq0, vq0);
+      b += nws;
+      if (b >= nblk) break;
+      compute_block(b, kqb, vqb);
+      if (b + 3 * nws < nblk) load_block(b + 3 * nws, kqb, vqb);
+      b += nws;
+      if (b >= nblk) break;
+      {
+        uint4 kqc[4][KL], vqc[NT];
+        ptx::mbar_wait_spin(slot_bar, ph);
+        ph ^= 1u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(kqc[j][0].x), "=r"(kqc[j][0].y), "=r"(kqc[j][0].z), "=r"(kqc[j][0].w) : "r"(sa + j * 512));
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(vqc[n].x), "=r"(vqc[n].y), "=r"(vqc[n].z), "=r"(vqc[n].w) : "r"(sa + 2048 + n * 512));
+        __syncwarp();                                         // every lane holds its part: the slot may be refilled
+        if (b + 3 * nws < nblk) kvslot_issue<HD>(kh, vt, b + 3 * nws, lane, slot, slot_bar);
+        compute_block(b, kqc, vqc);
+        b += nws;
+      }
+    }
+    *slot_phase = ph;
+  } else if (HD == 32) {
     // MG_ATTN_BUFS register sets: the loads of the next block(s) are in flight while this one is computed (bytes in flight per
     // SM = warps x sets x 4 KB).  Measured on B200 (same box, config 3 / config 4): 2 sets 78.8 ms / 80.7 us per step, 3 sets
     // 83.9 / 85.8, 4 sets 106.9 / 109.7 -- with more sets the loads of different sets end up on the same scoreboard and a
@@ -594,6 +652,7 @@ decode_mega_kernel(const MegaParams p) {
     ptx::mbar_init(&bars.xchg[1], 1);
     ptx::mbar_init(&bars.cand, 1);
     ptx::mbar_init(&bars.tok, 1);
+    for (int w = 0; w < 8; ++w) ptx::mbar_init(&bars.kvslot[w], 1);
     ptx::fence_mbar_init();
     for (int s = 0; s < 8; ++s) {
       const bool live = s < S;
@@ -819,6 +878,8 @@ decode_mega_kernel(const MegaParams p) {
         ptx::mbar_arrive_expect_tx(&bars.xchg[1], (CL - 1) * D * SMAX * 4);
       }
       uint32_t cand_use = 0, tok_use = 0;
+      uint8_t* const kvs_slot = smem + L::kKvSlot + cw * 4096;     // this warp's K/V staging slot (MG_MEGA_KVSLOT)
+      uint32_t kvs_phase = 0;
 
       for (int step = 0; step < n_steps; ++step) {
         // ---- embedding + LayerNorm 1 of the first block ----
@@ -846,6 +907,12 @@ decode_mega_kernel(const MegaParams p) {
           const bf16* at_kh = kbase + at_s * kv_seq + static_cast<size_t>(at_h) * p.Tvt * hd;
           const bf16* at_vt = vbase + at_s * vt_seq + static_cast<size_t>(at_h) * p.Tvt * hd;
           if (kAttnPre && (att_wi << 5) < at_len) attn_load_block<HD>(at_kh, at_vt, at_len, att_wi, lane, kq0, vq0);
+          // third block of this warp: into its staging slot by bulk copy, also ahead of the QKV GEMM
+          bool kvs_issued = false;
+          if (L::kHasKvSlot && HD == 32 && kAttnPre && ((att_wi + 2 * att_nws) << 5) < at_len) {
+            kvslot_issue<HD>(at_kh, at_vt, att_wi + 2 * att_nws, lane, kvs_slot, &bars.kvslot[cw]);
+            kvs_issued = true;
+          }
           // ---- QKV (LN1 was applied by the previous epilogue): stage rows 0..63 = q, 64..127 = k, 128..191 = v slice ----
           if (cw < GW) {
             // biases ahead of the MMAs (no load behind a store in the epilogue): k / v tile 4 + cw, q tile cw / 2
@@ -895,7 +962,8 @@ decode_mega_kernel(const MegaParams p) {
             // warp cw is the att_wi-th worker of (sequence, head) pair att_pair
             const int s = at_s, h = at_h;
             attn_tc<HD, kAttnPre>(at_kh, at_vt, at_len, att_wi, att_nws, lane, qs + s * FS + h * HD, knew + s * FS + h * HD,
-                                  vnew + s * FS + h * HD, att_wi == 0, part + cw * 68, kq0, vq0);
+                                  vnew + s * FS + h * HD, att_wi == 0, part + cw * 68, kq0, vq0,
+                                  L::kHasKvSlot ? kvs_slot : nullptr, &bars.kvslot[cw], &kvs_phase, kvs_issued);
           }
           fst();                                                            // attention stream done (this warp)
           bar_compute();
