@@ -519,11 +519,10 @@ def continuous_batching(mg):
                 nxt += len(take)
             fin, _ = eng.slots_step(32)
             chunks += 1
-            for b in range(BATCH):
-                if fin[b] and slot_req[b] is not None:
-                    row = eng.slots_fetch(b, 1100)
-                    assert len(row) == len(prompts[slot_req[b]]) + budgets[slot_req[b]]
-                    slot_req[b], done = None, done + 1
+            fin_slots = [b for b in range(BATCH) if fin[b] and slot_req[b] is not None]
+            for b, row in zip(fin_slots, eng.slots_fetch_many(fin_slots, as_arrays=True)):
+                assert len(row) == len(prompts[slot_req[b]]) + budgets[slot_req[b]]
+                slot_req[b], done = None, done + 1
         eng.slots_end()
         t_cont = time.perf_counter() - t0
     out.update({"static_batches_tokens_per_s": total_new / t_static, "continuous_tokens_per_s": total_new / t_cont,

@@ -163,6 +163,9 @@ int mg_slots_admit(mg_engine* e, int n, const int32_t* slots, const int32_t* pro
                    const int32_t* max_new, const int32_t* seq_index);
 int mg_slots_step(mg_engine* e, int n_steps, uint8_t* finished, int32_t* out_len);
 int mg_slots_fetch(mg_engine* e, int slot, int32_t* out_ids, int cap, int* n);
+/* the rows of n slots in one go (out_ids [n][out_stride], out_stride >= the session's row stride = max_len rounded up to 8;
+ * out_lens[j] = tokens of slots[j]): ONE synchronisation for all of them */
+int mg_slots_fetch_many(mg_engine* e, int n, const int32_t* slots, int32_t* out_ids, int out_stride, int32_t* out_lens);
 int mg_slots_end(mg_engine* e);
 
 /* Device-side detokenisation to note events: replaces the per-token regex / float() / pretty_midi look-ups of the reference's

@@ -248,9 +248,12 @@ class ContinuousBatcher:
             try:
                 fin, _ = self.engine.slots_step(self.chunk)
                 self.chunks += 1
-                for b in range(self.n_slots):
-                    if fin[b] and self._slot_req[b] is not None:
-                        self._slot_req[b].set_result(self.engine.slots_fetch(b, self.max_len + 8))
+                done = [b for b in range(self.n_slots) if fin[b] and self._slot_req[b] is not None]
+                if done:
+                    fetch_many = getattr(self.engine, "slots_fetch_many", None)
+                    rows = fetch_many(done) if fetch_many else [self.engine.slots_fetch(b, self.max_len + 8) for b in done]
+                    for b, row in zip(done, rows):
+                        self._slot_req[b].set_result(row)
                         self._slot_req[b] = None
             except Exception as e:                               # noqa: BLE001 -- device failure: nothing in flight survives
                 for b in range(self.n_slots):

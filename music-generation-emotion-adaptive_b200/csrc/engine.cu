@@ -95,6 +95,8 @@ struct mg_engine {
   int32_t* d_slot_last_rows = nullptr;
   int32_t* d_slot_out = nullptr;        // out_len [n] | out_ids [n][stride]
   int32_t* h_slot_flags = nullptr;      // pinned: finished [n] (bytes, padded) | out_len [n]
+  int32_t* h_slot_rows = nullptr;       // pinned staging for mg_slots_fetch_many: [n][stride]
+  size_t slot_rows_cap = 0;
   size_t slot_state_cap = 0, slot_out_cap = 0;
   std::vector<uint8_t> slot_busy;       // host mirror: admitted and not yet reported finished
   int4* d_note_table = nullptr;         // device-side detokenisation: one record per vocabulary entry (detok.cu)
@@ -1027,6 +1029,9 @@ void mg_engine_destroy(mg_engine* e) {
   if (e->h_sp) cudaFreeHost(e->h_sp);
   if (e->h_active) cudaFreeHost(e->h_active);
   if (e->h_flow_status) cudaFreeHost(e->h_flow_status);
+  if (e->h_slot_flags) cudaFreeHost(e->h_slot_flags);
+  if (e->h_slot_rows) cudaFreeHost(e->h_slot_rows);
+  if (e->h_detok) cudaFreeHost(e->h_detok);
   delete e->flow_plan;
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1385,6 +1390,11 @@ int mg_slots_begin(mg_engine* e, int n_slots, int max_len, float temperature, in
     MG_TRY(e->dmalloc(&e->d_slot_out, out_ints * sizeof(int32_t)));
     e->slot_out_cap = out_ints;
   }
+  if (out_ints > e->slot_rows_cap) {
+    if (e->h_slot_rows) { cudaFreeHost(e->h_slot_rows); e->h_slot_rows = nullptr; }
+    MG_CUDA_OK(cudaMallocHost(&e->h_slot_rows, out_ints * sizeof(int32_t)));
+    e->slot_rows_cap = out_ints;
+  }
   int32_t* d = e->d_slot_state;
   MG_CUDA_OK(cudaMemsetAsync(d, 0, state_ints * sizeof(int32_t), e->stream));
   MG_CUDA_OK(cudaMemsetAsync(d + 5 * n_slots, 1, n_slots, e->stream));                 // every slot starts idle (finished)
@@ -1529,6 +1539,32 @@ int mg_slots_fetch(mg_engine* e, int slot, int32_t* out_ids, int cap, int* n_out
   MG_CUDA_OK(cudaStreamSynchronize(e->stream));
   e->d2h += sizeof(int32_t) * (len + 1);
   *n_out = len;
+  return MG_OK;
+}
+
+int mg_slots_fetch_many(mg_engine* e, int n, const int32_t* slots, int32_t* out_ids, int out_stride, int32_t* out_lens) {
+  if (!e || !slots || !out_ids || !out_lens) return fail(MG_E_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  MG_CUDA_OK(cudaSetDevice(e->device));
+  if (!e->slots_active) return fail(MG_E_STATE, "no slot session (mg_slots_begin)");
+  if (n <= 0) return MG_OK;
+  const int stride = e->st.out_stride;
+  if (out_stride < stride) return fail(MG_E_ARG, "out_stride smaller than the session's row stride");
+  for (int j = 0; j < n; ++j)
+    if (slots[j] < 0 || slots[j] >= e->n_slots) return fail(MG_E_ARG, "slot index outside the session");
+  // whole rows (stride ints each) + the lengths of all slots, then ONE synchronisation
+  if (n > e->n_slots) return fail(MG_E_ARG, "more rows than slots");
+  for (int j = 0; j < n; ++j)
+    MG_CUDA_OK(cudaMemcpyAsync(e->h_slot_rows + static_cast<size_t>(j) * stride, e->st.out_ids + static_cast<size_t>(slots[j]) * stride,
+                               sizeof(int32_t) * stride, cudaMemcpyDeviceToHost, e->stream));
+  const int fin_ints = (e->n_slots + 3) / 4;
+  MG_CUDA_OK(cudaMemcpyAsync(e->h_slot_flags + fin_ints, e->st.out_len, e->n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  for (int j = 0; j < n; ++j) {
+    out_lens[j] = e->h_slot_flags[fin_ints + slots[j]];
+    std::memcpy(out_ids + static_cast<size_t>(j) * out_stride, e->h_slot_rows + static_cast<size_t>(j) * stride, sizeof(int32_t) * stride);
+  }
+  e->d2h += sizeof(int32_t) * (static_cast<size_t>(n) * stride + e->n_slots);
   return MG_OK;
 }
 

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "mg_abi_version", "mg_last_error", "mg_device_count", "mg_engine_create", "mg_engine_destroy", "mg_load_weight",
     "mg_engine_finalize", "mg_generate", "mg_upload_prompts", "mg_run", "mg_download", "mg_synchronize",
     "mg_engine_stream", "mg_step_logits", "mg_step_logits_at", "mg_generate_nocache", "mg_forward_nocache", "mg_sample_logits",
-    "mg_engine_stats", "mg_slots_begin", "mg_slots_admit", "mg_slots_step", "mg_slots_fetch", "mg_slots_end", "mg_set_note_table", "mg_note_events", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
+    "mg_engine_stats", "mg_slots_begin", "mg_slots_admit", "mg_slots_step", "mg_slots_fetch", "mg_slots_fetch_many", "mg_slots_end", "mg_set_note_table", "mg_note_events", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
     "mg_bert_finalize", "mg_classify", "mg_bert_upload", "mg_bert_run", "mg_bert_download", "mg_bert_synchronize",
     "mg_bert_stream", "mg_bert_stats", "mg_test_gemm_bf16",
 ]
@@ -97,6 +97,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mg_slots_admit": (c.c_int, [vp, c.c_int, i32p, i32p, i32p, i32p, i32p]),
         "mg_slots_step": (c.c_int, [vp, c.c_int, u8p, i32p]),
         "mg_slots_fetch": (c.c_int, [vp, c.c_int, i32p, c.c_int, c.POINTER(c.c_int)]),
+        "mg_slots_fetch_many": (c.c_int, [vp, c.c_int, i32p, i32p, c.c_int, i32p]),
         "mg_slots_end": (c.c_int, [vp]),
         "mg_set_note_table": (c.c_int, [vp, i32p, i32p, f32p, f32p, c.c_int]),
         "mg_note_events": (c.c_int, [vp, c.c_int, c.c_int, i32p, i32p, i32p, i32p, i32p, i32p, f32p, f32p]),
@@ -357,6 +358,7 @@ class Generator:
     def slots_begin(self, n_slots: int, max_len: int, temperature: float = 1.0, top_k: Optional[int] = 50, eos_id: int = -1,
                     seed: Optional[int] = None) -> None:
         self._n_slots = int(n_slots)
+        self._slots_max_len = int(max_len)
         _check(self.lib, self.lib.mg_slots_begin(self._h, int(n_slots), int(max_len), float(temperature),
                                                  0 if top_k is None else int(top_k), int(eos_id), _seed(seed)))
 
@@ -380,6 +382,17 @@ class Generator:
         buf, n = np.zeros(cap, np.int32), ctypes.c_int()
         _check(self.lib, self.lib.mg_slots_fetch(self._h, int(slot), _ptr(buf, ctypes.c_int32), cap, ctypes.byref(n)))
         return buf[:n.value].tolist()
+
+    def slots_fetch_many(self, slots: Sequence[int], as_arrays: bool = False):
+        """Token rows of several finished slots with one synchronisation."""
+        sl = _i32(slots)
+        if len(sl) == 0:
+            return []
+        stride = (int(self._slots_max_len) + 7) & ~7
+        buf, lens = np.zeros((len(sl), stride), np.int32), np.zeros(len(sl), np.int32)
+        _check(self.lib, self.lib.mg_slots_fetch_many(self._h, len(sl), _ptr(sl, ctypes.c_int32), _ptr(buf, ctypes.c_int32), stride,
+                                                      _ptr(lens, ctypes.c_int32)))
+        return [buf[j, :lens[j]] if as_arrays else buf[j, :lens[j]].tolist() for j in range(len(sl))]
 
     def slots_end(self) -> None:
         _check(self.lib, self.lib.mg_slots_end(self._h))

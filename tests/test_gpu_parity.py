@@ -754,7 +754,8 @@ def test_slot_session_persistent_kernel_late_admission_does_not_change_a_request
     for _ in range(6):
         fin, ln = e.slots_step(8)
     assert fin.all()
-    d = [e.slots_fetch(b) for b in range(64)]
+    d = e.slots_fetch_many(list(range(64)))
+    assert d[7] == e.slots_fetch(7)
     e.slots_end()
     c = e.generate(prompts, 48, 1.0, 40, seed=77, seq_index_base=1000)
     assert c == d
