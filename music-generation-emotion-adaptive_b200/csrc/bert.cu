@@ -63,6 +63,7 @@ struct mg_bert {
 
   int32_t* d_arena = nullptr;          // ids[M] pos[M] seq_start[N] seq_len[N] cls_rows[N] mask[M bytes]
   int32_t* h_arena = nullptr;          // pinned
+  cudaEvent_t ev_staged = nullptr;     // behind the H2D copy out of h_arena: waited for before the buffer is rewritten
   size_t arena_ints = 0;
   int32_t *d_ids = nullptr, *d_pos = nullptr, *d_seq_start = nullptr, *d_seq_len = nullptr, *d_cls_rows = nullptr;
   uint8_t* d_mask = nullptr;
@@ -210,6 +211,7 @@ int bert_upload_impl(mg_bert* b, const int32_t* ids, const uint8_t* mask, int N,
   for (size_t i = 0; i < M; ++i)
     if (ids[i] < 0 || ids[i] >= b->geo.vocab_size) return fail(MG_E_TOKEN, "token id outside [0, vocab)");
   int32_t* h = b->h_arena;
+  if (b->ev_staged) MG_CUDA_OK(cudaEventSynchronize(b->ev_staged));   // an earlier asynchronous upload may still be reading it
   int32_t* h_ids = h;
   int32_t* h_pos = h_ids + M;
   int32_t* h_ss = h_pos + M;
@@ -227,6 +229,8 @@ int bert_upload_impl(mg_bert* b, const int32_t* ids, const uint8_t* mask, int N,
   else std::memset(h_mask, 1, M);
   const size_t bytes = (2 * M + 3 * static_cast<size_t>(N)) * sizeof(int32_t) + M;
   MG_CUDA_OK(cudaMemcpyAsync(b->d_arena, h, bytes, cudaMemcpyHostToDevice, b->stream));
+  if (!b->ev_staged) MG_CUDA_OK(cudaEventCreateWithFlags(&b->ev_staged, cudaEventDisableTiming));
+  MG_CUDA_OK(cudaEventRecord(b->ev_staged, b->stream));
   b->h2d += bytes;
   b->d_ids = b->d_arena;
   b->d_pos = b->d_ids + M;
@@ -358,6 +362,7 @@ void mg_bert_destroy(mg_bert* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : b->allocs) cudaFree(p);
   if (b->h_arena) cudaFreeHost(b->h_arena);
+  if (b->ev_staged) cudaEventDestroy(b->ev_staged);
   if (b->h_logits) cudaFreeHost(b->h_logits);
   for (auto& ev : b->ev) if (ev) cudaEventDestroy(ev);
   if (b->stream) cudaStreamDestroy(b->stream);

@@ -83,6 +83,7 @@ struct mg_engine {
   // per-call device arena (int32): prompts + row maps + decode state
   int32_t* d_arena = nullptr;
   int32_t* h_arena = nullptr;          // pinned
+  cudaEvent_t ev_staged = nullptr;     // recorded behind every H2D copy out of h_arena / h_sp: waited for before they are rewritten
   size_t arena_cap = 0;
   int32_t *d_prompt = nullptr, *d_offsets = nullptr, *d_row_seq = nullptr, *d_row_pos = nullptr, *d_seq_start = nullptr,
           *d_seq_len = nullptr, *d_last_rows = nullptr;
@@ -352,8 +353,10 @@ int run_decode_loop(mg_engine* e, int eos_id) {
 
 template <typename T>
 int run_impl(mg_engine* e, float temperature, int top_k, int eos_id, uint64_t seed, uint64_t seq_base) {
+  MG_CUDA_OK(cudaEventSynchronize(e->ev_staged));           // the previous run's copy out of h_sp (and any upload) has been consumed
   *e->h_sp = SampleParams{temperature, top_k, eos_id, 0, seed, seq_base};
   MG_CUDA_OK(cudaMemcpyAsync(e->d_sp, e->h_sp, sizeof(SampleParams), cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaEventRecord(e->ev_staged, e->stream));
   MG_CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
   MG_TRY(prefill<T>(e));
   MG_CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
@@ -792,6 +795,7 @@ int upload_impl(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, in
   MG_TRY(ensure_arena(e, all_ints));
   MG_TRY(ensure_out(e, static_cast<size_t>(B) * (stride + 1)));
   int32_t* h = e->h_arena;
+  MG_CUDA_OK(cudaEventSynchronize(e->ev_staged));           // an earlier asynchronous upload may still be reading the staging buffer
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += n; return r; };
   const size_t o_prompt = take(M), o_offs = take(B + 1), o_rseq = take(M), o_rpos = take(M), o_sstart = take(B),
@@ -810,6 +814,7 @@ int upload_impl(mg_engine* e, const int32_t* ids, const int32_t* offs, int B, in
     h[o_last + b] = b;
   }
   MG_CUDA_OK(cudaMemcpyAsync(e->d_arena, h, up_ints * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaEventRecord(e->ev_staged, e->stream));
   e->h2d += up_ints * sizeof(int32_t);
   int32_t* da = e->d_arena;
   e->d_prompt = da + o_prompt; e->d_offsets = da + o_offs; e->d_row_seq = da + o_rseq; e->d_row_pos = da + o_rpos;
@@ -967,6 +972,7 @@ int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max
   auto body = [&]() -> int {
     MG_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto& ev : e->ev) MG_CUDA_OK(cudaEventCreate(&ev));
+    MG_CUDA_OK(cudaEventCreateWithFlags(&e->ev_staged, cudaEventDisableTiming));
     MG_TRY(kernels_init());
     if (e->use_tc) MG_TRY(gemm_tc_init());
     const size_t d = g.d_model, f = g.d_ff, V = g.vocab_size;
@@ -1034,6 +1040,7 @@ void mg_engine_destroy(mg_engine* e) {
   if (e->h_detok) cudaFreeHost(e->h_detok);
   delete e->flow_plan;
   for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->ev_staged) cudaEventDestroy(e->ev_staged);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1467,7 +1474,7 @@ int mg_slots_admit(mg_engine* e, int n, const int32_t* slots, const int32_t* ids
   auto take = [&](size_t k) { size_t r = o; o += k; return r; };
   const size_t o_prompt = take(M), o_offs = take(n + 1), o_rseq = take(M), o_rpos = take(M), o_sstart = take(n), o_slen = take(n),
                o_slots = take(n), o_maxnew = take(n), o_sidx = take(n);
-  MG_CUDA_OK(cudaStreamSynchronize(e->stream));                     // the staging buffer may still feed the previous admission
+  MG_CUDA_OK(cudaEventSynchronize(e->ev_staged));                   // the staging buffer may still feed the previous admission
   std::memcpy(h + o_prompt, ids, sizeof(int32_t) * M);
   std::memcpy(h + o_offs, offs, sizeof(int32_t) * (n + 1));
   for (int j = 0; j < n; ++j) {
@@ -1476,6 +1483,7 @@ int mg_slots_admit(mg_engine* e, int n, const int32_t* slots, const int32_t* ids
     h[o_sstart + j] = offs[j]; h[o_slen + j] = tp; h[o_slots + j] = slots[j]; h[o_maxnew + j] = max_new[j]; h[o_sidx + j] = seq_index[j];
   }
   MG_CUDA_OK(cudaMemcpyAsync(e->d_arena, h, ints * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  MG_CUDA_OK(cudaEventRecord(e->ev_staged, e->stream));
   e->h2d += ints * sizeof(int32_t);
   int32_t* da = e->d_arena;
   e->d_prompt = da + o_prompt; e->d_offsets = da + o_offs; e->d_row_seq = da + o_rseq; e->d_row_pos = da + o_rpos;

@@ -783,3 +783,26 @@ def test_continuous_batcher_serves_a_request_stream():
         assert r == gpt_kv.sample_ids(ora, p, max_len=len(p) + n, temperature=1.0, top_k=1)
     assert len(cb.admissions) > 3 and sum(n for _, n in cb.admissions) == 21       # admitted over several chunks, not as one batch
     e.close()
+
+
+def test_back_to_back_asynchronous_uploads_do_not_corrupt_the_staging_buffers():
+    """mg_upload_prompts / mg_run are asynchronous; a second upload (or run) issued before the first one's H2D copy
+    has been consumed must wait for it instead of overwriting the pinned staging buffer."""
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    p1 = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 64, seed=21)]
+    p2 = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 64, seed=22)]
+    e = engine("train_large", 0, "bf16", max_batch=64, max_seq=1088)
+    want1 = e.generate(p1, 24, 1.0, 40, seed=3)
+    want2 = e.generate(p2, 24, 1.0, 40, seed=4)
+    for _ in range(5):
+        e.upload(p1, 24)
+        e.run(1.0, 40, eos_id=-1, seed=3)
+        e.upload(p2, 24)                       # no synchronize in between: the first job may still be running
+        e.run(1.0, 40, eos_id=-1, seed=4)
+        e.synchronize()
+        assert e.download() == want2
+    e.upload(p1, 24)
+    e.run(1.0, 40, eos_id=-1, seed=3)
+    e.synchronize()
+    assert e.download() == want1
