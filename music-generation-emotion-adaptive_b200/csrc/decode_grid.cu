@@ -1,0 +1,863 @@
+// Grid-synchronous persistent decode kernel for sm_100a: the whole generation loop of reference api_cache.py:159-184
+// (embedding -> L x [LN1, in_proj, attention over the cache, out_proj, +x, LN2, mlp.0, GELU, mlp.2, +x] -> head -> /T ->
+// top-k -> softmax -> multinomial -> EOS) in ONE cooperative launch over all SMs, for up to 64 sequences that move through
+// the step in lock-step.
+//
+// Decomposition (the opposite of decode_mega.cu, where a 4-CTA cluster owns a few sequences and streams all weights):
+//   * the batch is the N dimension of every contraction (8 sequences = one n8 tile of mma.sync.m16n8k16 = one warp), a
+//     work item is 16 rows of one weight matrix, so every weight byte is read ONCE per step by ONE SM -- straight from
+//     L1 / L2 into A fragments (fragment-major packing, ld.global.nc: the per-SM weight set of a step is ~100 KB for the
+//     train_large geometry and stays L1-resident from step to step);
+//   * a step is 5 L + 2 phases separated by a grid barrier (one counter, release by one thread per CTA behind a
+//     __syncthreads, polled by one lane per warp); activations between phases live in L2 and are read with L1-bypassing
+//     loads; LayerNorm is applied by the consumer while it builds its B fragments (no LayerNorm phase), the residual adds sit
+//     in the out_proj / mlp.2 epilogues, the embedding is recomputed where it is needed;
+//   * attention: the (sequence, head, key range) units of a step are dealt evenly over ALL warps of ALL SMs by total K/V
+//     bytes (balanced partition recomputed every step from the cache lengths), each unit is the warp-level tensor-core
+//     flash-decoding of attn_tc.cuh; partial results are merged by the out_proj consumers while they load their operand;
+//   * sampling: one CTA per sequence, logits in registers, threshold from the per-thread maxima, exact ranking of the
+//     (small) candidate superset, Philox draw; general path = sampler.cuh on a global scratch row.
+// Any d_model in {256, 512} with d_ff = 4 d_model and head_dim 32 / 64 (the paper's train_large2 geometry included), any
+// cache length (config 4 uses all SMs), B <= 64.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
+#include "attn_tc.cuh"
+#include "decode_grid.cuh"
+#include "mg_engine.h"
+#include "ptx.cuh"
+#include "sampler.cuh"
+
+namespace mg {
+namespace grid {
+
+namespace {
+
+using namespace attn;
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kCandCap = 1024;         // candidate superset capacity of the sampler's fast path
+constexpr unsigned long long kWatchdogNs = 2000000000ull;   // a barrier that is not reached within 2 s aborts the launch
+
+// ---- L1-bypassing loads of data other SMs rewrite during the launch (ld.volatile: the fastest flavour measured, mb9) ----
+__device__ __forceinline__ uint4 ldv4u(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float4 ldv4f(const float* p) {
+  float4 r;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float2 ldv2f(const float* p) {
+  float2 r;
+  asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float ldvf(const float* p) {
+  float r;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ int ldvi(const int32_t* p) {
+  int r;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ unsigned ldvu(const unsigned* p) {
+  unsigned r;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ int ldvb(const uint8_t* p) {
+  unsigned r;
+  asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return static_cast<int>(r);
+}
+// weights: immutable for the whole launch, read-only path, allocate in L1
+__device__ __forceinline__ uint4 ldw16(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+struct GridSmem {
+  float4 red[8][32];                   // k-split partial accumulators [warp][lane]
+  float qs[8][64];                     // per-warp attention scratch: query (fp32, log2-scaled), new K / V rows, partial result
+  bf16 kn[8][64];
+  bf16 vn[8][64];
+  float part[8][68];
+  int nws[kMaxSeqs];                   // attention workers per (sequence, head) in this step (0: finished)
+  int istart[kMaxSeqs];                // first attention unit of the sequence
+  int len[kMaxSeqs];
+  int fin[kMaxSeqs];
+  int tok[kMaxSeqs];
+  int total_units;
+  // sampler
+  float mx[kThreads];
+  uint2 cand[kCandCap];
+  uint2 sorted[kThreads];
+  int wtot[8];
+  float tau;
+  int flag;
+  int result;
+  SampleSmem ss;
+  GridItem items[kMaxItems];
+};
+
+// Tile layout (grid_pack_kernel): a tile = 16 rows x K of a matrix; per pair of k-steps j (32 columns) two 512-byte blocks, block
+// e = the A fragments of MMA 2 j + e in lane order: lane (g, t) holds {W[g][c], W[g + 8][c], W[g][c + 2], W[g + 8][c + 2]} (bf16
+// pairs), c = 32 j + 8 t + 4 e.  The B fragments use the same permutation of the contraction index: lane (g, t) of sequence g
+// holds columns 32 j + 8 t .. + 7 as ONE 16-byte load, (x, y) feed MMA 2 j, (z, w) MMA 2 j + 1.
+template <int NP>
+__device__ __forceinline__ void mma_tile(const uint8_t* __restrict__ tile, int lane, const uint4 (&bq)[NP], int np, float (&acc)[4]) {
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint8_t* tp = tile + lane * 16;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    if (j < np) {
+      const uint4 w0 = ldw16(tp + j * 1024), w1 = ldw16(tp + j * 1024 + 512);
+      mma16816(a0, w0, bq[j].x, bq[j].y);
+      mma16816(a1, w1, bq[j].z, bq[j].w);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[e] = a0[e] + a1[e];
+}
+
+__device__ __forceinline__ uint32_t pk(float a, float b) { return pack_bf16(a, b); }
+
+template <int DM, int HD>
+__global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridParams p) {
+  constexpr int NPD = DM / 32;           // k-step pairs across d_model
+  constexpr int DFF = 4 * DM;
+  constexpr int PS = HD + 4;             // floats per attention partial
+  __shared__ GridSmem sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, qd = lane >> 2, tq = lane & 3;
+  const int cta = blockIdx.x, n_cta = p.n_cta, B = p.B, H = p.H, L = p.L;
+  const int n_items = p.n_items[cta];
+  for (int i = tid; i < n_items; i += kThreads) sm.items[i] = p.items[static_cast<size_t>(cta) * kMaxItems + i];
+  const SampleParams sp = *p.sp;
+  const float scale_log2 = kLog2e / sqrtf(static_cast<float>(HD));
+  const int n_active0 = __syncthreads_count(tid < B && p.st.finished[tid] == 0);
+  unsigned* const bar = p.ctrl;
+  unsigned bar_target = 0;
+  bool alive = true;
+
+  // ---- grid barrier: arrive (release by one thread behind the CTA barrier) / wait (one polling lane per warp) ----
+  auto arrive = [&]() {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(bar, 1u);
+    }
+    bar_target += static_cast<unsigned>(n_cta);
+  };
+  auto wait = [&]() {
+    int ok = 1;
+    if (lane == 0) {
+      unsigned spins = 0;
+      unsigned long long t0 = 0;
+      while (ldvu(bar) < bar_target) {
+        if ((++spins & 0xfffu) == 0) {
+          const unsigned long long now = ptx::global_timer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > kWatchdogNs || ldvu(p.ctrl + 2) != 0) { ok = 0; atomicExch(p.ctrl + 2, 1u); break; }
+        }
+      }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) alive = false;
+  };
+  const bool prof_on = p.prof != nullptr && cta == 0 && tid == 0;
+  int prof_i = 0;
+
+  const int s_own = 8 * warp + qd;                        // sequence of this lane's B fragments when a warp owns n-tile `warp`
+  const int sa = 8 * warp + 2 * tq, sb = sa + 1;          // sequences of this lane's accumulators (same n-tile)
+
+  for (int step = 0; step < p.n_steps && alive; ++step) {
+    auto stamp = [&]() { if (prof_on && step == p.prof_step) p.prof[prof_i++] = ptx::global_timer_ns(); };
+    // ---------------- per-step state + attention partition ----------------
+    if (tid < kMaxSeqs) {
+      const bool in = tid < B;
+      sm.len[tid] = in ? ldvi(p.st.lens + tid) : 0;
+      sm.fin[tid] = in ? ldvb(p.st.finished + tid) : 1;
+      sm.tok[tid] = in ? ldvi(p.st.cur_tok + tid) : 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int nb0 = sm.fin[lane] ? 0 : (sm.len[lane] + 31) >> 5, nb1 = sm.fin[lane + 32] ? 0 : (sm.len[lane + 32] + 31) >> 5;
+      const bool act0 = !sm.fin[lane], act1 = !sm.fin[lane + 32];
+      int tb = nb0 + nb1, mxb = max(nb0, nb1);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        tb += __shfl_xor_sync(0xffffffffu, tb, o);
+        mxb = max(mxb, __shfl_xor_sync(0xffffffffu, mxb, o));
+      }
+      const int NW = n_cta * 8;
+      int c = max(1, max((tb * H + NW - 1) / NW, (mxb + kMaxSplits - 1) / kMaxSplits));
+      int w0 = 0, w1 = 0, tot = 0;
+      for (;; ++c) {
+        w0 = act0 ? max(1, (nb0 + c - 1) / c) : 0;
+        w1 = act1 ? max(1, (nb1 + c - 1) / c) : 0;
+        tot = w0 + w1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (tot * H <= NW || c > 4096) break;
+      }
+      int i0 = w0 * H, i1 = w1 * H;                       // inclusive scans over the lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += t0; i1 += t1; }
+      }
+      const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+      sm.nws[lane] = w0; sm.nws[lane + 32] = w1;
+      sm.istart[lane] = i0 - w0 * H; sm.istart[lane + 32] = tot0 + i1 - w1 * H;
+      if (lane == 0) sm.total_units = tot * H;
+    }
+    __syncthreads();
+    // this warp's attention unit of the step (the same for every layer)
+    int at_b = -1, at_h = 0, at_wi = 0, at_nws = 1, at_len = 0;
+    {
+      const int gw = warp * n_cta + cta;
+      if (gw < sm.total_units) {
+        const bool in0 = sm.nws[lane] > 0 && sm.istart[lane] <= gw && gw < sm.istart[lane] + sm.nws[lane] * H;
+        const bool in1 = sm.nws[lane + 32] > 0 && sm.istart[lane + 32] <= gw && gw < sm.istart[lane + 32] + sm.nws[lane + 32] * H;
+        const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+        at_b = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : -1);
+        if (at_b >= 0) {
+          const int r = gw - sm.istart[at_b];
+          at_nws = sm.nws[at_b];
+          at_h = r % H;
+          at_wi = r / H;
+          at_len = sm.len[at_b];
+        }
+      }
+    }
+    stamp();
+    int it = 0;
+    const int dslot = !p.dbg_logits ? -1 : (p.dbg_slot ? p.dbg_slot[step] : step);
+
+    // ---------------- dense phases whose operand is a whole (LayerNorm-ed) residual row: in_proj, mlp.0, head ----------------
+    auto phase_rows = [&](int ph, int kind, int l) {
+      if (!(it < n_items && sm.items[it].phase == ph)) return;
+      const bool wactive = 8 * warp < B;
+      uint4 bq[NPD];
+      if (wactive) {
+        const int sq = min(s_own, B - 1);
+        float v[NPD * 8];
+        const float* src = kind == K_MLP1 ? p.x1 : ((kind == K_QKV && l == 0) ? nullptr : p.x);
+        if (src) {
+          const float* row = src + static_cast<size_t>(sq) * DM + 8 * tq;
+#pragma unroll
+          for (int j = 0; j < NPD; ++j) {
+            const float4 a = ldv4f(row + 32 * j), b = ldv4f(row + 32 * j + 4);
+            v[8 * j] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = a.z; v[8 * j + 3] = a.w;
+            v[8 * j + 4] = b.x; v[8 * j + 5] = b.y; v[8 * j + 6] = b.z; v[8 * j + 7] = b.w;
+          }
+        } else {
+          // embedding x = tok_emb[tok] + pos_emb[0] (api_cache.py:99 with T == 1)
+          const bf16* te = p.tok_emb + static_cast<size_t>(sm.tok[sq]) * DM + 8 * tq;
+          const bf16* pe = p.pos_emb + 8 * tq;
+#pragma unroll
+          for (int j = 0; j < NPD; ++j) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(te + 32 * j)), b = __ldg(reinterpret_cast<const uint4*>(pe + 32 * j));
+            float fa[8], fb[8];
+            unpack8(a, fa);
+            unpack8(b, fb);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 * j + e] = fa[e] + fb[e];
+          }
+        }
+        if (kind != K_HEAD) {
+          const GridLayer& lw = p.layers[l];
+          const float* gw = kind == K_QKV ? lw.ln1w : lw.ln2w;
+          const float* gb = kind == K_QKV ? lw.ln1b : lw.ln2b;
+          float sum = 0.f;
+#pragma unroll
+          for (int e = 0; e < NPD * 8; ++e) sum += v[e];
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          const float mean = sum * (1.0f / DM);
+          float sq2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < NPD * 8; ++e) { const float d = v[e] - mean; sq2 = fmaf(d, d, sq2); }
+          sq2 += __shfl_xor_sync(0xffffffffu, sq2, 1);
+          sq2 += __shfl_xor_sync(0xffffffffu, sq2, 2);
+          const float rstd = rsqrtf(sq2 * (1.0f / DM) + 1e-5f);
+#pragma unroll
+          for (int j = 0; j < NPD; ++j) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(gw + 32 * j + 8 * tq)), w1 = __ldg(reinterpret_cast<const float4*>(gw + 32 * j + 8 * tq + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(gb + 32 * j + 8 * tq)), b1 = __ldg(reinterpret_cast<const float4*>(gb + 32 * j + 8 * tq + 4));
+            v[8 * j] = (v[8 * j] - mean) * rstd * w0.x + b0.x; v[8 * j + 1] = (v[8 * j + 1] - mean) * rstd * w0.y + b0.y;
+            v[8 * j + 2] = (v[8 * j + 2] - mean) * rstd * w0.z + b0.z; v[8 * j + 3] = (v[8 * j + 3] - mean) * rstd * w0.w + b0.w;
+            v[8 * j + 4] = (v[8 * j + 4] - mean) * rstd * w1.x + b1.x; v[8 * j + 5] = (v[8 * j + 5] - mean) * rstd * w1.y + b1.y;
+            v[8 * j + 6] = (v[8 * j + 6] - mean) * rstd * w1.z + b1.z; v[8 * j + 7] = (v[8 * j + 7] - mean) * rstd * w1.w + b1.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NPD; ++j)
+          bq[j] = make_uint4(pk(v[8 * j], v[8 * j + 1]), pk(v[8 * j + 2], v[8 * j + 3]), pk(v[8 * j + 4], v[8 * j + 5]), pk(v[8 * j + 6], v[8 * j + 7]));
+      }
+      while (it < n_items && sm.items[it].phase == ph) {
+        const int rt = sm.items[it].row_tile;
+        ++it;
+        if (!wactive) continue;
+        const int ra = 16 * rt + qd, rb = ra + 8;
+        float acc[4];
+        if (kind == K_QKV) {
+          const GridLayer& lw = p.layers[l];
+          const float ba = __ldg(lw.b_in + ra), bb = __ldg(lw.b_in + rb);
+          mma_tile<NPD>(p.packed + lw.w_in + static_cast<size_t>(rt) * (16 * DM * 2), lane, bq, NPD, acc);
+          const int part = ra / DM, fa = ra - part * DM, fb = fa + 8;        // a tile never straddles q | k | v
+          const float va[2] = {acc[0] + ba, acc[1] + ba}, vb[2] = {acc[2] + bb, acc[3] + bb};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int s = sa + e;
+            if (s >= B) continue;
+            if (part == 0) {
+              p.q[static_cast<size_t>(s) * DM + fa] = va[e] * scale_log2;
+              p.q[static_cast<size_t>(s) * DM + fb] = vb[e] * scale_log2;
+            } else {
+              const bf16 xa = __float2bfloat16_rn(va[e]), xb = __float2bfloat16_rn(vb[e]);
+              bf16* nw = part == 1 ? p.knew : p.vnew;
+              nw[static_cast<size_t>(s) * DM + fa] = xa;
+              nw[static_cast<size_t>(s) * DM + fb] = xb;
+              if (!sm.fin[s]) {                                         // append to the cache (api_cache.py:66-67)
+                const int key = sm.len[s], hh = fa / HD, d0 = fa - hh * HD, d1 = d0 + 8;   // both rows lie in the same head
+                const size_t hb = (static_cast<size_t>(s) * H + hh) * p.Tvt * HD;
+                if (part == 1) {
+                  lw.kh[hb + static_cast<size_t>(key) * HD + d0] = xa;
+                  lw.kh[hb + static_cast<size_t>(key) * HD + d1] = xb;
+                } else {
+                  const int ki = key & 31, pos = 8 * ((ki >> 1) & 3) + 2 * (ki >> 3) + (ki & 1);      // see attn_tc
+                  bf16* vb2 = lw.vt + hb + static_cast<size_t>(key >> 5) * (HD * 32) + pos;
+                  vb2[d0 * 32] = xa;
+                  vb2[d1 * 32] = xb;
+                }
+              }
+            }
+          }
+        } else if (kind == K_MLP1) {
+          const GridLayer& lw = p.layers[l];
+          const float ba = __ldg(lw.b1 + ra), bb = __ldg(lw.b1 + rb);
+          mma_tile<NPD>(p.packed + lw.w1 + static_cast<size_t>(rt) * (16 * DM * 2), lane, bq, NPD, acc);
+          if (sa < B) {
+            p.h[static_cast<size_t>(sa) * DFF + ra] = __float2bfloat16_rn(gelu_erf_f(acc[0] + ba));
+            p.h[static_cast<size_t>(sa) * DFF + rb] = __float2bfloat16_rn(gelu_erf_f(acc[2] + bb));
+          }
+          if (sb < B) {
+            p.h[static_cast<size_t>(sb) * DFF + ra] = __float2bfloat16_rn(gelu_erf_f(acc[1] + ba));
+            p.h[static_cast<size_t>(sb) * DFF + rb] = __float2bfloat16_rn(gelu_erf_f(acc[3] + bb));
+          }
+        } else {
+          const float ba = ra < p.V ? __ldg(p.head_b + ra) : 0.f, bb = rb < p.V ? __ldg(p.head_b + rb) : 0.f;
+          mma_tile<NPD>(p.packed + p.w_head + static_cast<size_t>(rt) * (16 * DM * 2), lane, bq, NPD, acc);
+          const float va[2] = {acc[0] + ba, acc[1] + ba}, vb[2] = {acc[2] + bb, acc[3] + bb};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int s = sa + e;
+            if (s >= B) continue;
+            if (ra < p.V) p.logits[static_cast<size_t>(s) * p.ldl + ra] = va[e];
+            if (rb < p.V) p.logits[static_cast<size_t>(s) * p.ldl + rb] = vb[e];
+            if (dslot >= 0) {
+              float* dl = p.dbg_logits + (static_cast<size_t>(dslot) * B + s) * p.V;
+              if (ra < p.V) dl[ra] = va[e];
+              if (rb < p.V) dl[rb] = vb[e];
+            }
+          }
+        }
+      }
+    };
+
+    // ---------------- dense phases with k-splits across the warps of a CTA: out_proj (operand = merged attention partials) and
+    //                  mlp.2 (operand = bf16 hidden activations); both add the residual stream in their epilogue ----------------
+    auto phase_split = [&](int ph, int kind, int l) {
+      const int TN = p.tn[kind], KS = p.ks[kind];
+      const int ntl = warp % TN, ksp = warp / TN;
+      const GridLayer& lw = p.layers[l];
+      while (it < n_items && sm.items[it].phase == ph) {
+        const int rt = sm.items[it].row_tile, ntile = sm.items[it].group * TN + ntl;
+        ++it;
+        const bool wactive = 8 * ntile < B;
+        const int sq = min(8 * ntile + qd, B - 1);
+        const int s0 = 8 * ntile + 2 * tq, s1 = s0 + 1;
+        const int ra = 16 * rt + qd, rb = ra + 8;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float res[4] = {0.f, 0.f, 0.f, 0.f}, ba = 0.f, bb = 0.f;
+        if (wactive && ksp == 0) {
+          // residual + bias of this lane's four outputs, requested ahead of the operand
+          const float* bias = kind == K_OUT ? lw.b_out : lw.b2;
+          ba = __ldg(bias + ra); bb = __ldg(bias + rb);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int s = min(s0 + e, B - 1);
+            if (kind == K_OUT && l == 0) {
+              const bf16* te = p.tok_emb + static_cast<size_t>(sm.tok[s]) * DM;
+              res[e] = __bfloat162float(te[ra]) + __bfloat162float(p.pos_emb[ra]);
+              res[2 + e] = __bfloat162float(te[rb]) + __bfloat162float(p.pos_emb[rb]);
+            } else {
+              const float* xr = (kind == K_OUT ? p.x : p.x1) + static_cast<size_t>(s) * DM;
+              res[e] = ldvf(xr + ra);
+              res[2 + e] = ldvf(xr + rb);
+            }
+          }
+        }
+        if (wactive) {
+          uint4 bq[16];
+          if (kind == K_MLP2) {
+            const int npw = (DFF / 32) / KS;
+            const bf16* hrow = p.h + static_cast<size_t>(sq) * DFF + ksp * npw * 32 + 8 * tq;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < npw) bq[j] = ldv4u(hrow + 32 * j);
+            mma_tile<16>(p.packed + lw.w2 + static_cast<size_t>(rt) * (16 * DFF * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
+          } else {
+            const int npw = NPD / KS;
+            const int nsp = sm.nws[sq];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < npw) {
+                const int fb0 = 32 * (ksp * npw + j), hh = fb0 / HD, fo = fb0 - hh * HD + 8 * tq;
+                const float* pb = p.part + (static_cast<size_t>(sq) * H + hh) * kMaxSplits * PS;
+                float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY, Ls = 0.f;
+                for (int s4 = 0; s4 < nsp; s4 += 4) {
+                  float2 ml[4];
+                  float4 oa[4], ob[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const bool on = s4 + u < nsp;
+                    const float* pp = pb + static_cast<size_t>(on ? s4 + u : s4) * PS;
+                    ml[u] = ldv2f(pp + HD);
+                    oa[u] = ldv4f(pp + fo);
+                    ob[u] = ldv4f(pp + fo + 4);
+                    if (!on) ml[u] = make_float2(-INFINITY, 0.f);
+                  }
+                  float Mn = M;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) Mn = fmaxf(Mn, ml[u].x);
+                  const float corr = fast_exp2(M - Mn);                    // M == -inf: exp2(-inf) = 0 (Mn is finite: worker 0 folds the new token)
+                  Ls *= corr;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] *= corr;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float w = fast_exp2(ml[u].x - Mn);
+                    Ls = fmaf(ml[u].y, w, Ls);
+                    o[0] = fmaf(oa[u].x, w, o[0]); o[1] = fmaf(oa[u].y, w, o[1]); o[2] = fmaf(oa[u].z, w, o[2]); o[3] = fmaf(oa[u].w, w, o[3]);
+                    o[4] = fmaf(ob[u].x, w, o[4]); o[5] = fmaf(ob[u].y, w, o[5]); o[6] = fmaf(ob[u].z, w, o[6]); o[7] = fmaf(ob[u].w, w, o[7]);
+                  }
+                  M = Mn;
+                }
+                const float inv = Ls > 0.f ? __fdividef(1.0f, Ls) : 0.f;
+                bq[j] = make_uint4(pk(o[0] * inv, o[1] * inv), pk(o[2] * inv, o[3] * inv), pk(o[4] * inv, o[5] * inv), pk(o[6] * inv, o[7] * inv));
+              }
+            }
+            mma_tile<16>(p.packed + lw.w_out + static_cast<size_t>(rt) * (16 * DM * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
+          }
+        }
+        if (KS > 1) {
+          sm.red[warp][lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          __syncthreads();
+          if (ksp == 0) {
+            for (int s = 1; s < KS; ++s) {
+              const float4 r = sm.red[s * TN + ntl][lane];
+              acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
+            }
+          }
+        }
+        if (wactive && ksp == 0) {
+          float* dst = kind == K_OUT ? p.x1 : p.x;
+          if (s0 < B) {
+            dst[static_cast<size_t>(s0) * DM + ra] = res[0] + (acc[0] + ba);
+            dst[static_cast<size_t>(s0) * DM + rb] = res[2] + (acc[2] + bb);
+          }
+          if (s1 < B) {
+            dst[static_cast<size_t>(s1) * DM + ra] = res[1] + (acc[1] + ba);
+            dst[static_cast<size_t>(s1) * DM + rb] = res[3] + (acc[3] + bb);
+          }
+        }
+        if (KS > 1 && it < n_items && sm.items[it].phase == ph) __syncthreads();     // `red` is reused by the next item
+      }
+    };
+
+    for (int l = 0; l < L && alive; ++l) {
+      const GridLayer& lw = p.layers[l];
+      phase_rows(5 * l + K_QKV, K_QKV, l);
+      arrive(); wait(); stamp();
+      if (!alive) break;
+      // ---------------- attention: this warp's (sequence, head, key range) unit ----------------
+      if (at_b >= 0) {
+        const size_t so = static_cast<size_t>(at_b) * DM + at_h * HD;
+        if (lane < HD / 4) *reinterpret_cast<float4*>(&sm.qs[warp][lane * 4]) = ldv4f(p.q + so + lane * 4);
+        if (lane < HD / 8) {
+          *reinterpret_cast<uint4*>(&sm.kn[warp][lane * 8]) = ldv4u(p.knew + so + lane * 8);
+          *reinterpret_cast<uint4*>(&sm.vn[warp][lane * 8]) = ldv4u(p.vnew + so + lane * 8);
+        }
+        __syncwarp();
+        const size_t hb = (static_cast<size_t>(at_b) * H + at_h) * p.Tvt * HD;
+        uint4 kq0[4][HD / 32], vq0[HD / 8];
+        attn_tc<HD, false>(lw.kh + hb, lw.vt + hb, at_len, at_wi, at_nws, lane, sm.qs[warp], sm.kn[warp], sm.vn[warp], at_wi == 0,
+                           sm.part[warp], kq0, vq0);
+        __syncwarp();
+        float* dst = p.part + ((static_cast<size_t>(at_b) * H + at_h) * kMaxSplits + at_wi) * PS;
+        if (lane < HD / 4) *reinterpret_cast<float4*>(dst + lane * 4) = *reinterpret_cast<const float4*>(&sm.part[warp][lane * 4]);
+        if (lane == 0) *reinterpret_cast<float2*>(dst + HD) = make_float2(sm.part[warp][64], sm.part[warp][65]);
+      }
+      arrive(); wait(); stamp();
+      if (!alive) break;
+      phase_split(5 * l + K_OUT, K_OUT, l);
+      arrive(); wait(); stamp();
+      if (!alive) break;
+      phase_rows(5 * l + K_MLP1, K_MLP1, l);
+      arrive(); wait(); stamp();
+      if (!alive) break;
+      phase_split(5 * l + K_MLP2, K_MLP2, l);
+      arrive(); wait(); stamp();
+    }
+    if (!alive) break;
+    phase_rows(5 * L + K_QKV, K_HEAD, 0);
+    arrive(); wait(); stamp();
+    if (!alive) break;
+
+    // ---------------- sampler (api_cache.py:169-181): CTA b owns sequence b ----------------
+    if (cta < B && !sm.fin[cta]) {
+      const int b = cta;
+      const float* row = p.logits + static_cast<size_t>(b) * p.ldl;
+      const int V = p.V, k = sp.top_k;
+      const uint64_t seq = sp.seq_base + static_cast<uint64_t>(p.st.seq_idx ? p.st.seq_idx[b] : b);
+      const uint32_t nn = static_cast<uint32_t>(ldvi(p.st.n_new + b));
+      int tok = -1;
+      const bool fast = V <= kThreads * kSampMaxPer && k >= 1 && k <= kThreads && k < V;
+      bool done = false;
+      if (p.forced) {
+        tok = p.forced[static_cast<size_t>(b) * p.forced_stride + step];
+        done = true;
+      } else if (fast) {
+        float z[kSampMaxPer];
+        float tmax = -INFINITY;
+        int timax = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < kSampMaxPer; ++j) {
+          const int i = tid + kThreads * j;
+          z[j] = i < V ? ldvf(row + i) / sp.temperature : -INFINITY;
+          if (z[j] > tmax) { tmax = z[j]; timax = i; }               // ascending i: the lowest index wins ties
+        }
+        if (k == 1) {
+          // greedy: arg-max, lowest index on ties (torch.topk / multinomial over a one-hot distribution)
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, tmax, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, timax, o);
+            if (ov > tmax || (ov == tmax && oi < timax)) { tmax = ov; timax = oi; }
+          }
+          if (lane == 0) { sm.mx[warp] = tmax; sm.wtot[warp] = timax; }
+          __syncthreads();
+          float bv = sm.mx[0];
+          int bi = sm.wtot[0];
+#pragma unroll
+          for (int w = 1; w < 8; ++w)
+            if (sm.mx[w] > bv || (sm.mx[w] == bv && sm.wtot[w] < bi)) { bv = sm.mx[w]; bi = sm.wtot[w]; }
+          tok = bi;
+          done = true;
+        } else {
+          // threshold = the k-th largest per-thread maximum: a lower bound of the k-th largest logit, so {z >= tau} is a superset
+          // of the top-k
+          sm.mx[tid] = tmax;
+          if (tid == 0) sm.flag = 0;
+          __syncthreads();
+          int rank = 0;
+#pragma unroll 8
+          for (int u4 = 0; u4 < kThreads / 4; ++u4) {
+            const float4 m4 = *reinterpret_cast<const float4*>(&sm.mx[4 * u4]);
+            const int u = 4 * u4;
+            rank += (m4.x > tmax || (m4.x == tmax && u < tid)) + (m4.y > tmax || (m4.y == tmax && u + 1 < tid)) +
+                    (m4.z > tmax || (m4.z == tmax && u + 2 < tid)) + (m4.w > tmax || (m4.w == tmax && u + 3 < tid));
+          }
+          if (rank == k - 1) sm.tau = tmax;
+          __syncthreads();
+          const float tau = sm.tau;
+          int cnt = 0;
+#pragma unroll
+          for (int j = 0; j < kSampMaxPer; ++j) cnt += (z[j] >= tau) && (tid + kThreads * j < V);
+          int inc = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          if (lane == 31) sm.wtot[warp] = inc;
+          __syncthreads();
+          int base = 0, total = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const int t = sm.wtot[w];
+            if (w < warp) base += t;
+            total += t;
+          }
+          if (total <= kCandCap) {
+            int pos = base + inc - cnt;
+#pragma unroll
+            for (int j = 0; j < kSampMaxPer; ++j)
+              if (z[j] >= tau && tid + kThreads * j < V) sm.cand[pos++] = make_uint2(__float_as_uint(z[j]), static_cast<uint32_t>(tid + kThreads * j));
+            __syncthreads();
+            // exact rank of every candidate: value descending, index ascending
+            for (int c = tid; c < total; c += kThreads) {
+              const uint2 me = sm.cand[c];
+              const float mv = __uint_as_float(me.x);
+              int r = 0;
+              for (int u = 0; u < total; ++u) {
+                const uint2 o = sm.cand[u];
+                const float ov = __uint_as_float(o.x);
+                r += (ov > mv) || (ov == mv && o.y < me.y);
+              }
+              if (r < k) sm.sorted[r] = me;
+            }
+            __syncthreads();
+            if (warp == 0) {
+              const float z0 = __uint_as_float(sm.sorted[0].x);
+              float w[8], run = 0.f;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int r = lane * 8 + e;
+                w[e] = r < k ? expf(__uint_as_float(sm.sorted[r].x) - z0) : 0.f;
+                run += w[e];
+              }
+              float incw = run;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(0xffffffffu, incw, o);
+                if (lane >= o) incw += t;
+              }
+              const float totalw = __shfl_sync(0xffffffffu, incw, 31);
+              const float target = philox_uniform(sp.seed, seq, nn) * totalw;
+              float cum = incw - run;
+              int pick = -1;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                cum += w[e];
+                if (pick < 0 && lane * 8 + e < k && cum > target) pick = lane * 8 + e;
+              }
+              const unsigned hit = __ballot_sync(0xffffffffu, pick >= 0);
+              const int src = hit ? __ffs(hit) - 1 : 0;
+              int pk2 = __shfl_sync(0xffffffffu, pick, src);
+              if (!hit) pk2 = k - 1;                                     // rounding corner: the last kept candidate
+              if (lane == 0) sm.result = static_cast<int>(sm.sorted[pk2].y);
+            }
+            __syncthreads();
+            tok = sm.result;
+            done = true;
+          }
+        }
+      }
+      if (!done) {
+        // general path (top_k = 0 / >= V / > 256, huge vocabularies, more than kCandCap ties at the threshold)
+        // the row is staged with L1-bypassing loads into a scratch row only this CTA ever touches (sample_row uses plain loads)
+        float* vr = p.vals + static_cast<size_t>(b) * p.ldl;
+        for (int i = tid; i < V; i += kThreads) vr[i] = ldvf(row + i);
+        __syncthreads();
+        tok = sample_row(vr, V, sp.temperature, k, sp.seed, seq, nn, vr, sm.ss);
+      }
+      if (tid == 0) {
+        tok = min(max(tok, 0), p.V - 1);                       // never index the embedding table out of range
+        const int pos = ldvi(p.st.out_len + b);
+        p.st.out_ids[static_cast<size_t>(b) * p.st.out_stride + pos] = tok;      // api_cache.py:179
+        if (p.st.step_ns && b == 0) p.st.step_ns[step] = ptx::global_timer_ns();   // per-token latency read-out
+        p.st.out_len[b] = pos + 1;
+        p.st.cur_tok[b] = tok;
+        p.st.lens[b] = sm.len[b] + 1;
+        const int n = static_cast<int>(nn) + 1;
+        p.st.n_new[b] = n;
+        if (tok == sp.eos_id || n >= ldvi(p.st.max_new + b)) {             // api_cache.py:181
+          p.st.finished[b] = 1;
+          atomicAdd(p.ctrl + 1, 1u);
+        }
+      }
+    }
+    arrive(); wait(); stamp();
+    if (!alive) break;
+    if (p.early_exit && static_cast<int>(ldvu(p.ctrl + 1)) >= n_active0) break;
+  }
+}
+
+// ---- weight packing: bf16 [rows, K] row-major -> tiles (see mma_tile) ----
+__global__ void grid_pack_kernel(const bf16* __restrict__ w, int rows, int K, uint4* __restrict__ dst, size_t n_chunks) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_chunks; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int per_tile = K * 2;                               // 16-byte chunks per tile: 16 rows x K x 2 B / 16
+    const int tile = static_cast<int>(idx / per_tile), c = static_cast<int>(idx % per_tile);
+    const int j = c >> 6, e = (c >> 5) & 1, lane = c & 31, g = lane >> 2, t = lane & 3;
+    const int col = 32 * j + 8 * t + 4 * e, r0 = 16 * tile + g, r1 = r0 + 8;
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    if (r0 < rows) {
+      v[0] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r0) * K + col);
+      v[2] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r0) * K + col + 2);
+    }
+    if (r1 < rows) {
+      v[1] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r1) * K + col);
+      v[3] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r1) * K + col + 2);
+    }
+    dst[idx] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// prefill caches [B][d / 64][Tmax][64] -> kh [B][H][Tvt][hd], vt [B][H][Tvt / 32][hd][32] (attn_tc.cuh)
+__global__ void grid_relayout_kv_kernel(const bf16* __restrict__ ksrc0, const bf16* __restrict__ vsrc0, bf16* __restrict__ kdst0,
+                                        bf16* __restrict__ vdst0, const int32_t* __restrict__ lens, int ns, int Tmax, int Tvt, int hd) {
+  const int bs = blockIdx.x, b = bs / ns;
+  const int len = lens[b];
+  const bf16* ksrc = ksrc0 + static_cast<size_t>(bs) * Tmax * 64;
+  const bf16* vsrc = vsrc0 + static_cast<size_t>(bs) * Tmax * 64;
+  bf16* kdst = kdst0 + static_cast<size_t>(bs) * Tvt * 64;
+  bf16* vdst = vdst0 + static_cast<size_t>(bs) * Tvt * 64;
+  for (int i = threadIdx.x; i < len * 64; i += blockDim.x) {
+    const int t = i >> 6, f = i & 63, h = f / hd, d = f - h * hd, ki = t & 31;
+    const int pos = 8 * ((ki >> 1) & 3) + 2 * (ki >> 3) + (ki & 1);
+    kdst[(static_cast<size_t>(h) * Tvt + t) * hd + d] = ksrc[i];
+    vdst[(static_cast<size_t>(h) * (Tvt >> 5) + (t >> 5)) * (hd * 32) + d * 32 + pos] = vsrc[i];
+  }
+}
+
+template <typename F>
+auto grid_dispatch(int d_model, int hd, F&& f) {
+  if (d_model == 256) return hd == 32 ? f(decode_grid_kernel<256, 32>) : f(decode_grid_kernel<256, 64>);
+  return hd == 32 ? f(decode_grid_kernel<512, 32>) : f(decode_grid_kernel<512, 64>);
+}
+
+}  // namespace
+
+bool grid_eligible(int d_model, int d_ff, int n_head, int n_layer, int V) {
+  if (d_model != 256 && d_model != 512) return false;
+  if (d_ff != 4 * d_model || n_head <= 0 || d_model % n_head) return false;
+  const int hd = d_model / n_head;
+  if (hd != 32 && hd != 64) return false;
+  return n_layer >= 1 && n_layer <= kMaxLayers && V >= 2;
+}
+
+static size_t tiles_bytes(int rows, int K) { return static_cast<size_t>((rows + 15) / 16) * 16 * K * 2; }
+
+size_t grid_packed_bytes(int d_model, int d_ff, int n_layer, int V) {
+  return n_layer * (tiles_bytes(3 * d_model, d_model) + tiles_bytes(d_model, d_model) + tiles_bytes(d_ff, d_model) + tiles_bytes(d_model, d_ff)) +
+         tiles_bytes(V, d_model);
+}
+
+int grid_pack_weights(cudaStream_t s, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1, const bf16* const* w2,
+                      const bf16* head, int n_layer, int d_model, int d_ff, int V, uint8_t* packed, GridLayer* layers, size_t* w_head) {
+  size_t off = 0;
+  auto pack = [&](const bf16* w, int rows, int K, size_t* at) -> int {
+    *at = off;
+    const size_t bytes = tiles_bytes(rows, K);
+    grid_pack_kernel<<<296, 256, 0, s>>>(w, rows, K, reinterpret_cast<uint4*>(packed + off), bytes / 16);
+    MG_LAUNCH_CHECK();
+    off += bytes;
+    return MG_OK;
+  };
+  for (int l = 0; l < n_layer; ++l) {
+    MG_TRY(pack(w_in[l], 3 * d_model, d_model, &layers[l].w_in));
+    MG_TRY(pack(w_out[l], d_model, d_model, &layers[l].w_out));
+    MG_TRY(pack(w1[l], d_ff, d_model, &layers[l].w1));
+    MG_TRY(pack(w2[l], d_model, d_ff, &layers[l].w2));
+  }
+  MG_TRY(pack(head, V, d_model, w_head));
+  return MG_OK;
+}
+
+int grid_plan(int d_model, int d_ff, int n_layer, int V, int B, int n_cta, int* tn, int* ks, GridItem* items, int32_t* n_items) {
+  const int NT = (B + 7) / 8;
+  for (int k = 0; k < 8; ++k) { tn[k] = 8; ks[k] = 1; }
+  // k-split phases: n-tiles per item x k-splits = 8 warps; the fewer sequences, the more warps split K
+  auto shape = [&](int kind, int K, int want_tn) {
+    int t = std::min(want_tn, 8);
+    while (t > 1 && t / 2 >= NT) t /= 2;                  // no point in more n-tiles per item than the batch has
+    int s = 8 / t;
+    while ((K / 32) % s != 0 && s > 1) { s /= 2; t = 8 / s; }
+    while ((K / 32) / s > 16 && s < 8) { s *= 2; t = 8 / s; }   // <= 16 k-step pairs per warp (registers)
+    tn[kind] = t; ks[kind] = s;
+  };
+  int want_out = 2, want_mlp2 = 2;
+  if (const char* e = std::getenv("MG_GRID_TN_OUT")) want_out = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("MG_GRID_TN_MLP2")) want_mlp2 = std::max(1, std::atoi(e));
+  shape(K_OUT, d_model, want_out);
+  shape(K_MLP2, d_ff, want_mlp2);
+  if ((d_model / 32) / ks[K_OUT] > 16 || (d_ff / 32) / ks[K_MLP2] > 16) return MG_E_SHAPE;
+  for (int c = 0; c < n_cta; ++c) n_items[c] = 0;
+  int cursor = 0;
+  auto add = [&](int phase, int tiles, int groups) -> int {
+    for (int t = 0; t < tiles; ++t)
+      for (int g = 0; g < groups; ++g) {
+        const int c = cursor % n_cta;
+        ++cursor;
+        if (n_items[c] >= kMaxItems) return MG_E_SHAPE;
+        items[static_cast<size_t>(c) * kMaxItems + n_items[c]++] = GridItem{static_cast<int16_t>(phase), static_cast<int16_t>(t), static_cast<int16_t>(g), 0};
+      }
+    return MG_OK;
+  };
+  for (int l = 0; l < n_layer; ++l) {
+    MG_TRY(add(5 * l + K_QKV, 3 * d_model / 16, 1));
+    MG_TRY(add(5 * l + K_OUT, d_model / 16, (NT + tn[K_OUT] - 1) / tn[K_OUT]));
+    MG_TRY(add(5 * l + K_MLP1, d_ff / 16, 1));
+    MG_TRY(add(5 * l + K_MLP2, d_model / 16, (NT + tn[K_MLP2] - 1) / tn[K_MLP2]));
+  }
+  MG_TRY(add(5 * n_layer, (V + 15) / 16, 1));
+  return MG_OK;
+}
+
+int grid_init() {
+  for (int d : {256, 512})
+    for (int hd : {32, 64}) {
+      const cudaError_t e = grid_dispatch(d, hd, [&](auto* k) {
+        return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 20);
+      });
+      MG_CUDA_OK(e);
+    }
+  return MG_OK;
+}
+
+int grid_max_ctas(int d_model, int hd) {
+  int per_sm = 0, dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  const cudaError_t e = grid_dispatch(d_model, hd, [&](auto* k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0); });
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return per_sm > 0 ? prop.multiProcessorCount : 0;          // one CTA per SM
+}
+
+int grid_relayout_kv(cudaStream_t s, const bf16* const* kc, const bf16* const* vc, bf16* const* kh, bf16* const* vt, const int32_t* lens,
+                     int B, int n_layer, int d_model, int hd, int Tmax, int Tvt) {
+  const int ns = d_model / 64;
+  for (int l = 0; l < n_layer; ++l) {
+    grid_relayout_kv_kernel<<<B * ns, 256, 0, s>>>(kc[l], vc[l], kh[l], vt[l], lens, ns, Tmax, Tvt, hd);
+    MG_LAUNCH_CHECK();
+  }
+  return MG_OK;
+}
+
+int launch_decode_grid(cudaStream_t s, const GridParams& p, int d_model, int hd) {
+  if ((d_model != 256 && d_model != 512) || (hd != 32 && hd != 64)) return MG_E_SHAPE;
+  GridParams pc = p;
+  void* args[] = {&pc};
+  const cudaError_t e = grid_dispatch(d_model, hd, [&](auto* k) {
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k), dim3(p.n_cta), dim3(kThreads), args, 0, s);
+  });
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(MG_E_CUDA, std::string("decode_grid_kernel launch: ") + cudaGetErrorString(e));
+  }
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return MG_OK;
+}
+
+}  // namespace grid
+}  // namespace mg

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "decode_flow.cuh"
 #include "detok.cuh"
+#include "decode_grid.cuh"
 #include "decode_mega.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -138,6 +139,21 @@ struct mg_engine {
   unsigned long long* d_flow_prof = nullptr;
   int flow_tcap = 0, n_sm = 0;
 
+  // grid-synchronous decode kernel (decode_grid.cu): bf16, d_model 256 / 512, <= 64 sequences
+  bool grid_ok = false, use_grid = false, last_run_grid = false;
+  uint8_t* d_grid_packed = nullptr;
+  grid::GridLayer grid_layers[grid::kMaxLayers]{};
+  size_t grid_w_head = 0;
+  grid::GridItem* d_grid_items = nullptr;
+  int32_t* d_grid_nitems = nullptr;
+  int grid_plan_B = -1, grid_ctas = 0, grid_ldl = 0;
+  int grid_tn[8]{}, grid_ks[8]{};
+  float *g_x = nullptr, *g_x1 = nullptr, *g_q = nullptr, *g_logits = nullptr, *g_vals = nullptr, *g_part = nullptr;
+  bf16 *g_knew = nullptr, *g_vnew = nullptr, *g_h = nullptr;
+  unsigned* d_grid_ctrl = nullptr;
+  unsigned* h_grid_ctrl = nullptr;             // pinned
+  unsigned long long* d_grid_prof = nullptr;
+
   cudaGraphExec_t graph = nullptr;
   int graph_B = -1;
   uint64_t graph_kernels = 0;          // kernels inside the captured decode step (counted per replay)
@@ -176,6 +192,7 @@ bool run_decode_persistent(mg_engine* e, int top_k, int eos_id, int* rc, float* 
                            const int32_t* forced = nullptr, int forced_stride = 0, const int32_t* dbg_slot = nullptr);
 int persistent_status(mg_engine* e);          // after a stream sync: MG_E_CUDA if the flow kernel's watchdog fired
 int setup_mega(mg_engine* e);
+int setup_grid(mg_engine* e);
 int setup_flow(mg_engine* e);
 
 int decode_nsplit(const mg_engine* e, int B) {
@@ -505,6 +522,140 @@ bool run_decode_mega(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   return true;
 }
 
+// ---- grid-synchronous decode kernel: eligibility, packing, plan, launch -----------------------------------------------
+static int alloc_persistent_caches(mg_engine* e) {
+  const mg_geometry& g = e->geo;
+  for (auto& w : e->layers) {
+    if (w.vt) continue;
+    // zero-filled once so that V entries beyond a sequence's length are always finite (they meet probability 0)
+    const size_t vt_bytes = sizeof(bf16) * static_cast<size_t>(e->max_batch) * g.d_model * mega_tvt(e->max_seq);
+    MG_TRY(e->dmalloc(&w.vt, vt_bytes));
+    MG_CUDA_OK(cudaMemsetAsync(w.vt, 0, vt_bytes, e->stream));
+    // + one 32-row block of slack: the last block of the last sequence is read whole
+    const size_t kh_bytes = vt_bytes + sizeof(bf16) * 32 * g.d_model;
+    MG_TRY(e->dmalloc(&w.kh, kh_bytes));
+    MG_CUDA_OK(cudaMemsetAsync(w.kh, 0, kh_bytes, e->stream));
+  }
+  return MG_OK;
+}
+
+int setup_grid(mg_engine* e) {
+  const mg_geometry& g = e->geo;
+  e->grid_ok = false;
+  if (!e->use_grid || e->dtype != MG_DTYPE_BF16 || !grid::grid_eligible(g.d_model, g.d_ff, g.n_head, g.n_layer, g.vocab_size)) return MG_OK;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+  if (!coop) return MG_OK;
+  MG_TRY(grid::grid_init());
+  const int hd = g.d_model / g.n_head, L = g.n_layer, D = g.d_model;
+  e->grid_ctas = grid::grid_max_ctas(D, hd);
+  if (e->grid_ctas <= 0) return MG_OK;
+  MG_TRY(alloc_persistent_caches(e));
+  std::vector<const bf16*> w_in(L), w_out(L), w1(L), w2(L);
+  for (int l = 0; l < L; ++l) {
+    LayerW& w = e->layers[l];
+    w_in[l] = reinterpret_cast<const bf16*>(w.w_in); w_out[l] = reinterpret_cast<const bf16*>(w.w_out);
+    w1[l] = reinterpret_cast<const bf16*>(w.w1); w2[l] = reinterpret_cast<const bf16*>(w.w2);
+    e->grid_layers[l] = grid::GridLayer{w.b_in, w.b_out, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
+                                        reinterpret_cast<bf16*>(w.kh), reinterpret_cast<bf16*>(w.vt), 0, 0, 0, 0};
+  }
+  if (!e->d_grid_packed) {
+    const int S = grid::kMaxSeqs;
+    e->grid_ldl = (g.vocab_size + 15) / 16 * 16;
+    MG_TRY(e->dmalloc(&e->d_grid_packed, grid::grid_packed_bytes(D, g.d_ff, L, g.vocab_size)));
+    MG_TRY(e->dmalloc(&e->d_grid_items, sizeof(grid::GridItem) * grid::kMaxItems * e->grid_ctas));
+    MG_TRY(e->dmalloc(&e->d_grid_nitems, sizeof(int32_t) * e->grid_ctas));
+    const size_t part_floats = static_cast<size_t>(S) * g.n_head * grid::kMaxSplits * (hd + 4);
+    struct { void** p; size_t bytes; } bufs[] = {
+        {reinterpret_cast<void**>(&e->g_x), sizeof(float) * S * D}, {reinterpret_cast<void**>(&e->g_x1), sizeof(float) * S * D},
+        {reinterpret_cast<void**>(&e->g_q), sizeof(float) * S * D}, {reinterpret_cast<void**>(&e->g_knew), sizeof(bf16) * S * D},
+        {reinterpret_cast<void**>(&e->g_vnew), sizeof(bf16) * S * D}, {reinterpret_cast<void**>(&e->g_h), sizeof(bf16) * S * g.d_ff},
+        {reinterpret_cast<void**>(&e->g_logits), sizeof(float) * S * e->grid_ldl}, {reinterpret_cast<void**>(&e->g_vals), sizeof(float) * S * e->grid_ldl},
+        {reinterpret_cast<void**>(&e->g_part), sizeof(float) * part_floats}, {reinterpret_cast<void**>(&e->d_grid_ctrl), 64}};
+    for (auto& b : bufs) {
+      MG_TRY(e->dmalloc(reinterpret_cast<uint8_t**>(b.p), b.bytes));
+      MG_CUDA_OK(cudaMemsetAsync(*b.p, 0, b.bytes, e->stream));
+    }
+    MG_CUDA_OK(cudaMallocHost(&e->h_grid_ctrl, 64));
+    std::memset(e->h_grid_ctrl, 0, 64);
+  }
+  MG_TRY(grid::grid_pack_weights(e->stream, w_in.data(), w_out.data(), w1.data(), w2.data(), reinterpret_cast<const bf16*>(e->head_w), L, D,
+                                 g.d_ff, g.vocab_size, e->d_grid_packed, e->grid_layers, &e->grid_w_head));
+  MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->grid_plan_B = -1;
+  e->grid_ok = true;
+  return MG_OK;
+}
+
+bool run_decode_grid(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride,
+                     const int32_t* dbg_slot) {
+  *rc = MG_OK;
+  const int B = e->cur_B;
+  if (!e->grid_ok || !e->use_grid || e->cur_steps <= 0 || B > grid::kMaxSeqs || e->slots_active) return false;
+  const mg_geometry& g = e->geo;
+  const int hd = g.d_model / g.n_head;
+  auto cuda_ok = [&](cudaError_t ce, const char* what) {
+    if (ce == cudaSuccess) return true;
+    *rc = fail(MG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+    return false;
+  };
+  if (e->grid_plan_B != B) {
+    std::vector<grid::GridItem> items(static_cast<size_t>(grid::kMaxItems) * e->grid_ctas);
+    std::vector<int32_t> n_items(e->grid_ctas);
+    if (grid::grid_plan(g.d_model, g.d_ff, g.n_layer, g.vocab_size, B, e->grid_ctas, e->grid_tn, e->grid_ks, items.data(), n_items.data()) != MG_OK)
+      return false;
+    if (!cuda_ok(cudaStreamSynchronize(e->stream), "grid plan sync")) return true;      // a previous launch may still read the tables
+    if (!cuda_ok(cudaMemcpy(e->d_grid_items, items.data(), sizeof(grid::GridItem) * items.size(), cudaMemcpyHostToDevice), "grid items")) return true;
+    if (!cuda_ok(cudaMemcpy(e->d_grid_nitems, n_items.data(), sizeof(int32_t) * n_items.size(), cudaMemcpyHostToDevice), "grid item counts")) return true;
+    e->grid_plan_B = B;
+  }
+  grid::GridParams p{};
+  p.packed = e->d_grid_packed; p.w_head = e->grid_w_head;
+  for (int l = 0; l < g.n_layer; ++l) p.layers[l] = e->grid_layers[l];
+  p.items = e->d_grid_items; p.n_items = e->d_grid_nitems;
+  p.tok_emb = reinterpret_cast<const bf16*>(e->tok_emb); p.pos_emb = reinterpret_cast<const bf16*>(e->pos_emb);
+  p.head_b = e->head_b; p.sp = e->d_sp; p.st = e->st;
+  p.x = e->g_x; p.x1 = e->g_x1; p.q = e->g_q; p.knew = e->g_knew; p.vnew = e->g_vnew; p.h = e->g_h; p.logits = e->g_logits;
+  p.vals = e->g_vals; p.part = e->g_part; p.ctrl = e->d_grid_ctrl;
+  p.L = g.n_layer; p.V = g.vocab_size; p.B = B; p.H = g.n_head; p.n_steps = e->cur_steps; p.Tvt = mega_tvt(e->max_seq);
+  p.ldl = e->grid_ldl; p.n_cta = e->grid_ctas;
+  for (int k = 0; k < 8; ++k) { p.tn[k] = e->grid_tn[k]; p.ks[k] = e->grid_ks[k]; }
+  p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
+  p.dbg_logits = dbg_logits; p.dbg_slot = dbg_slot; p.forced = forced; p.forced_stride = forced_stride;
+  p.prof = nullptr; p.prof_step = -1;
+  const int n_stamps = 5 * g.n_layer + 3;
+  if (const char* ps = std::getenv("MG_GRID_PROF_STEP")) {          // debug: phase timeline of CTA 0 in one decode step -> stderr
+    if (!e->d_grid_prof && e->dmalloc(&e->d_grid_prof, 64 * sizeof(unsigned long long)) != MG_OK) e->d_grid_prof = nullptr;
+    if (e->d_grid_prof) {
+      cudaMemsetAsync(e->d_grid_prof, 0, 64 * sizeof(unsigned long long), e->stream);
+      p.prof = e->d_grid_prof; p.prof_step = std::atoi(ps);
+    }
+  }
+  if (!cuda_ok(cudaMemsetAsync(e->d_grid_ctrl, 0, 64, e->stream), "grid control reset")) return true;
+  {
+    std::vector<const bf16*> kc(g.n_layer), vc(g.n_layer);
+    std::vector<bf16*> kh(g.n_layer), vt(g.n_layer);
+    for (int l = 0; l < g.n_layer; ++l) {
+      kc[l] = reinterpret_cast<const bf16*>(e->layers[l].kc); vc[l] = reinterpret_cast<const bf16*>(e->layers[l].vc);
+      kh[l] = reinterpret_cast<bf16*>(e->layers[l].kh); vt[l] = reinterpret_cast<bf16*>(e->layers[l].vt);
+    }
+    *rc = grid::grid_relayout_kv(e->stream, kc.data(), vc.data(), kh.data(), vt.data(), e->st.lens, B, g.n_layer, g.d_model, hd, e->max_seq, p.Tvt);
+  }
+  if (*rc == MG_OK) *rc = grid::launch_decode_grid(e->stream, p, g.d_model, hd);
+  if (*rc == MG_OK && !cuda_ok(cudaMemcpyAsync(e->h_grid_ctrl, e->d_grid_ctrl, 64, cudaMemcpyDeviceToHost, e->stream), "grid status copy")) return true;
+  if (p.prof && *rc == MG_OK) {
+    unsigned long long h[64];
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(h, e->d_grid_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[grid prof] step %d, CTA 0 (ns since step start; then per layer: qkv attn out mlp1 mlp2; head; sampler):", p.prof_step);
+    for (int i = 0; i < n_stamps && i < 64 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
+    fprintf(stderr, "\n");
+  }
+  e->t_steps = e->cur_steps;
+  e->last_run_grid = true;
+  return true;
+}
+
 // ---- weight-stationary flow kernel: eligibility, plan, packing, launch ---------------------------------------------
 int setup_flow(mg_engine* e) {
   const mg_geometry& g = e->geo;
@@ -658,13 +809,18 @@ bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
 
 bool run_decode_persistent(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride,
                            const int32_t* dbg_slot) {
-  e->last_run_flow = false;
+  e->last_run_flow = e->last_run_grid = false;
+  if (run_decode_grid(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
   if (run_decode_flow(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
   return run_decode_mega(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot);
 }
 
 // After the stream has been synchronised: did the flow kernel's watchdog fire?
 int persistent_status(mg_engine* e) {
+  if (e->last_run_grid && e->h_grid_ctrl && e->h_grid_ctrl[2] != 0) {
+    e->grid_ok = false;                                                  // do not trust it again in this process
+    return fail(MG_E_CUDA, "grid decode kernel aborted: a grid barrier was not reached within the watchdog time");
+  }
   if (!e->last_run_flow || !e->h_flow_status || e->h_flow_status[0] == 0) return MG_OK;
   const int32_t* s = e->h_flow_status;
   e->flow_ok = false;                                                  // do not trust it again in this process
@@ -957,6 +1113,8 @@ int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max
   e->use_mega = !(env_mega && env_mega[0] == '1');
   // The weight-stationary flow kernel (decode_flow.cu) is OPT-IN (MG_FLOW=1): parity-green, but measured slower than the cluster
   // kernel on every BASELINE configuration (profiles/r2b_flow_*).
+  const char* env_grid = std::getenv("MG_GRID");
+  e->use_grid = env_grid && env_grid[0] == '1';
   const char* env_flow = std::getenv("MG_FLOW");
   e->use_flow = env_flow && env_flow[0] == '1';
   {
@@ -1105,6 +1263,7 @@ int mg_engine_finalize(mg_engine* e) {
     MG_TRY(make_wmaps(&e->m_head, e->head_w, e->geo.vocab_size, d));
   }
   MG_TRY(setup_mega(e));
+  MG_TRY(setup_grid(e));
   MG_TRY(setup_flow(e));
   e->ready = true;
   return MG_OK;
@@ -1147,7 +1306,7 @@ int mg_synchronize(mg_engine* e) {
 
 int mg_last_decode_path(mg_engine* e) {
   if (!e) return fail(MG_E_ARG, "null engine");
-  return e->last_run_flow ? 2 : (e->last_run_mega ? 1 : 0);
+  return e->last_run_grid ? 3 : (e->last_run_flow ? 2 : (e->last_run_mega ? 1 : 0));
 }
 
 void* mg_engine_stream(mg_engine* e) { return e ? reinterpret_cast<void*>(e->stream) : nullptr; }
@@ -1233,7 +1392,7 @@ static int step_logits_impl(mg_engine* e, const int32_t* ids, const int32_t* off
     MG_TRY(rc);
     MG_TRY(mrc);
   }
-  e->last_run_mega = e->last_run_flow = false;
+  e->last_run_mega = e->last_run_flow = e->last_run_grid = false;
   for (int i = 0; i < n_steps; ++i) {
     MG_TRY(is_bf16 ? decode_forward<bf16>(e) : decode_forward<float>(e));
     const int sl = want ? slot[i] : i;
@@ -1509,7 +1668,7 @@ int mg_slots_step(mg_engine* e, int n_steps, uint8_t* finished_out, int32_t* out
   if (n_steps <= 0 || n_steps > e->max_seq) return fail(MG_E_ARG, "n_steps must be in [1, max_seq]");
   e->cur_steps = n_steps;
   e->d_last_rows = e->d_slot_last_rows;
-  e->last_run_mega = e->last_run_flow = false;
+  e->last_run_mega = e->last_run_flow = e->last_run_grid = false;
   if (e->slots_mega) {
     int rc = MG_OK;
     if (!run_decode_mega(e, e->slots_topk, e->slots_eos, &rc, nullptr, nullptr, 0, nullptr))

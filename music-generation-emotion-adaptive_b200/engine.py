@@ -348,10 +348,11 @@ class Generator:
         _check(self.lib, self.lib.mg_engine_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
 
-    DECODE_PATHS = {0: "step_graph", 1: "cluster_kernel", 2: "flow_kernel"}
+    DECODE_PATHS = {0: "step_graph", 1: "cluster_kernel", 2: "flow_kernel", 3: "grid_kernel"}
 
     def last_decode_path(self) -> str:
-        """Which CUDA decode path served the last run: step_graph / cluster_kernel (decode_mega.cu) / flow_kernel (decode_flow.cu)."""
+        """Which CUDA decode path served the last run: step_graph / cluster_kernel (decode_mega.cu) / flow_kernel (decode_flow.cu) /
+        grid_kernel (decode_grid.cu)."""
         return self.DECODE_PATHS[int(self.lib.mg_last_decode_path(self._h))]
 
     # -- slot session: continuous batching (caller side: api_cache.py:186-204) --------------------

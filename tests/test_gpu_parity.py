@@ -617,6 +617,90 @@ def test_flow_kernel_sampler_distribution_chi_square():
 
 
 # ---------------------------------------------------------------------------------------------------
+# the grid-synchronous decode kernel (decode_grid.cu, MG_GRID=1): all SMs, any d_model in {256, 512}
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("geo_name,B,tp,n_steps,steps,max_seq", [
+    ("train_large", 64, 6, 320, [0, 1, 25, 26, 27, 63, 64, 65, 319], 512),
+    ("train_large", 9, [3, 4, 5, 6, 7, 8, 30, 70, 200], 40, [0, 5, 39], 512),
+    ("train_large", 1, 12, 48, [0, 20, 47], 512),
+    ("train_mini", 3, 5, 80, [0, 26, 27, 79], 512),
+    ("train_large2", 64, 6, 72, [0, 26, 58, 71], 256),
+    ("train_large2", 5, [9, 40, 64, 65, 130], 40, [0, 39], 256),
+])
+def test_grid_kernel_logits_match_the_oracle(geo_name, B, tp, n_steps, steps, max_seq):
+    """Teacher-forced bf16 logits of the grid-synchronous kernel against the fp64 oracle: full and ragged batches, one
+    sequence, head_dim 32 and 64, d_model 256 and 512 (the paper's train_large2 geometry), cache lengths across the 32-key block
+    boundaries."""
+    rows = sorted({0, B // 2, B - 1})
+    path, worst = _long_cache_case(geo_name, B, tp, n_steps, steps, rows=rows, max_seq=max_seq, env={"MG_GRID": "1"})
+    assert path == "grid_kernel"
+    print(f"grid kernel {geo_name} B {B}: worst |logit error| {worst:.4f}")
+
+
+def test_grid_kernel_config3_and_config4_cache_lengths():
+    """The benchmarked shapes through the grid kernel: config 3 (B 64, cache to 1030) and config 4 (B 16, cache to 4352: every
+    (sequence, head) is split over up to 16 key ranges on different SMs)."""
+    tp = 6
+    path, worst = _long_cache_case("train_large", 64, tp, 1024, [0, 511 - tp, 512 - tp, 1023], rows=(0, 31, 63), max_seq=1088,
+                                   env={"MG_GRID": "1"})
+    assert path == "grid_kernel"
+    print(f"grid kernel config-3 worst |logit error| {worst:.4f}")
+    path, worst = _long_cache_case("train_large_pos512", 16, 256, 4096, [0, 2047 - 256, 2048 - 256, 4095], rows=(0, 7, 15),
+                                   max_seq=4352, env={"MG_GRID": "1"})
+    assert path == "grid_kernel"
+    print(f"grid kernel config-4 worst |logit error| {worst:.4f}")
+
+
+def test_grid_kernel_generation_determinism_ragged_budgets_eos_and_general_sampler():
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], 24, seed=4)]
+    e = _engine_with_env("train_large", 0, {"MG_GRID": "1"}, max_batch=64, max_seq=320)
+    a = e.generate(prompts, 48, 1.0, 40, seed=7)
+    assert e.last_decode_path() == "grid_kernel"
+    assert a == e.generate(prompts, 48, 1.0, 40, seed=7) and a != e.generate(prompts, 48, 1.0, 40, seed=8)
+    assert all(len(o) == len(p) + 48 for o, p in zip(a, prompts))
+    max_new = [1 + (5 * i) % 40 for i in range(24)]
+    r = e.generate(prompts, max_new, 1.0, 40, seed=7)                  # ragged budgets: prefixes of the full run
+    assert all(o == f[:len(o)] and len(o) == len(p) + n for o, f, p, n in zip(r, a, prompts, max_new))
+    # EOS: pick a token the full run produced; every sequence stops right behind its first occurrence
+    eos = a[0][len(prompts[0]) + 5]
+    s = e.generate(prompts, 48, 1.0, 40, seed=7, eos_id=eos)
+    for o, f, p in zip(s, a, prompts):
+        new = f[len(p):]
+        cut = new.index(eos) + 1 if eos in new else len(new)
+        assert o == f[:len(p) + cut]
+    # greedy agrees with the cluster kernel up to bf16 near-ties
+    g = e.generate(prompts, 8, 1.0, 1)
+    mega = engine("train_large", 0, "bf16", max_batch=64, max_seq=1088)
+    gm = mega.generate(prompts, 8, 1.0, 1)
+    assert sum(x == y for x, y in zip(g, gm)) >= 20
+    # general sampler path (top_k = None: whole vocabulary) runs and is deterministic
+    w = e.generate(prompts[:5], 6, 1.0, None, seed=3)
+    assert e.last_decode_path() == "grid_kernel" and w == e.generate(prompts[:5], 6, 1.0, None, seed=3)
+    e.close()
+
+
+def test_grid_kernel_sampler_distribution_chi_square():
+    """The grid kernel's sampler (threshold from the per-thread maxima, exact ranking of the candidate superset, Philox): 102400
+    draws of one decode step against the top-k softmax of the engine's own logits."""
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompt = mg.encode(ck["vocab"], mg.synthetic_prompts(ck["vocab"], 1, seed=0)[0])
+    e = _engine_with_env("train_large", 0, {"MG_GRID": "1"}, max_batch=64, max_seq=320)
+    lg = e.step_logits([prompt], None, 1)[0, 0]
+    assert e.last_decode_path() == "grid_kernel"
+    probs = gpt_kv.topk_probs(torch.from_numpy(lg.astype(np.float64)), 1.0, 40).numpy()
+    counts = np.zeros(geo.vocab_size, np.int64)
+    for it in range(1600):
+        out = e.generate([prompt] * 64, 1, 1.0, 40, seed=5000 + it, as_arrays=True)
+        counts += np.bincount([int(o[-1]) for o in out], minlength=geo.vocab_size)
+    assert counts[probs == 0].sum() == 0                            # never a token outside the top-k set
+    assert _chi_square_p(counts, probs / probs.sum()) > 1e-3
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------------
 # device-side detokenisation (SURVEY 8 f3): api_cache.py:157,208-221 as a gather over the token ids in HBM
 # ---------------------------------------------------------------------------------------------------
 def _note_line_vocab(V, seed=0):
