@@ -34,22 +34,25 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 __device__ __forceinline__ uint4 ldg_stream16(const bf16* p) { return ptx::ld_global_stream16(p); }
-
-// Tensor-core flash-decoding of ONE (sequence, head) by ONE warp straight from global memory (no shared-memory staging):
-// this worker takes the 32-key blocks wi, wi + nws, ... of the cache.
-//   scores   S = q K^T   : A = the query (row 0 = bf16 hi part, row 8 = bf16 lo part of the fp32 query, so the product keeps
-//                          fp32-query accuracy for free), B = K rows; lane (g, t) loads 16 bytes = dims [8t, 8t+8) of key row
-//                          8 j + g for the j-th MMA of the block: eight consecutive rows of the head-major K cache, one
-//                          contiguous 512-byte request (head_dim 32); lane t of row 0 receives the scores of keys 8j + 2t + {0,1};
-//   output   O = P V     : A = the probabilities (row 0), B = V^T: lane (g, t) loads 16 bytes = key positions [8t, 8t+8) of dim
-//                          8 n + g.  The V cache of this kernel is stored per 32-key block as [dim][32 positions] with key
-//                          8j + 2t + e at position 8t + 2j + e, i.e. exactly in the order the score MMAs leave the
-//                          probabilities in lane t -- no shuffles, and again one contiguous 512-byte request per load.
-// The contraction index of an MMA may be permuted freely as long as A and B agree, which is what makes 16-byte loads work.
-// Only row 0 (lanes 0..3) carries data; the other 15 rows of the m16 tile are idle -- the tensor pipe has nothing else to do.
-// kh: K rows of this (sequence, head) [T][HD], vt: V blocks of this (sequence, head) [T / 32][HD][32], q: fp32, log2-scaled.
-// 16-byte loads of one 32-key block (see attn_tc): K rows 8 j + g, V^T rows 8 n + g
-template <int HD>
+// L1-bypassing flavour for caches whose rows are appended by OTHER SMs during the launch (decode_grid.cu): a weak load may be
+// served from a stale L1 line (observed on B200: the appending SM keeps the line it wrote); ld.volatile never looks at L1
+#ifndef MG_GRID_KVLD
+#define MG_GRID_KVLD 2
+#endif
+__device__ __forceinline__ uint4 ldg_strong16(const bf16* p) {
+  uint4 r;
+#if MG_GRID_KVLD == 0
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#elif MG_GRID_KVLD == 1
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#elif MG_GRID_KVLD == 2
+  asm volatile("ld.relaxed.gpu.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#else
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#endif
+  return r;
+}
+template <int HD, bool STRONG = false>
 __device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int b, int lane,
                                                 uint4 (&kq)[4][HD / 32], uint4 (&vq)[HD / 8]) {
   const int g = lane >> 2, t = lane & 3;
@@ -59,10 +62,10 @@ __device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, con
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int c = 0; c < HD / 32; ++c) kq[j][c] = ldg_stream16(kb + j * 8 * HD + 32 * c);
+    for (int c = 0; c < HD / 32; ++c) kq[j][c] = STRONG ? ldg_strong16(kb + j * 8 * HD + 32 * c) : ldg_stream16(kb + j * 8 * HD + 32 * c);
   const bf16* vb = vt + static_cast<size_t>(b) * (HD * 32) + g * 32 + 8 * t;
 #pragma unroll
-  for (int n = 0; n < HD / 8; ++n) vq[n] = ldg_stream16(vb + n * 256);
+  for (int n = 0; n < HD / 8; ++n) vq[n] = STRONG ? ldg_strong16(vb + n * 256) : ldg_stream16(vb + n * 256);
 }
 
 // kq0 / vq0: block `wi` of this worker, loaded by the caller ahead of time (before the QKV GEMM, whose result the loads do not
@@ -79,7 +82,7 @@ __device__ __forceinline__ void kvslot_issue(const bf16* __restrict__ kh, const 
   }
 }
 
-template <int HD, bool PRE>
+template <int HD, bool PRE, bool STRONG = false>
 __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int wi, int nws,
                                         int lane, const float* __restrict__ q, const bf16* __restrict__ knew,
                                         const bf16* __restrict__ vnew, bool fold_new, float* __restrict__ out,
@@ -111,7 +114,7 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
   float m_run = -INFINITY, l_run = 0.f;   // l_run: this lane's share of the denominator (summed over the quad at the end)
 
   const int nblk = (len + 31) >> 5;
-  auto load_block = [&](int b, uint4 (&kq)[4][KL], uint4 (&vq)[NT]) { attn_load_block<HD>(kh, vt, len, b, lane, kq, vq); };
+  auto load_block = [&](int b, uint4 (&kq)[4][KL], uint4 (&vq)[NT]) { attn_load_block<HD, STRONG>(kh, vt, len, b, lane, kq, vq); };
   auto compute_block = [&](int b, const uint4 (&kq)[4][KL], const uint4 (&vq)[NT]) {
     const int key0 = b << 5;
     float sc[4][2];

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 
 #include "attn_tc.cuh"
 #include "decode_grid.cuh"
@@ -83,18 +84,22 @@ __device__ __forceinline__ int ldvb(const uint8_t* p) {
 // weights: immutable for the whole launch, read-only path, allocate in L1
 __device__ __forceinline__ uint4 ldw16(const uint8_t* p) {
   uint4 r;
-  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));   // not volatile: the compiler may hoist / batch them
   return r;
 }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// cache append: L2-only store (no copy of the line is left in the appending SM's L1)
+__device__ __forceinline__ void st_kv(bf16* p, bf16 v) {
+  asm volatile("st.global.cg.u16 [%0], %1;" ::"l"(p), "h"(*reinterpret_cast<const unsigned short*>(&v)) : "memory");
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 struct GridSmem {
-  float4 red[8][32];                   // k-split partial accumulators [warp][lane]
+  alignas(16) float4 red[8][32];                   // k-split partial accumulators [warp][lane]
   float qs[8][64];                     // per-warp attention scratch: query (fp32, log2-scaled), new K / V rows, partial result
   bf16 kn[8][64];
   bf16 vn[8][64];
@@ -106,13 +111,14 @@ struct GridSmem {
   int tok[kMaxSeqs];
   int total_units;
   // sampler
-  float mx[kThreads];
-  uint2 cand[kCandCap];
+  alignas(16) float mx[kThreads];
+  alignas(16) uint2 cand[kCandCap];
   uint2 sorted[kThreads];
   int wtot[8];
   float tau;
   int flag;
   int result;
+  int next_tok;                        // sampler -> embedding producer of the same CTA (-1: the sequence has just finished)
   SampleSmem ss;
   GridItem items[kMaxItems];
 };
@@ -144,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
   constexpr int NPD = DM / 32;           // k-step pairs across d_model
   constexpr int DFF = 4 * DM;
   constexpr int PS = HD + 4;             // floats per attention partial
+  constexpr int NT16 = DM / 16;          // 16-row tiles across d_model = LayerNorm partial statistics per sequence
   __shared__ GridSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, qd = lane >> 2, tq = lane & 3;
   const int cta = blockIdx.x, n_cta = p.n_cta, B = p.B, H = p.H, L = p.L;
@@ -155,21 +162,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
   unsigned* const bar = p.ctrl;
   unsigned bar_target = 0;
   bool alive = true;
+  unsigned long long* tr = nullptr;     // fine trace (clock64) of one dense phase of CTA 0: p.prof[96..]
+  auto trace = [&]() { if (tr) *tr++ = clock64(); };
 
   // ---- grid barrier: arrive (release by one thread behind the CTA barrier) / wait (one polling lane per warp) ----
   auto arrive = [&]() {
+    trace();
     __syncthreads();
+    trace();
+    // release only: __threadfence() (MEMBAR.SC + CCTL.IVALL) would invalidate this SM's L1, i.e. the weight tiles it keeps there
     if (tid == 0) {
-      __threadfence();
-      atomicAdd(bar, 1u);
+      if (p.fence_mode == 1) { __threadfence(); atomicAdd(bar, 1u); }
+      else asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
     }
+    trace();
     bar_target += static_cast<unsigned>(n_cta);
   };
   auto wait = [&]() {
-    int ok = 1;
-    if (lane == 0) {
+    // ONE polling thread per CTA (a poller per warp = 1184 loads hammering the counter's L2 slice delays the arrivals themselves)
+    if (tid == 0) {
       unsigned spins = 0;
       unsigned long long t0 = 0;
+      int ok = 1;
       while (ldvu(bar) < bar_target) {
         if ((++spins & 0xfffu) == 0) {
           const unsigned long long now = ptx::global_timer_ns();
@@ -177,15 +191,34 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
           else if (now - t0 > kWatchdogNs || ldvu(p.ctrl + 2) != 0) { ok = 0; atomicExch(p.ctrl + 2, 1u); break; }
         }
       }
+      sm.flag = ok;
+      trace();
     }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    if (!ok) alive = false;
+    __syncthreads();
+    if (!sm.flag) alive = false;
   };
   const bool prof_on = p.prof != nullptr && cta == 0 && tid == 0;
   int prof_i = 0;
 
   const int s_own = 8 * warp + qd;                        // sequence of this lane's B fragments when a warp owns n-tile `warp`
   const int sa = 8 * warp + 2 * tq, sb = sa + 1;          // sequences of this lane's accumulators (same n-tile)
+
+  // embedding x = tok_emb[tok] + pos_emb[0] (api_cache.py:99 with T == 1) of sequence b by its owner CTA: fp32 + bf16 copies and the
+  // per-16-feature LayerNorm statistics, exactly what an mlp.2 epilogue leaves for the next block
+  auto embed = [&](int b, int tok) {
+    const bf16* te = p.tok_emb + static_cast<size_t>(tok) * DM;
+    for (int f = tid; f < DM; f += kThreads) {
+      const float v = __bfloat162float(te[f]) + __bfloat162float(p.pos_emb[f]);
+      p.x[static_cast<size_t>(b) * DM + f] = v;
+      p.xb[static_cast<size_t>(b) * DM + f] = __float2bfloat16_rn(v);
+      float a = v, q = v * v;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+      if ((lane & 15) == 0) *reinterpret_cast<float2*>(p.sx + (static_cast<size_t>(b) * NT16 + (f >> 4)) * 2) = make_float2(a, q);
+    }
+  };
+  if (cta < B && p.st.finished[cta] == 0) embed(cta, min(max(p.st.cur_tok[cta], 0), p.V - 1));
+  arrive(); wait();
 
   for (int step = 0; step < p.n_steps && alive; ++step) {
     auto stamp = [&]() { if (prof_on && step == p.prof_step) p.prof[prof_i++] = ptx::global_timer_ns(); };
@@ -252,73 +285,61 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
     const int dslot = !p.dbg_logits ? -1 : (p.dbg_slot ? p.dbg_slot[step] : step);
 
     // ---------------- dense phases whose operand is a whole (LayerNorm-ed) residual row: in_proj, mlp.0, head ----------------
-    auto phase_rows = [&](int ph, int kind, int l) {
+    auto phase_rows = [&](int ph, auto kind_c, int l) {
+      constexpr int kind = decltype(kind_c)::value;
       if (!(it < n_items && sm.items[it].phase == ph)) return;
       const bool wactive = 8 * warp < B;
       uint4 bq[NPD];
+      if (prof_on && step == p.prof_step && kind == K_MLP1 && l == 1) tr = p.prof + 96;
+      trace();
       if (wactive) {
+        // operand = the bf16 copy of the residual stream its producer left next to the fp32 one; LayerNorm from the producer's
+        // per-tile (sum, sum of squares) -- no pass over the row for the statistics, half the bytes of an fp32 row
         const int sq = min(s_own, B - 1);
-        float v[NPD * 8];
-        const float* src = kind == K_MLP1 ? p.x1 : ((kind == K_QKV && l == 0) ? nullptr : p.x);
-        if (src) {
-          const float* row = src + static_cast<size_t>(sq) * DM + 8 * tq;
+        const bf16* row = (kind == K_MLP1 ? p.x1b : p.xb) + static_cast<size_t>(sq) * DM + 8 * tq;
+        uint4 raw[NPD];
 #pragma unroll
-          for (int j = 0; j < NPD; ++j) {
-            const float4 a = ldv4f(row + 32 * j), b = ldv4f(row + 32 * j + 4);
-            v[8 * j] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = a.z; v[8 * j + 3] = a.w;
-            v[8 * j + 4] = b.x; v[8 * j + 5] = b.y; v[8 * j + 6] = b.z; v[8 * j + 7] = b.w;
-          }
-        } else {
-          // embedding x = tok_emb[tok] + pos_emb[0] (api_cache.py:99 with T == 1)
-          const bf16* te = p.tok_emb + static_cast<size_t>(sm.tok[sq]) * DM + 8 * tq;
-          const bf16* pe = p.pos_emb + 8 * tq;
-#pragma unroll
-          for (int j = 0; j < NPD; ++j) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(te + 32 * j)), b = __ldg(reinterpret_cast<const uint4*>(pe + 32 * j));
-            float fa[8], fb[8];
-            unpack8(a, fa);
-            unpack8(b, fb);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[8 * j + e] = fa[e] + fb[e];
-          }
-        }
-        if (kind != K_HEAD) {
+        for (int j = 0; j < NPD; ++j) raw[j] = ldv4u(row + 32 * j);
+        if constexpr (kind != K_HEAD) {
           const GridLayer& lw = p.layers[l];
           const float* gw = kind == K_QKV ? lw.ln1w : lw.ln2w;
           const float* gb = kind == K_QKV ? lw.ln1b : lw.ln2b;
-          float sum = 0.f;
+          const float* st = (kind == K_MLP1 ? p.sx1 : p.sx) + static_cast<size_t>(sq) * (2 * NT16) + 2 * tq;
+          float sum = 0.f, ssq = 0.f;
 #pragma unroll
-          for (int e = 0; e < NPD * 8; ++e) sum += v[e];
-          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          for (int i = 0; i < NT16 / 4; ++i) {
+            const float2 t2 = ldv2f(st + 8 * i);
+            sum += t2.x; ssq += t2.y;
+          }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
+          trace();
           const float mean = sum * (1.0f / DM);
-          float sq2 = 0.f;
-#pragma unroll
-          for (int e = 0; e < NPD * 8; ++e) { const float d = v[e] - mean; sq2 = fmaf(d, d, sq2); }
-          sq2 += __shfl_xor_sync(0xffffffffu, sq2, 1);
-          sq2 += __shfl_xor_sync(0xffffffffu, sq2, 2);
-          const float rstd = rsqrtf(sq2 * (1.0f / DM) + 1e-5f);
+          const float rstd = rsqrtf(fmaxf(ssq * (1.0f / DM) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
           for (int j = 0; j < NPD; ++j) {
             const float4 w0 = __ldg(reinterpret_cast<const float4*>(gw + 32 * j + 8 * tq)), w1 = __ldg(reinterpret_cast<const float4*>(gw + 32 * j + 8 * tq + 4));
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(gb + 32 * j + 8 * tq)), b1 = __ldg(reinterpret_cast<const float4*>(gb + 32 * j + 8 * tq + 4));
-            v[8 * j] = (v[8 * j] - mean) * rstd * w0.x + b0.x; v[8 * j + 1] = (v[8 * j + 1] - mean) * rstd * w0.y + b0.y;
-            v[8 * j + 2] = (v[8 * j + 2] - mean) * rstd * w0.z + b0.z; v[8 * j + 3] = (v[8 * j + 3] - mean) * rstd * w0.w + b0.w;
-            v[8 * j + 4] = (v[8 * j + 4] - mean) * rstd * w1.x + b1.x; v[8 * j + 5] = (v[8 * j + 5] - mean) * rstd * w1.y + b1.y;
-            v[8 * j + 6] = (v[8 * j + 6] - mean) * rstd * w1.z + b1.z; v[8 * j + 7] = (v[8 * j + 7] - mean) * rstd * w1.w + b1.w;
+            float vj[8];
+            unpack8(raw[j], vj);
+            bq[j] = make_uint4(pk((vj[0] - mean) * rstd * w0.x + b0.x, (vj[1] - mean) * rstd * w0.y + b0.y),
+                               pk((vj[2] - mean) * rstd * w0.z + b0.z, (vj[3] - mean) * rstd * w0.w + b0.w),
+                               pk((vj[4] - mean) * rstd * w1.x + b1.x, (vj[5] - mean) * rstd * w1.y + b1.y),
+                               pk((vj[6] - mean) * rstd * w1.z + b1.z, (vj[7] - mean) * rstd * w1.w + b1.w));
           }
-        }
+        } else {
 #pragma unroll
-        for (int j = 0; j < NPD; ++j)
-          bq[j] = make_uint4(pk(v[8 * j], v[8 * j + 1]), pk(v[8 * j + 2], v[8 * j + 3]), pk(v[8 * j + 4], v[8 * j + 5]), pk(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < NPD; ++j) bq[j] = raw[j];           // no final LayerNorm (api_cache.py:105)
+        }
       }
+      trace();
       while (it < n_items && sm.items[it].phase == ph) {
         const int rt = sm.items[it].row_tile;
         ++it;
         if (!wactive) continue;
         const int ra = 16 * rt + qd, rb = ra + 8;
         float acc[4];
-        if (kind == K_QKV) {
+        if constexpr (kind == K_QKV) {
           const GridLayer& lw = p.layers[l];
           const float ba = __ldg(lw.b_in + ra), bb = __ldg(lw.b_in + rb);
           mma_tile<NPD>(p.packed + lw.w_in + static_cast<size_t>(rt) * (16 * DM * 2), lane, bq, NPD, acc);
@@ -340,21 +361,22 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
                 const int key = sm.len[s], hh = fa / HD, d0 = fa - hh * HD, d1 = d0 + 8;   // both rows lie in the same head
                 const size_t hb = (static_cast<size_t>(s) * H + hh) * p.Tvt * HD;
                 if (part == 1) {
-                  lw.kh[hb + static_cast<size_t>(key) * HD + d0] = xa;
-                  lw.kh[hb + static_cast<size_t>(key) * HD + d1] = xb;
+                  st_kv(lw.kh + hb + static_cast<size_t>(key) * HD + d0, xa);
+                  st_kv(lw.kh + hb + static_cast<size_t>(key) * HD + d1, xb);
                 } else {
                   const int ki = key & 31, pos = 8 * ((ki >> 1) & 3) + 2 * (ki >> 3) + (ki & 1);      // see attn_tc
                   bf16* vb2 = lw.vt + hb + static_cast<size_t>(key >> 5) * (HD * 32) + pos;
-                  vb2[d0 * 32] = xa;
-                  vb2[d1 * 32] = xb;
+                  st_kv(vb2 + d0 * 32, xa);
+                  st_kv(vb2 + d1 * 32, xb);
                 }
               }
             }
           }
-        } else if (kind == K_MLP1) {
+        } else if constexpr (kind == K_MLP1) {
           const GridLayer& lw = p.layers[l];
           const float ba = __ldg(lw.b1 + ra), bb = __ldg(lw.b1 + rb);
           mma_tile<NPD>(p.packed + lw.w1 + static_cast<size_t>(rt) * (16 * DM * 2), lane, bq, NPD, acc);
+          if (tr) { asm volatile("" ::"f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3])); trace(); }
           if (sa < B) {
             p.h[static_cast<size_t>(sa) * DFF + ra] = __float2bfloat16_rn(gelu_erf_f(acc[0] + ba));
             p.h[static_cast<size_t>(sa) * DFF + rb] = __float2bfloat16_rn(gelu_erf_f(acc[2] + bb));
@@ -385,7 +407,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
 
     // ---------------- dense phases with k-splits across the warps of a CTA: out_proj (operand = merged attention partials) and
     //                  mlp.2 (operand = bf16 hidden activations); both add the residual stream in their epilogue ----------------
-    auto phase_split = [&](int ph, int kind, int l) {
+    auto phase_split = [&](int ph, auto kind_c, int l) {
+      constexpr int kind = decltype(kind_c)::value;
       const int TN = p.tn[kind], KS = p.ks[kind];
       const int ntl = warp % TN, ksp = warp / TN;
       const GridLayer& lw = p.layers[l];
@@ -405,68 +428,68 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int s = min(s0 + e, B - 1);
-            if (kind == K_OUT && l == 0) {
-              const bf16* te = p.tok_emb + static_cast<size_t>(sm.tok[s]) * DM;
-              res[e] = __bfloat162float(te[ra]) + __bfloat162float(p.pos_emb[ra]);
-              res[2 + e] = __bfloat162float(te[rb]) + __bfloat162float(p.pos_emb[rb]);
-            } else {
-              const float* xr = (kind == K_OUT ? p.x : p.x1) + static_cast<size_t>(s) * DM;
-              res[e] = ldvf(xr + ra);
-              res[2 + e] = ldvf(xr + rb);
-            }
+            const float* xr = (kind == K_OUT ? p.x : p.x1) + static_cast<size_t>(s) * DM;
+            res[e] = ldvf(xr + ra);
+            res[2 + e] = ldvf(xr + rb);
           }
         }
-        if (wactive) {
-          uint4 bq[16];
-          if (kind == K_MLP2) {
-            const int npw = (DFF / 32) / KS;
+        auto contract = [&](auto npw_c) {
+          constexpr int npw = decltype(npw_c)::value;          // k-step pairs of this warp: compile-time, so that all loads are batched
+          uint4 bq[npw];
+          if constexpr (kind == K_MLP2) {
             const bf16* hrow = p.h + static_cast<size_t>(sq) * DFF + ksp * npw * 32 + 8 * tq;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < npw) bq[j] = ldv4u(hrow + 32 * j);
-            mma_tile<16>(p.packed + lw.w2 + static_cast<size_t>(rt) * (16 * DFF * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
+            for (int j = 0; j < npw; ++j) bq[j] = ldv4u(hrow + 32 * j);
+            mma_tile<npw>(p.packed + lw.w2 + static_cast<size_t>(rt) * (16 * DFF * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
           } else {
-            const int npw = NPD / KS;
             const int nsp = sm.nws[sq];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (j < npw) {
-                const int fb0 = 32 * (ksp * npw + j), hh = fb0 / HD, fo = fb0 - hh * HD + 8 * tq;
-                const float* pb = p.part + (static_cast<size_t>(sq) * H + hh) * kMaxSplits * PS;
-                float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY, Ls = 0.f;
-                for (int s4 = 0; s4 < nsp; s4 += 4) {
-                  float2 ml[4];
-                  float4 oa[4], ob[4];
+            for (int j = 0; j < npw; ++j) {
+              const int fb0 = 32 * (ksp * npw + j), hh = fb0 / HD, fo = fb0 - hh * HD + 8 * tq;
+              const float* pb = p.part + (static_cast<size_t>(sq) * H + hh) * kMaxSplits * PS;
+              float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY, Ls = 0.f;
+              for (int s4 = 0; s4 < nsp; s4 += 4) {
+                float2 ml[4];
+                float4 oa[4], ob[4];
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const bool on = s4 + u < nsp;
-                    const float* pp = pb + static_cast<size_t>(on ? s4 + u : s4) * PS;
-                    ml[u] = ldv2f(pp + HD);
-                    oa[u] = ldv4f(pp + fo);
-                    ob[u] = ldv4f(pp + fo + 4);
-                    if (!on) ml[u] = make_float2(-INFINITY, 0.f);
-                  }
-                  float Mn = M;
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) Mn = fmaxf(Mn, ml[u].x);
-                  const float corr = fast_exp2(M - Mn);                    // M == -inf: exp2(-inf) = 0 (Mn is finite: worker 0 folds the new token)
-                  Ls *= corr;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] *= corr;
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const float w = fast_exp2(ml[u].x - Mn);
-                    Ls = fmaf(ml[u].y, w, Ls);
-                    o[0] = fmaf(oa[u].x, w, o[0]); o[1] = fmaf(oa[u].y, w, o[1]); o[2] = fmaf(oa[u].z, w, o[2]); o[3] = fmaf(oa[u].w, w, o[3]);
-                    o[4] = fmaf(ob[u].x, w, o[4]); o[5] = fmaf(ob[u].y, w, o[5]); o[6] = fmaf(ob[u].z, w, o[6]); o[7] = fmaf(ob[u].w, w, o[7]);
-                  }
-                  M = Mn;
+                for (int u = 0; u < 4; ++u) {
+                  const bool on = s4 + u < nsp;
+                  const float* pp = pb + static_cast<size_t>(on ? s4 + u : s4) * PS;
+                  ml[u] = ldv2f(pp + HD);
+                  oa[u] = ldv4f(pp + fo);
+                  ob[u] = ldv4f(pp + fo + 4);
+                  if (!on) ml[u] = make_float2(-INFINITY, 0.f);
                 }
-                const float inv = Ls > 0.f ? __fdividef(1.0f, Ls) : 0.f;
-                bq[j] = make_uint4(pk(o[0] * inv, o[1] * inv), pk(o[2] * inv, o[3] * inv), pk(o[4] * inv, o[5] * inv), pk(o[6] * inv, o[7] * inv));
+                float Mn = M;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) Mn = fmaxf(Mn, ml[u].x);
+                const float corr = fast_exp2(M - Mn);                    // M == -inf: exp2(-inf) = 0 (Mn is finite: worker 0 folds the new token)
+                Ls *= corr;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] *= corr;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float w = fast_exp2(ml[u].x - Mn);
+                  Ls = fmaf(ml[u].y, w, Ls);
+                  o[0] = fmaf(oa[u].x, w, o[0]); o[1] = fmaf(oa[u].y, w, o[1]); o[2] = fmaf(oa[u].z, w, o[2]); o[3] = fmaf(oa[u].w, w, o[3]);
+                  o[4] = fmaf(ob[u].x, w, o[4]); o[5] = fmaf(ob[u].y, w, o[5]); o[6] = fmaf(ob[u].z, w, o[6]); o[7] = fmaf(ob[u].w, w, o[7]);
+                }
+                M = Mn;
               }
+              const float inv = Ls > 0.f ? __fdividef(1.0f, Ls) : 0.f;
+              bq[j] = make_uint4(pk(o[0] * inv, o[1] * inv), pk(o[2] * inv, o[3] * inv), pk(o[4] * inv, o[5] * inv), pk(o[6] * inv, o[7] * inv));
             }
-            mma_tile<16>(p.packed + lw.w_out + static_cast<size_t>(rt) * (16 * DM * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
+            mma_tile<npw>(p.packed + lw.w_out + static_cast<size_t>(rt) * (16 * DM * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
+          }
+        };
+        if (wactive) {
+          const int npw_rt = (kind == K_MLP2 ? DFF / 32 : NPD) / KS;
+          switch (npw_rt) {
+            case 1: contract(std::integral_constant<int, 1>{}); break;
+            case 2: contract(std::integral_constant<int, 2>{}); break;
+            case 4: contract(std::integral_constant<int, 4>{}); break;
+            case 8: contract(std::integral_constant<int, 8>{}); break;
+            default: contract(std::integral_constant<int, 16>{}); break;
           }
         }
         if (KS > 1) {
@@ -481,23 +504,51 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
         }
         if (wactive && ksp == 0) {
           float* dst = kind == K_OUT ? p.x1 : p.x;
+          bf16* dstb = kind == K_OUT ? p.x1b : p.xb;
+          float* dsts = kind == K_OUT ? p.sx1 : p.sx;
+          const float y0 = res[0] + (acc[0] + ba), y1 = res[1] + (acc[1] + ba), y2 = res[2] + (acc[2] + bb), y3 = res[3] + (acc[3] + bb);
           if (s0 < B) {
-            dst[static_cast<size_t>(s0) * DM + ra] = res[0] + (acc[0] + ba);
-            dst[static_cast<size_t>(s0) * DM + rb] = res[2] + (acc[2] + bb);
+            dst[static_cast<size_t>(s0) * DM + ra] = y0; dstb[static_cast<size_t>(s0) * DM + ra] = __float2bfloat16_rn(y0);
+            dst[static_cast<size_t>(s0) * DM + rb] = y2; dstb[static_cast<size_t>(s0) * DM + rb] = __float2bfloat16_rn(y2);
           }
           if (s1 < B) {
-            dst[static_cast<size_t>(s1) * DM + ra] = res[1] + (acc[1] + ba);
-            dst[static_cast<size_t>(s1) * DM + rb] = res[3] + (acc[3] + bb);
+            dst[static_cast<size_t>(s1) * DM + ra] = y1; dstb[static_cast<size_t>(s1) * DM + ra] = __float2bfloat16_rn(y1);
+            dst[static_cast<size_t>(s1) * DM + rb] = y3; dstb[static_cast<size_t>(s1) * DM + rb] = __float2bfloat16_rn(y3);
+          }
+          // (sum, sum of squares) of this tile's 16 rows per sequence: the next LayerNorm's statistics are assembled by its consumer
+          float a0 = y0 + y2, q0 = fmaf(y0, y0, y2 * y2), a1 = y1 + y3, q1 = fmaf(y1, y1, y3 * y3);
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+          }
+          if (qd == 0) {
+            if (s0 < B) *reinterpret_cast<float2*>(dsts + (static_cast<size_t>(s0) * NT16 + rt) * 2) = make_float2(a0, q0);
+            if (s1 < B) *reinterpret_cast<float2*>(dsts + (static_cast<size_t>(s1) * NT16 + rt) * 2) = make_float2(a1, q1);
           }
         }
         if (KS > 1 && it < n_items && sm.items[it].phase == ph) __syncthreads();     // `red` is reused by the next item
       }
     };
 
+    // Between the arrival at a grid barrier and the wait: pull the weight tile of this CTA's first item of the NEXT phase into L1
+    // (immutable data, independent of the barrier), so that the phase starts with ONE L2 round trip (its operand) instead of two
+    auto prefetch_next = [&](int ph_next) {
+      if (!(it < n_items && sm.items[it].phase == ph_next)) return;
+      const int rt = sm.items[it].row_tile;
+      const int kind = ph_next >= 5 * L ? K_HEAD : ph_next % 5, l = ph_next >= 5 * L ? 0 : ph_next / 5;
+      const GridLayer& lw = p.layers[l];
+      const size_t mat = kind == K_QKV ? lw.w_in : (kind == K_OUT ? lw.w_out : (kind == K_MLP1 ? lw.w1 : (kind == K_MLP2 ? lw.w2 : p.w_head)));
+      const int bytes = 32 * (kind == K_MLP2 ? DFF : DM);
+      const uint8_t* base = p.packed + mat + static_cast<size_t>(rt) * bytes;
+      for (int i = tid; i < bytes / 128; i += kThreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + i * 128));
+    };
+    auto sync_phase = [&](int ph_next) { stamp(); arrive(); prefetch_next(ph_next); wait(); stamp(); };
+
     for (int l = 0; l < L && alive; ++l) {
       const GridLayer& lw = p.layers[l];
-      phase_rows(5 * l + K_QKV, K_QKV, l);
-      arrive(); wait(); stamp();
+      phase_rows(5 * l + K_QKV, std::integral_constant<int, K_QKV>{}, l);
+      sync_phase(5 * l + K_ATT);
       if (!alive) break;
       // ---------------- attention: this warp's (sequence, head, key range) unit ----------------
       if (at_b >= 0) {
@@ -510,27 +561,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
         __syncwarp();
         const size_t hb = (static_cast<size_t>(at_b) * H + at_h) * p.Tvt * HD;
         uint4 kq0[4][HD / 32], vq0[HD / 8];
-        attn_tc<HD, false>(lw.kh + hb, lw.vt + hb, at_len, at_wi, at_nws, lane, sm.qs[warp], sm.kn[warp], sm.vn[warp], at_wi == 0,
+        attn_tc<HD, false, true>(lw.kh + hb, lw.vt + hb, at_len, at_wi, at_nws, lane, sm.qs[warp], sm.kn[warp], sm.vn[warp], at_wi == 0,
                            sm.part[warp], kq0, vq0);
         __syncwarp();
         float* dst = p.part + ((static_cast<size_t>(at_b) * H + at_h) * kMaxSplits + at_wi) * PS;
         if (lane < HD / 4) *reinterpret_cast<float4*>(dst + lane * 4) = *reinterpret_cast<const float4*>(&sm.part[warp][lane * 4]);
         if (lane == 0) *reinterpret_cast<float2*>(dst + HD) = make_float2(sm.part[warp][64], sm.part[warp][65]);
       }
-      arrive(); wait(); stamp();
+      sync_phase(5 * l + K_OUT);
       if (!alive) break;
-      phase_split(5 * l + K_OUT, K_OUT, l);
-      arrive(); wait(); stamp();
+      phase_split(5 * l + K_OUT, std::integral_constant<int, K_OUT>{}, l);
+      sync_phase(5 * l + K_MLP1);
       if (!alive) break;
-      phase_rows(5 * l + K_MLP1, K_MLP1, l);
-      arrive(); wait(); stamp();
+      phase_rows(5 * l + K_MLP1, std::integral_constant<int, K_MLP1>{}, l);
+      sync_phase(5 * l + K_MLP2);
+      tr = nullptr;
       if (!alive) break;
-      phase_split(5 * l + K_MLP2, K_MLP2, l);
-      arrive(); wait(); stamp();
+      phase_split(5 * l + K_MLP2, std::integral_constant<int, K_MLP2>{}, l);
+      sync_phase(5 * l + 5);
     }
     if (!alive) break;
-    phase_rows(5 * L + K_QKV, K_HEAD, 0);
-    arrive(); wait(); stamp();
+    phase_rows(5 * L + K_QKV, std::integral_constant<int, K_HEAD>{}, 0);
+    sync_phase(5 * L + 1);
     if (!alive) break;
 
     // ---------------- sampler (api_cache.py:169-181): CTA b owns sequence b ----------------
@@ -539,7 +591,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
       const float* row = p.logits + static_cast<size_t>(b) * p.ldl;
       const int V = p.V, k = sp.top_k;
       const uint64_t seq = sp.seq_base + static_cast<uint64_t>(p.st.seq_idx ? p.st.seq_idx[b] : b);
+      // the sequence's state words are requested first: their L2 round trips overlap the logits loads
       const uint32_t nn = static_cast<uint32_t>(ldvi(p.st.n_new + b));
+      const int out_pos = ldvi(p.st.out_len + b), budget = ldvi(p.st.max_new + b);
       int tok = -1;
       const bool fast = V <= kThreads * kSampMaxPer && k >= 1 && k <= kThreads && k < V;
       bool done = false;
@@ -547,15 +601,24 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
         tok = p.forced[static_cast<size_t>(b) * p.forced_stride + step];
         done = true;
       } else if (fast) {
+        // logits / temperature (api_cache.py:169) in registers: element 4 (tid + 256 j) + e
         float z[kSampMaxPer];
+        const float inv_temp = 1.0f / sp.temperature;
+#pragma unroll
+        for (int j = 0; j < kSampMaxPer / 4; ++j) {
+          const int i0 = 4 * (tid + kThreads * j);
+          float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i0 < V) q4 = ldv4f(row + i0);                                   // rows are padded to a multiple of 16 floats
+          z[4 * j] = i0 < V ? q4.x * inv_temp : -INFINITY;
+          z[4 * j + 1] = i0 + 1 < V ? q4.y * inv_temp : -INFINITY;
+          z[4 * j + 2] = i0 + 2 < V ? q4.z * inv_temp : -INFINITY;
+          z[4 * j + 3] = i0 + 3 < V ? q4.w * inv_temp : -INFINITY;
+        }
         float tmax = -INFINITY;
         int timax = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < kSampMaxPer; ++j) {
-          const int i = tid + kThreads * j;
-          z[j] = i < V ? ldvf(row + i) / sp.temperature : -INFINITY;
-          if (z[j] > tmax) { tmax = z[j]; timax = i; }               // ascending i: the lowest index wins ties
-        }
+        for (int j = 0; j < kSampMaxPer; ++j)
+          if (z[j] > tmax) { tmax = z[j]; timax = 4 * (tid + kThreads * (j >> 2)) + (j & 3); }   // ascending index: the lowest index wins ties
         if (k == 1) {
           // greedy: arg-max, lowest index on ties (torch.topk / multinomial over a one-hot distribution)
 #pragma unroll
@@ -574,25 +637,34 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
           tok = bi;
           done = true;
         } else {
-          // threshold = the k-th largest per-thread maximum: a lower bound of the k-th largest logit, so {z >= tau} is a superset
-          // of the top-k
-          sm.mx[tid] = tmax;
-          if (tid == 0) sm.flag = 0;
-          __syncthreads();
-          int rank = 0;
-#pragma unroll 8
-          for (int u4 = 0; u4 < kThreads / 4; ++u4) {
-            const float4 m4 = *reinterpret_cast<const float4*>(&sm.mx[4 * u4]);
-            const int u = 4 * u4;
-            rank += (m4.x > tmax || (m4.x == tmax && u < tid)) + (m4.y > tmax || (m4.y == tmax && u + 1 < tid)) +
-                    (m4.z > tmax || (m4.z == tmax && u + 2 < tid)) + (m4.w > tmax || (m4.w == tmax && u + 3 < tid));
+          // threshold = the k-th largest of G group maxima (G = 64 quads of threads for k <= 64, else the 256 threads): a lower
+          // bound of the k-th largest logit, so {z >= tau} is a (small) superset of the top-k
+          const int G = k <= 64 ? 64 : kThreads;
+          float gm = tmax;
+          if (G == 64) {
+            gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 1));
+            gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 2));
+            if (tq == 0) sm.mx[tid >> 2] = gm;
+          } else {
+            sm.mx[tid] = gm;
           }
-          if (rank == k - 1) sm.tau = tmax;
+          __syncthreads();
+          if (tid < G) {
+            const float mine = sm.mx[tid];
+            int rank = 0;
+            for (int u4 = 0; u4 < G / 4; ++u4) {
+              const float4 m4 = *reinterpret_cast<const float4*>(&sm.mx[4 * u4]);
+              const int u = 4 * u4;
+              rank += (m4.x > mine || (m4.x == mine && u < tid)) + (m4.y > mine || (m4.y == mine && u + 1 < tid)) +
+                      (m4.z > mine || (m4.z == mine && u + 2 < tid)) + (m4.w > mine || (m4.w == mine && u + 3 < tid));
+            }
+            if (rank == k - 1) sm.tau = mine;
+          }
           __syncthreads();
           const float tau = sm.tau;
           int cnt = 0;
 #pragma unroll
-          for (int j = 0; j < kSampMaxPer; ++j) cnt += (z[j] >= tau) && (tid + kThreads * j < V);
+          for (int j = 0; j < kSampMaxPer; ++j) cnt += z[j] >= tau && 4 * (tid + kThreads * (j >> 2)) + (j & 3) < V;
           int inc = cnt;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
@@ -612,7 +684,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
             int pos = base + inc - cnt;
 #pragma unroll
             for (int j = 0; j < kSampMaxPer; ++j)
-              if (z[j] >= tau && tid + kThreads * j < V) sm.cand[pos++] = make_uint2(__float_as_uint(z[j]), static_cast<uint32_t>(tid + kThreads * j));
+              {
+                const int idx = 4 * (tid + kThreads * (j >> 2)) + (j & 3);
+                if (z[j] >= tau && idx < V) sm.cand[pos++] = make_uint2(__float_as_uint(z[j]), static_cast<uint32_t>(idx));
+              }
             __syncthreads();
             // exact rank of every candidate: value descending, index ascending
             for (int c = tid; c < total; c += kThreads) {
@@ -673,7 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
       }
       if (tid == 0) {
         tok = min(max(tok, 0), p.V - 1);                       // never index the embedding table out of range
-        const int pos = ldvi(p.st.out_len + b);
+        const int pos = out_pos;
         p.st.out_ids[static_cast<size_t>(b) * p.st.out_stride + pos] = tok;      // api_cache.py:179
         if (p.st.step_ns && b == 0) p.st.step_ns[step] = ptx::global_timer_ns();   // per-token latency read-out
         p.st.out_len[b] = pos + 1;
@@ -681,13 +756,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
         p.st.lens[b] = sm.len[b] + 1;
         const int n = static_cast<int>(nn) + 1;
         p.st.n_new[b] = n;
-        if (tok == sp.eos_id || n >= ldvi(p.st.max_new + b)) {             // api_cache.py:181
+        const bool fin_now = tok == sp.eos_id || n >= budget;               // api_cache.py:181
+        if (fin_now) {
           p.st.finished[b] = 1;
           atomicAdd(p.ctrl + 1, 1u);
         }
+        sm.next_tok = fin_now ? -1 : tok;
       }
+      __syncthreads();
+      if (sm.next_tok >= 0) embed(b, sm.next_tok);                  // the next step's input row
     }
-    arrive(); wait(); stamp();
+    sync_phase(0);
     if (!alive) break;
     if (p.early_exit && static_cast<int>(ldvu(p.ctrl + 1)) >= n_active0) break;
   }

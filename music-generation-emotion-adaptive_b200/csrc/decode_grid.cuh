@@ -49,6 +49,8 @@ struct GridParams {
   // activations of the current step, [kMaxSeqs][...] (global memory; L2 is the exchange medium between the phases)
   float* x;                            // residual stream entering a block (written by mlp.2)
   float* x1;                           // residual stream after the attention sub-layer
+  bf16 *xb, *x1b;                      // bf16 copies (GEMM operands of the consumers)
+  float *sx, *sx1;                     // [seq][D / 16][2] per-tile (sum, sum of squares): LayerNorm statistics assembled by the consumer
   float* q;                            // [seq][D] fp32, pre-scaled by log2(e) / sqrt(hd)
   bf16* knew;                          // [seq][D] the new token's K / V rows (folded by the first attention worker)
   bf16* vnew;
@@ -60,6 +62,7 @@ struct GridParams {
   int L, V, B, H, n_steps, Tvt, ldl, n_cta;
   int tn[8], ks[8];                    // per phase kind: n-tiles per item x k-splits (tn * ks == 8)
   int early_exit;
+  int fence_mode;                      // debug: 1 = __threadfence() + atomicAdd (invalidates L1) instead of red.release
   float* dbg_logits;                   // parity path: [kept steps][B][V]
   const int32_t* dbg_slot;             // optional [n_steps] -> row block of dbg_logits, -1 = not kept
   const int32_t* forced;               // teacher forcing: next token of sequence b after step t = forced[b * stride + t]

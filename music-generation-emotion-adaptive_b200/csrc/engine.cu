@@ -141,6 +141,7 @@ struct mg_engine {
 
   // grid-synchronous decode kernel (decode_grid.cu): bf16, d_model 256 / 512, <= 64 sequences
   bool grid_ok = false, use_grid = false, last_run_grid = false;
+  int grid_mode = 2;                           // MG_GRID: 0 = never, 1 = wherever eligible, unset = where the cluster kernel does not take the geometry
   uint8_t* d_grid_packed = nullptr;
   grid::GridLayer grid_layers[grid::kMaxLayers]{};
   size_t grid_w_head = 0;
@@ -149,7 +150,8 @@ struct mg_engine {
   int grid_plan_B = -1, grid_ctas = 0, grid_ldl = 0;
   int grid_tn[8]{}, grid_ks[8]{};
   float *g_x = nullptr, *g_x1 = nullptr, *g_q = nullptr, *g_logits = nullptr, *g_vals = nullptr, *g_part = nullptr;
-  bf16 *g_knew = nullptr, *g_vnew = nullptr, *g_h = nullptr;
+  bf16 *g_knew = nullptr, *g_vnew = nullptr, *g_h = nullptr, *g_xb = nullptr, *g_x1b = nullptr;
+  float *g_sx = nullptr, *g_sx1 = nullptr;
   unsigned* d_grid_ctrl = nullptr;
   unsigned* h_grid_ctrl = nullptr;             // pinned
   unsigned long long* d_grid_prof = nullptr;
@@ -542,6 +544,7 @@ static int alloc_persistent_caches(mg_engine* e) {
 int setup_grid(mg_engine* e) {
   const mg_geometry& g = e->geo;
   e->grid_ok = false;
+  if (e->grid_mode == 2) e->use_grid = !e->mega_ok && e->use_mega;   // MG_NO_MEGA=1 means "no persistent kernel": the step graph
   if (!e->use_grid || e->dtype != MG_DTYPE_BF16 || !grid::grid_eligible(g.d_model, g.d_ff, g.n_head, g.n_layer, g.vocab_size)) return MG_OK;
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
@@ -571,7 +574,9 @@ int setup_grid(mg_engine* e) {
         {reinterpret_cast<void**>(&e->g_q), sizeof(float) * S * D}, {reinterpret_cast<void**>(&e->g_knew), sizeof(bf16) * S * D},
         {reinterpret_cast<void**>(&e->g_vnew), sizeof(bf16) * S * D}, {reinterpret_cast<void**>(&e->g_h), sizeof(bf16) * S * g.d_ff},
         {reinterpret_cast<void**>(&e->g_logits), sizeof(float) * S * e->grid_ldl}, {reinterpret_cast<void**>(&e->g_vals), sizeof(float) * S * e->grid_ldl},
-        {reinterpret_cast<void**>(&e->g_part), sizeof(float) * part_floats}, {reinterpret_cast<void**>(&e->d_grid_ctrl), 64}};
+        {reinterpret_cast<void**>(&e->g_part), sizeof(float) * part_floats},
+        {reinterpret_cast<void**>(&e->g_xb), sizeof(bf16) * S * D}, {reinterpret_cast<void**>(&e->g_x1b), sizeof(bf16) * S * D},
+        {reinterpret_cast<void**>(&e->g_sx), sizeof(float) * S * (D / 16) * 2}, {reinterpret_cast<void**>(&e->g_sx1), sizeof(float) * S * (D / 16) * 2}, {reinterpret_cast<void**>(&e->d_grid_ctrl), 64}};
     for (auto& b : bufs) {
       MG_TRY(e->dmalloc(reinterpret_cast<uint8_t**>(b.p), b.bytes));
       MG_CUDA_OK(cudaMemsetAsync(*b.p, 0, b.bytes, e->stream));
@@ -617,17 +622,19 @@ bool run_decode_grid(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   p.head_b = e->head_b; p.sp = e->d_sp; p.st = e->st;
   p.x = e->g_x; p.x1 = e->g_x1; p.q = e->g_q; p.knew = e->g_knew; p.vnew = e->g_vnew; p.h = e->g_h; p.logits = e->g_logits;
   p.vals = e->g_vals; p.part = e->g_part; p.ctrl = e->d_grid_ctrl;
+  p.xb = e->g_xb; p.x1b = e->g_x1b; p.sx = e->g_sx; p.sx1 = e->g_sx1;
   p.L = g.n_layer; p.V = g.vocab_size; p.B = B; p.H = g.n_head; p.n_steps = e->cur_steps; p.Tvt = mega_tvt(e->max_seq);
   p.ldl = e->grid_ldl; p.n_cta = e->grid_ctas;
   for (int k = 0; k < 8; ++k) { p.tn[k] = e->grid_tn[k]; p.ks[k] = e->grid_ks[k]; }
   p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
   p.dbg_logits = dbg_logits; p.dbg_slot = dbg_slot; p.forced = forced; p.forced_stride = forced_stride;
+  p.fence_mode = std::getenv("MG_GRID_FENCE") ? std::atoi(std::getenv("MG_GRID_FENCE")) : 0;
   p.prof = nullptr; p.prof_step = -1;
-  const int n_stamps = 5 * g.n_layer + 3;
+  const int n_stamps = 2 * (5 * g.n_layer + 2) + 1;
   if (const char* ps = std::getenv("MG_GRID_PROF_STEP")) {          // debug: phase timeline of CTA 0 in one decode step -> stderr
-    if (!e->d_grid_prof && e->dmalloc(&e->d_grid_prof, 64 * sizeof(unsigned long long)) != MG_OK) e->d_grid_prof = nullptr;
+    if (!e->d_grid_prof && e->dmalloc(&e->d_grid_prof, 128 * sizeof(unsigned long long)) != MG_OK) e->d_grid_prof = nullptr;
     if (e->d_grid_prof) {
-      cudaMemsetAsync(e->d_grid_prof, 0, 64 * sizeof(unsigned long long), e->stream);
+      cudaMemsetAsync(e->d_grid_prof, 0, 128 * sizeof(unsigned long long), e->stream);
       p.prof = e->d_grid_prof; p.prof_step = std::atoi(ps);
     }
   }
@@ -644,11 +651,13 @@ bool run_decode_grid(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   if (*rc == MG_OK) *rc = grid::launch_decode_grid(e->stream, p, g.d_model, hd);
   if (*rc == MG_OK && !cuda_ok(cudaMemcpyAsync(e->h_grid_ctrl, e->d_grid_ctrl, 64, cudaMemcpyDeviceToHost, e->stream), "grid status copy")) return true;
   if (p.prof && *rc == MG_OK) {
-    unsigned long long h[64];
+    unsigned long long h[128];
     cudaStreamSynchronize(e->stream);
     cudaMemcpy(h, e->d_grid_prof, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[grid prof] step %d, CTA 0 (ns since step start; then per layer: qkv attn out mlp1 mlp2; head; sampler):", p.prof_step);
-    for (int i = 0; i < n_stamps && i < 64 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
+    fprintf(stderr, "[grid prof] step %d, CTA 0, ns since step start: partition done | per phase (qkv attn out mlp1 mlp2 per layer, head, sampler): work done, barrier passed:", p.prof_step);
+    for (int i = 0; i < n_stamps && i < 128 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[0]);
+    fprintf(stderr, "\n[grid prof] mlp.0 of layer 1, CTA 0 thread 0, SM cycles: entry | statistics landed | operand built | MMAs done | epilogue issued (arrive) | CTA barrier | released (MEMBAR + RED) | poll done:");
+    for (int i = 96; i < 112 && h[i]; ++i) fprintf(stderr, " %lld", (long long)(h[i] - h[96]));
     fprintf(stderr, "\n");
   }
   e->t_steps = e->cur_steps;
@@ -1114,7 +1123,8 @@ int mg_engine_create(const mg_geometry* geo, int device, int dtype_mode, int max
   // The weight-stationary flow kernel (decode_flow.cu) is OPT-IN (MG_FLOW=1): parity-green, but measured slower than the cluster
   // kernel on every BASELINE configuration (profiles/r2b_flow_*).
   const char* env_grid = std::getenv("MG_GRID");
-  e->use_grid = env_grid && env_grid[0] == '1';
+  e->grid_mode = !env_grid ? 2 : (env_grid[0] == '1' ? 1 : 0);
+  e->use_grid = e->grid_mode == 1;
   const char* env_flow = std::getenv("MG_FLOW");
   e->use_flow = env_flow && env_flow[0] == '1';
   {
@@ -1359,7 +1369,7 @@ static int step_logits_impl(mg_engine* e, const int32_t* ids, const int32_t* off
   }
   const bool is_bf16 = e->dtype == MG_DTYPE_BF16;
   MG_TRY(is_bf16 ? prefill<bf16>(e) : prefill<float>(e));
-  if (is_bf16 && (e->mega_ok || e->flow_ok)) {
+  if (is_bf16 && (e->mega_ok || e->flow_ok || e->grid_ok)) {
     // the persistent kernels in teacher-forcing mode: same code path as mg_run, logits of the kept steps dumped
     float* d_lg = nullptr;
     int32_t* d_slot = nullptr;
