@@ -84,11 +84,11 @@ __device__ __forceinline__ int ldvb(const uint8_t* p) {
 // weights: immutable for the whole launch, read-only path, allocate in L1
 __device__ __forceinline__ uint4 ldw16(const uint8_t* p) {
   uint4 r;
-  asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));   // not volatile: the compiler may hoist / batch them
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
@@ -110,6 +110,7 @@ struct GridSmem {
   int fin[kMaxSeqs];
   int tok[kMaxSeqs];
   int total_units;
+  int upc;                             // attention units per CTA in this step (consecutive units = consecutive warps of one CTA)
   // sampler
   alignas(16) float mx[kThreads];
   alignas(16) uint2 cand[kCandCap];
@@ -129,14 +130,27 @@ struct GridSmem {
 // holds columns 32 j + 8 t .. + 7 as ONE 16-byte load, (x, y) feed MMA 2 j, (z, w) MMA 2 j + 1.
 template <int NP>
 __device__ __forceinline__ void mma_tile(const uint8_t* __restrict__ tile, int lane, const uint4 (&bq)[NP], int np, float (&acc)[4]) {
+  // groups of G k-step pairs; the loads of group g + 1 are issued before the MMAs of group g (asm volatile keeps this order: left to
+  // itself the compiler sinks every load next to its MMA to save registers, and the tile costs one L1 / L2 round trip per pair)
+  constexpr int G = NP >= 4 ? 4 : NP, NG = NP / G;
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
   const uint8_t* tp = tile + lane * 16;
+  uint4 wa[2][2 * G];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    if (j < np) {
-      const uint4 w0 = ldw16(tp + j * 1024), w1 = ldw16(tp + j * 1024 + 512);
-      mma16816(a0, w0, bq[j].x, bq[j].y);
-      mma16816(a1, w1, bq[j].z, bq[j].w);
+  for (int i = 0; i < G; ++i) { wa[0][2 * i] = ldw16(tp + i * 1024); wa[0][2 * i + 1] = ldw16(tp + i * 1024 + 512); }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    if (g + 1 < NG) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        wa[(g + 1) & 1][2 * i] = ldw16(tp + ((g + 1) * G + i) * 1024);
+        wa[(g + 1) & 1][2 * i + 1] = ldw16(tp + ((g + 1) * G + i) * 1024 + 512);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      mma16816(a0, wa[g & 1][2 * i], bq[g * G + i].x, bq[g * G + i].y);
+      mma16816(a1, wa[g & 1][2 * i + 1], bq[g * G + i].z, bq[g * G + i].w);
     }
   }
 #pragma unroll
@@ -158,40 +172,44 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
   for (int i = tid; i < n_items; i += kThreads) sm.items[i] = p.items[static_cast<size_t>(cta) * kMaxItems + i];
   const SampleParams sp = *p.sp;
   const float scale_log2 = kLog2e / sqrtf(static_cast<float>(HD));
+  if (tid == 0) sm.flag = 1;
   const int n_active0 = __syncthreads_count(tid < B && p.st.finished[tid] == 0);
   unsigned* const bar = p.ctrl;
-  unsigned bar_target = 0;
+  unsigned epoch = 0;                    // grid barriers passed so far
   bool alive = true;
   unsigned long long* tr = nullptr;     // fine trace (clock64) of one dense phase of CTA 0: p.prof[96..]
   auto trace = [&]() { if (tr) *tr++ = clock64(); };
 
   // ---- grid barrier: arrive (release by one thread behind the CTA barrier) / wait (one polling lane per warp) ----
+  // Grid barrier: one release-only RED per CTA on a monotonic counter (behind the CTA barrier), ONE polling thread per CTA.
+  // Measured alternatives (profiles/r2n_grid_barrier_ab.txt): a poller per warp 108 -> 132 us per step (the arrivals queue behind the
+  // polls in the counter's L2 slice); last arriver publishes the epoch in 16 flag lines that the CTAs poll instead 108 -> 114 (one more
+  // L2 hop); __threadfence() + atomicAdd invalidates this SM's L1 (MEMBAR.SC + CCTL.IVALL), i.e. the weight tiles it keeps there.
   auto arrive = [&]() {
     trace();
     __syncthreads();
     trace();
-    // release only: __threadfence() (MEMBAR.SC + CCTL.IVALL) would invalidate this SM's L1, i.e. the weight tiles it keeps there
+    ++epoch;
     if (tid == 0) {
       if (p.fence_mode == 1) { __threadfence(); atomicAdd(bar, 1u); }
       else asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
     }
     trace();
-    bar_target += static_cast<unsigned>(n_cta);
   };
   auto wait = [&]() {
-    // ONE polling thread per CTA (a poller per warp = 1184 loads hammering the counter's L2 slice delays the arrivals themselves)
     if (tid == 0) {
+      const unsigned target = epoch * static_cast<unsigned>(n_cta);
       unsigned spins = 0;
       unsigned long long t0 = 0;
       int ok = 1;
-      while (ldvu(bar) < bar_target) {
+      while (ldvu(bar) < target) {
         if ((++spins & 0xfffu) == 0) {
           const unsigned long long now = ptx::global_timer_ns();
           if (t0 == 0) t0 = now;
           else if (now - t0 > kWatchdogNs || ldvu(p.ctrl + 2) != 0) { ok = 0; atomicExch(p.ctrl + 2, 1u); break; }
         }
       }
-      sm.flag = ok;
+      if (!ok) sm.flag = 0;
       trace();
     }
     __syncthreads();
@@ -259,25 +277,30 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
       const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
       sm.nws[lane] = w0; sm.nws[lane + 32] = w1;
       sm.istart[lane] = i0 - w0 * H; sm.istart[lane + 32] = tot0 + i1 - w1 * H;
-      if (lane == 0) sm.total_units = tot * H;
+      if (lane == 0) { sm.total_units = tot * H; sm.upc = max(1, (tot * H + n_cta - 1) / n_cta); }
     }
     __syncthreads();
-    // this warp's attention unit of the step (the same for every layer)
-    int at_b = -1, at_h = 0, at_wi = 0, at_nws = 1, at_len = 0;
+    // this warp's attention unit of the step (the same for every layer).  Units are numbered sequence-major, head, key range
+    // fastest, and dealt in runs of `upc` consecutive units per CTA: the key ranges of one (sequence, head) sit in neighbouring warps
+    // of one CTA (two at a run boundary) and are merged in shared memory before anything is written
+    int at_b = -1, at_h = 0, at_wi = 0, at_nws = 1, at_len = 0, at_run = 0, at_slot = 0;
+    const int upc = sm.upc;
     {
-      const int gw = warp * n_cta + cta;
-      if (gw < sm.total_units) {
-        const bool in0 = sm.nws[lane] > 0 && sm.istart[lane] <= gw && gw < sm.istart[lane] + sm.nws[lane] * H;
-        const bool in1 = sm.nws[lane + 32] > 0 && sm.istart[lane + 32] <= gw && gw < sm.istart[lane + 32] + sm.nws[lane + 32] * H;
-        const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
-        at_b = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : -1);
-        if (at_b >= 0) {
-          const int r = gw - sm.istart[at_b];
-          at_nws = sm.nws[at_b];
-          at_h = r % H;
-          at_wi = r / H;
-          at_len = sm.len[at_b];
-        }
+      const int gw = cta * upc + warp;
+      const bool mine = warp < upc && gw < sm.total_units;
+      const bool in0 = mine && sm.nws[lane] > 0 && sm.istart[lane] <= gw && gw < sm.istart[lane] + sm.nws[lane] * H;
+      const bool in1 = mine && sm.nws[lane + 32] > 0 && sm.istart[lane + 32] <= gw && gw < sm.istart[lane + 32] + sm.nws[lane + 32] * H;
+      const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+      at_b = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : -1);
+      if (at_b >= 0) {
+        const int r = gw - sm.istart[at_b];
+        at_nws = sm.nws[at_b];
+        at_h = r / at_nws;
+        at_wi = r - at_h * at_nws;
+        at_len = sm.len[at_b];
+        // the first warp of a run of key ranges of the same (sequence, head) inside this CTA merges the run
+        if (warp == 0 || at_wi == 0) at_run = min(at_nws - at_wi, min(upc - warp, sm.total_units - gw));
+        at_slot = cta - (gw - at_wi) / upc;              // partial index = CTAs since the one that holds key range 0
       }
     }
     stamp();
@@ -290,46 +313,37 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
       if (!(it < n_items && sm.items[it].phase == ph)) return;
       const bool wactive = 8 * warp < B;
       uint4 bq[NPD];
+      float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
       if (prof_on && step == p.prof_step && kind == K_MLP1 && l == 1) tr = p.prof + 96;
       trace();
       if (wactive) {
-        // operand = the bf16 copy of the residual stream its producer left next to the fp32 one; LayerNorm from the producer's
-        // per-tile (sum, sum of squares) -- no pass over the row for the statistics, half the bytes of an fp32 row
+        // operand = the bf16 copy of the residual stream its producer left next to the fp32 one, used AS IS: LayerNorm is folded
+        // into the packed weights (GridLayer) and finished in the epilogue from the row statistics
         const int sq = min(s_own, B - 1);
         const bf16* row = (kind == K_MLP1 ? p.x1b : p.xb) + static_cast<size_t>(sq) * DM + 8 * tq;
-        uint4 raw[NPD];
 #pragma unroll
-        for (int j = 0; j < NPD; ++j) raw[j] = ldv4u(row + 32 * j);
+        for (int j = 0; j < NPD; ++j) bq[j] = ldv4u(row + 32 * j);
         if constexpr (kind != K_HEAD) {
-          const GridLayer& lw = p.layers[l];
-          const float* gw = kind == K_QKV ? lw.ln1w : lw.ln2w;
-          const float* gb = kind == K_QKV ? lw.ln1b : lw.ln2b;
-          const float* st = (kind == K_MLP1 ? p.sx1 : p.sx) + static_cast<size_t>(sq) * (2 * NT16) + 2 * tq;
-          float sum = 0.f, ssq = 0.f;
+          // row statistics of this lane's two accumulator sequences from the producer's per-tile (sum, sum of squares): the eight
+          // lanes of a column group read different tiles
+          const float* stp = (kind == K_MLP1 ? p.sx1 : p.sx);
+          const float* st_a = stp + static_cast<size_t>(min(sa, B - 1)) * (2 * NT16) + 2 * qd;
+          const float* st_b = stp + static_cast<size_t>(min(sb, B - 1)) * (2 * NT16) + 2 * qd;
+          float sum_a = 0.f, ssq_a = 0.f, sum_b = 0.f, ssq_b = 0.f;
 #pragma unroll
-          for (int i = 0; i < NT16 / 4; ++i) {
-            const float2 t2 = ldv2f(st + 8 * i);
-            sum += t2.x; ssq += t2.y;
+          for (int i = 0; i < NT16 / 8; ++i) {
+            const float2 ta = ldv2f(st_a + 16 * i), tb = ldv2f(st_b + 16 * i);
+            sum_a += ta.x; ssq_a += ta.y; sum_b += tb.x; ssq_b += tb.y;
           }
-          sum += __shfl_xor_sync(0xffffffffu, sum, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
-          sum += __shfl_xor_sync(0xffffffffu, sum, 2); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            sum_a += __shfl_xor_sync(0xffffffffu, sum_a, o); ssq_a += __shfl_xor_sync(0xffffffffu, ssq_a, o);
+            sum_b += __shfl_xor_sync(0xffffffffu, sum_b, o); ssq_b += __shfl_xor_sync(0xffffffffu, ssq_b, o);
+          }
+          mean_a = sum_a * (1.0f / DM); mean_b = sum_b * (1.0f / DM);
+          rstd_a = rsqrtf(fmaxf(ssq_a * (1.0f / DM) - mean_a * mean_a, 0.f) + 1e-5f);
+          rstd_b = rsqrtf(fmaxf(ssq_b * (1.0f / DM) - mean_b * mean_b, 0.f) + 1e-5f);
           trace();
-          const float mean = sum * (1.0f / DM);
-          const float rstd = rsqrtf(fmaxf(ssq * (1.0f / DM) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll
-          for (int j = 0; j < NPD; ++j) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(gw + 32 * j + 8 * tq)), w1 = __ldg(reinterpret_cast<const float4*>(gw + 32 * j + 8 * tq + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(gb + 32 * j + 8 * tq)), b1 = __ldg(reinterpret_cast<const float4*>(gb + 32 * j + 8 * tq + 4));
-            float vj[8];
-            unpack8(raw[j], vj);
-            bq[j] = make_uint4(pk((vj[0] - mean) * rstd * w0.x + b0.x, (vj[1] - mean) * rstd * w0.y + b0.y),
-                               pk((vj[2] - mean) * rstd * w0.z + b0.z, (vj[3] - mean) * rstd * w0.w + b0.w),
-                               pk((vj[4] - mean) * rstd * w1.x + b1.x, (vj[5] - mean) * rstd * w1.y + b1.y),
-                               pk((vj[6] - mean) * rstd * w1.z + b1.z, (vj[7] - mean) * rstd * w1.w + b1.w));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < NPD; ++j) bq[j] = raw[j];           // no final LayerNorm (api_cache.py:105)
         }
       }
       trace();
@@ -341,10 +355,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
         float acc[4];
         if constexpr (kind == K_QKV) {
           const GridLayer& lw = p.layers[l];
-          const float ba = __ldg(lw.b_in + ra), bb = __ldg(lw.b_in + rb);
+          const float ca = __ldg(lw.c_in + ra), cb = __ldg(lw.c_in + rb), da = __ldg(lw.d_in + ra), db = __ldg(lw.d_in + rb);
           mma_tile<NPD>(p.packed + lw.w_in + static_cast<size_t>(rt) * (16 * DM * 2), lane, bq, NPD, acc);
           const int part = ra / DM, fa = ra - part * DM, fb = fa + 8;        // a tile never straddles q | k | v
-          const float va[2] = {acc[0] + ba, acc[1] + ba}, vb[2] = {acc[2] + bb, acc[3] + bb};
+          const float va[2] = {fmaf(rstd_a, acc[0] - mean_a * ca, da), fmaf(rstd_b, acc[1] - mean_b * ca, da)};
+          const float vb[2] = {fmaf(rstd_a, acc[2] - mean_a * cb, db), fmaf(rstd_b, acc[3] - mean_b * cb, db)};
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int s = sa + e;
@@ -374,16 +389,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
           }
         } else if constexpr (kind == K_MLP1) {
           const GridLayer& lw = p.layers[l];
-          const float ba = __ldg(lw.b1 + ra), bb = __ldg(lw.b1 + rb);
+          const float ca = __ldg(lw.c_1 + ra), cb = __ldg(lw.c_1 + rb), da = __ldg(lw.d_1 + ra), db = __ldg(lw.d_1 + rb);
           mma_tile<NPD>(p.packed + lw.w1 + static_cast<size_t>(rt) * (16 * DM * 2), lane, bq, NPD, acc);
           if (tr) { asm volatile("" ::"f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3])); trace(); }
           if (sa < B) {
-            p.h[static_cast<size_t>(sa) * DFF + ra] = __float2bfloat16_rn(gelu_erf_f(acc[0] + ba));
-            p.h[static_cast<size_t>(sa) * DFF + rb] = __float2bfloat16_rn(gelu_erf_f(acc[2] + bb));
+            p.h[static_cast<size_t>(sa) * DFF + ra] = __float2bfloat16_rn(gelu_erf_f(fmaf(rstd_a, acc[0] - mean_a * ca, da)));
+            p.h[static_cast<size_t>(sa) * DFF + rb] = __float2bfloat16_rn(gelu_erf_f(fmaf(rstd_a, acc[2] - mean_a * cb, db)));
           }
           if (sb < B) {
-            p.h[static_cast<size_t>(sb) * DFF + ra] = __float2bfloat16_rn(gelu_erf_f(acc[1] + ba));
-            p.h[static_cast<size_t>(sb) * DFF + rb] = __float2bfloat16_rn(gelu_erf_f(acc[3] + bb));
+            p.h[static_cast<size_t>(sb) * DFF + ra] = __float2bfloat16_rn(gelu_erf_f(fmaf(rstd_b, acc[1] - mean_b * ca, da)));
+            p.h[static_cast<size_t>(sb) * DFF + rb] = __float2bfloat16_rn(gelu_erf_f(fmaf(rstd_b, acc[3] - mean_b * cb, db)));
           }
         } else {
           const float ba = ra < p.V ? __ldg(p.head_b + ra) : 0.f, bb = rb < p.V ? __ldg(p.head_b + rb) : 0.f;
@@ -442,23 +457,27 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
             for (int j = 0; j < npw; ++j) bq[j] = ldv4u(hrow + 32 * j);
             mma_tile<npw>(p.packed + lw.w2 + static_cast<size_t>(rt) * (16 * DFF * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
           } else {
-            const int nsp = sm.nws[sq];
+            const int nws_q = sm.nws[sq];
 #pragma unroll
             for (int j = 0; j < npw; ++j) {
               const int fb0 = 32 * (ksp * npw + j), hh = fb0 / HD, fo = fb0 - hh * HD + 8 * tq;
               const float* pb = p.part + (static_cast<size_t>(sq) * H + hh) * kMaxSplits * PS;
+              const int g0 = sm.istart[sq] + hh * nws_q;
+              const int nsp = nws_q == 0 ? 0 : (g0 + nws_q - 1) / upc - g0 / upc + 1;     // CTAs the key ranges of this (sequence, head) ran on
               float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY, Ls = 0.f;
               for (int s4 = 0; s4 < nsp; s4 += 4) {
                 float2 ml[4];
                 float4 oa[4], ob[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const bool on = s4 + u < nsp;
-                  const float* pp = pb + static_cast<size_t>(on ? s4 + u : s4) * PS;
-                  ml[u] = ldv2f(pp + HD);
-                  oa[u] = ldv4f(pp + fo);
-                  ob[u] = ldv4f(pp + fo + 4);
-                  if (!on) ml[u] = make_float2(-INFINITY, 0.f);
+                  const float* pp = pb + static_cast<size_t>(s4 + u) * PS;
+                  ml[u] = make_float2(-INFINITY, 0.f);
+                  oa[u] = ob[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (s4 + u < nsp) {                                   // (at most two partials unless a run is cut by many CTA boundaries)
+                    ml[u] = ldv2f(pp + HD);
+                    oa[u] = ldv4f(pp + fo);
+                    ob[u] = ldv4f(pp + fo + 4);
+                  }
                 }
                 float Mn = M;
 #pragma unroll
@@ -564,9 +583,23 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
         attn_tc<HD, false, true>(lw.kh + hb, lw.vt + hb, at_len, at_wi, at_nws, lane, sm.qs[warp], sm.kn[warp], sm.vn[warp], at_wi == 0,
                            sm.part[warp], kq0, vq0);
         __syncwarp();
-        float* dst = p.part + ((static_cast<size_t>(at_b) * H + at_h) * kMaxSplits + at_wi) * PS;
-        if (lane < HD / 4) *reinterpret_cast<float4*>(dst + lane * 4) = *reinterpret_cast<const float4*>(&sm.part[warp][lane * 4]);
-        if (lane == 0) *reinterpret_cast<float2*>(dst + HD) = make_float2(sm.part[warp][64], sm.part[warp][65]);
+      }
+      __syncthreads();
+      if (at_run > 0) {
+        // merge the run's partial results (each: numerators | m | l, log2 domain) and write ONE partial for this CTA
+        float M = -INFINITY;
+        for (int i = 0; i < at_run; ++i) M = fmaxf(M, sm.part[warp + i][64]);
+        float o0 = 0.f, o1 = 0.f, Ls = 0.f;
+        for (int i = 0; i < at_run; ++i) {
+          const float w = fast_exp2(sm.part[warp + i][64] - M);
+          Ls = fmaf(sm.part[warp + i][65], w, Ls);
+          o0 = fmaf(sm.part[warp + i][lane], w, o0);
+          if (HD == 64) o1 = fmaf(sm.part[warp + i][32 + lane], w, o1);
+        }
+        float* dst = p.part + ((static_cast<size_t>(at_b) * H + at_h) * kMaxSplits + at_slot) * PS;
+        dst[lane] = o0;
+        if (HD == 64) dst[32 + lane] = o1;
+        if (lane == 0) *reinterpret_cast<float2*>(dst + HD) = make_float2(M, Ls);
       }
       sync_phase(5 * l + K_OUT);
       if (!alive) break;
@@ -773,7 +806,30 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
 }
 
 // ---- weight packing: bf16 [rows, K] row-major -> tiles (see mma_tile) ----
-__global__ void grid_pack_kernel(const bf16* __restrict__ w, int rows, int K, uint4* __restrict__ dst, size_t n_chunks) {
+__device__ __forceinline__ uint32_t scale2(uint32_t w2, const float* __restrict__ g, int col) {
+  if (!g) return w2;
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w2);
+  return pack_bf16(__bfloat162float(v.x) * g[col], __bfloat162float(v.y) * g[col + 1]);
+}
+
+// c[r] = sum_k bf16(W[r][k] gamma[k]) (exactly the values the MMAs see), d[r] = sum_k W[r][k] beta[k] + bias[r]; one warp per row
+__global__ void grid_fold_kernel(const bf16* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ bias, int rows, int K, float* __restrict__ c, float* __restrict__ d) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float cs = 0.f, ds = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __bfloat162float(w[static_cast<size_t>(r) * K + k]);
+    cs += __bfloat162float(__float2bfloat16_rn(wv * gamma[k]));
+    ds = fmaf(wv, beta[k], ds);
+  }
+  cs = warp_sum(cs);
+  ds = warp_sum(ds);
+  if (lane == 0) { c[r] = cs; d[r] = ds + bias[r]; }
+}
+
+__global__ void grid_pack_kernel(const bf16* __restrict__ w, int rows, int K, uint4* __restrict__ dst, size_t n_chunks,
+                                 const float* __restrict__ gamma) {
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_chunks; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int per_tile = K * 2;                               // 16-byte chunks per tile: 16 rows x K x 2 B / 16
     const int tile = static_cast<int>(idx / per_tile), c = static_cast<int>(idx % per_tile);
@@ -781,12 +837,12 @@ __global__ void grid_pack_kernel(const bf16* __restrict__ w, int rows, int K, ui
     const int col = 32 * j + 8 * t + 4 * e, r0 = 16 * tile + g, r1 = r0 + 8;
     uint32_t v[4] = {0u, 0u, 0u, 0u};
     if (r0 < rows) {
-      v[0] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r0) * K + col);
-      v[2] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r0) * K + col + 2);
+      v[0] = scale2(*reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r0) * K + col), gamma, col);
+      v[2] = scale2(*reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r0) * K + col + 2), gamma, col + 2);
     }
     if (r1 < rows) {
-      v[1] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r1) * K + col);
-      v[3] = *reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r1) * K + col + 2);
+      v[1] = scale2(*reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r1) * K + col), gamma, col);
+      v[3] = scale2(*reinterpret_cast<const uint32_t*>(w + static_cast<size_t>(r1) * K + col + 2), gamma, col + 2);
     }
     dst[idx] = make_uint4(v[0], v[1], v[2], v[3]);
   }
@@ -832,24 +888,36 @@ size_t grid_packed_bytes(int d_model, int d_ff, int n_layer, int V) {
          tiles_bytes(V, d_model);
 }
 
-int grid_pack_weights(cudaStream_t s, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1, const bf16* const* w2,
-                      const bf16* head, int n_layer, int d_model, int d_ff, int V, uint8_t* packed, GridLayer* layers, size_t* w_head) {
+int grid_pack_weights(cudaStream_t s, const GridPackSrc* src, const bf16* head, int n_layer, int d_model, int d_ff, int V, uint8_t* packed,
+                      float* fold, GridLayer* layers, size_t* w_head) {
   size_t off = 0;
-  auto pack = [&](const bf16* w, int rows, int K, size_t* at) -> int {
+  auto pack = [&](const bf16* w, int rows, int K, const float* gamma, size_t* at) -> int {
     *at = off;
     const size_t bytes = tiles_bytes(rows, K);
-    grid_pack_kernel<<<296, 256, 0, s>>>(w, rows, K, reinterpret_cast<uint4*>(packed + off), bytes / 16);
+    grid_pack_kernel<<<296, 256, 0, s>>>(w, rows, K, reinterpret_cast<uint4*>(packed + off), bytes / 16, gamma);
     MG_LAUNCH_CHECK();
     off += bytes;
     return MG_OK;
   };
+  auto foldv = [&](const bf16* w, const float* gamma, const float* beta, const float* bias, int rows, int K, float* c, float* d) -> int {
+    grid_fold_kernel<<<(rows + 7) / 8, 256, 0, s>>>(w, gamma, beta, bias, rows, K, c, d);
+    MG_LAUNCH_CHECK();
+    return MG_OK;
+  };
+  const int per_layer = 2 * (3 * d_model + d_ff);
   for (int l = 0; l < n_layer; ++l) {
-    MG_TRY(pack(w_in[l], 3 * d_model, d_model, &layers[l].w_in));
-    MG_TRY(pack(w_out[l], d_model, d_model, &layers[l].w_out));
-    MG_TRY(pack(w1[l], d_ff, d_model, &layers[l].w1));
-    MG_TRY(pack(w2[l], d_model, d_ff, &layers[l].w2));
+    const GridPackSrc& q = src[l];
+    float* f = fold + static_cast<size_t>(l) * per_layer;
+    float *c_in = f, *d_in = f + 3 * d_model, *c_1 = f + 6 * d_model, *d_1 = f + 6 * d_model + d_ff;
+    layers[l] = GridLayer{c_in, d_in, c_1, d_1, q.b_out, q.b2, q.kh, q.vt, 0, 0, 0, 0};
+    MG_TRY(pack(q.w_in, 3 * d_model, d_model, q.ln1w, &layers[l].w_in));
+    MG_TRY(pack(q.w_out, d_model, d_model, nullptr, &layers[l].w_out));
+    MG_TRY(pack(q.w1, d_ff, d_model, q.ln2w, &layers[l].w1));
+    MG_TRY(pack(q.w2, d_model, d_ff, nullptr, &layers[l].w2));
+    MG_TRY(foldv(q.w_in, q.ln1w, q.ln1b, q.b_in, 3 * d_model, d_model, c_in, d_in));
+    MG_TRY(foldv(q.w1, q.ln2w, q.ln2b, q.b1, d_ff, d_model, c_1, d_1));
   }
-  MG_TRY(pack(head, V, d_model, w_head));
+  MG_TRY(pack(head, V, d_model, nullptr, w_head));
   return MG_OK;
 }
 

@@ -16,13 +16,16 @@ constexpr int kMaxSeqs = 64;           // 8 n-tiles of the m16n8k16 MMA = the 8 
 constexpr int kThreads = 256;
 constexpr int kMaxSplits = 16;         // key ranges per (sequence, head) in the attention phase
 constexpr int kMaxItems = 96;          // dense work items of one CTA per decode step
+constexpr int kGridCtrlBytes = 4096;
 constexpr int kSampMaxPer = 36;        // fast sampler: logits per thread held in registers (V <= 256 * 36)
 
 // phase kinds of a decode step; phase index = 5 * layer + kind (kind < 5), 5 L = head, 5 L + 1 = sampler
 enum Kind { K_QKV = 0, K_ATT = 1, K_OUT = 2, K_MLP1 = 3, K_MLP2 = 4, K_HEAD = 5, K_SAMPLE = 6 };
 
+// LayerNorm is folded into the matrices that consume it: W' = W diag(gamma) (packed), c[r] = sum_k W'[r][k], d[r] = sum_k W[r][k] beta[k]
+// + bias[r], so that  W LN(x) + bias = rstd (W' x - mean c) + d  with the row statistics applied in the epilogue (grid_pack_weights).
 struct GridLayer {
-  const float *b_in, *b_out, *b1, *b2, *ln1w, *ln1b, *ln2w, *ln2b;
+  const float *c_in, *d_in, *c_1, *d_1, *b_out, *b2;
   bf16 *kh, *vt;                       // K head-major [B][H][Tvt][hd], V per 32-key block transposed [B][H][Tvt / 32][hd][32] (attn_tc.cuh)
   size_t w_in, w_out, w1, w2;          // byte offsets of the matrices' first tile inside `packed`
 };
@@ -58,7 +61,7 @@ struct GridParams {
   float* logits;                       // [seq][ldl]
   float* vals;                         // [seq][ldl] scratch of the sampler's general path
   float* part;                         // attention partials [seq][head][kMaxSplits][hd + 4]: numerators | m | l
-  unsigned* ctrl;                      // [0] grid barrier counter (monotonic), [1] sequences finished inside this launch, [2] status
+  unsigned* ctrl;                      // [0] grid barrier counter (monotonic), [1] sequences finished inside this launch, [2] status (kGridCtrlBytes, zeroed before every launch)
   int L, V, B, H, n_steps, Tvt, ldl, n_cta;
   int tn[8], ks[8];                    // per phase kind: n-tiles per item x k-splits (tn * ks == 8)
   int early_exit;
@@ -73,9 +76,15 @@ struct GridParams {
 
 bool grid_eligible(int d_model, int d_ff, int n_head, int n_layer, int V);
 size_t grid_packed_bytes(int d_model, int d_ff, int n_layer, int V);
-// bf16 matrices [out, in] row-major -> 16-row fragment-major tiles; fills the w_* offsets of `layers` and *w_head
-int grid_pack_weights(cudaStream_t s, const bf16* const* w_in, const bf16* const* w_out, const bf16* const* w1, const bf16* const* w2,
-                      const bf16* head, int n_layer, int d_model, int d_ff, int V, uint8_t* packed, GridLayer* layers, size_t* w_head);
+struct GridPackSrc {
+  const bf16 *w_in, *w_out, *w1, *w2;          // bf16 matrices [out, in] row-major
+  const float *b_in, *b_out, *b1, *b2, *ln1w, *ln1b, *ln2w, *ln2b;
+  bf16 *kh, *vt;
+};
+// 16-row fragment-major tiles (LayerNorm weights folded into in_proj / mlp.0), the fold vectors (`fold`: n_layer x 2 x (3 d + d_ff) floats)
+// and the GridLayer table
+int grid_pack_weights(cudaStream_t s, const GridPackSrc* src, const bf16* head, int n_layer, int d_model, int d_ff, int V, uint8_t* packed,
+                      float* fold, GridLayer* layers, size_t* w_head);
 // phase shapes for a batch of B sequences + the per-CTA item lists (host arrays: items [n_cta][kMaxItems], n_items [n_cta]);
 // MG_E_SHAPE when a CTA would get more than kMaxItems items
 int grid_plan(int d_model, int d_ff, int n_layer, int V, int B, int n_cta, int* tn, int* ks, GridItem* items, int32_t* n_items);

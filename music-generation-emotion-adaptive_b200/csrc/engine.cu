@@ -143,6 +143,7 @@ struct mg_engine {
   bool grid_ok = false, use_grid = false, last_run_grid = false;
   int grid_mode = 2;                           // MG_GRID: 0 = never, 1 = wherever eligible, unset = where the cluster kernel does not take the geometry
   uint8_t* d_grid_packed = nullptr;
+  float* d_grid_fold = nullptr;
   grid::GridLayer grid_layers[grid::kMaxLayers]{};
   size_t grid_w_head = 0;
   grid::GridItem* d_grid_items = nullptr;
@@ -554,18 +555,18 @@ int setup_grid(mg_engine* e) {
   e->grid_ctas = grid::grid_max_ctas(D, hd);
   if (e->grid_ctas <= 0) return MG_OK;
   MG_TRY(alloc_persistent_caches(e));
-  std::vector<const bf16*> w_in(L), w_out(L), w1(L), w2(L);
+  std::vector<grid::GridPackSrc> src(L);
   for (int l = 0; l < L; ++l) {
     LayerW& w = e->layers[l];
-    w_in[l] = reinterpret_cast<const bf16*>(w.w_in); w_out[l] = reinterpret_cast<const bf16*>(w.w_out);
-    w1[l] = reinterpret_cast<const bf16*>(w.w1); w2[l] = reinterpret_cast<const bf16*>(w.w2);
-    e->grid_layers[l] = grid::GridLayer{w.b_in, w.b_out, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
-                                        reinterpret_cast<bf16*>(w.kh), reinterpret_cast<bf16*>(w.vt), 0, 0, 0, 0};
+    src[l] = grid::GridPackSrc{reinterpret_cast<const bf16*>(w.w_in), reinterpret_cast<const bf16*>(w.w_out), reinterpret_cast<const bf16*>(w.w1),
+                               reinterpret_cast<const bf16*>(w.w2), w.b_in, w.b_out, w.b1, w.b2, w.ln1w, w.ln1b, w.ln2w, w.ln2b,
+                               reinterpret_cast<bf16*>(w.kh), reinterpret_cast<bf16*>(w.vt)};
   }
   if (!e->d_grid_packed) {
     const int S = grid::kMaxSeqs;
     e->grid_ldl = (g.vocab_size + 15) / 16 * 16;
     MG_TRY(e->dmalloc(&e->d_grid_packed, grid::grid_packed_bytes(D, g.d_ff, L, g.vocab_size)));
+    MG_TRY(e->dmalloc(&e->d_grid_fold, sizeof(float) * L * 2 * (3 * D + g.d_ff)));
     MG_TRY(e->dmalloc(&e->d_grid_items, sizeof(grid::GridItem) * grid::kMaxItems * e->grid_ctas));
     MG_TRY(e->dmalloc(&e->d_grid_nitems, sizeof(int32_t) * e->grid_ctas));
     const size_t part_floats = static_cast<size_t>(S) * g.n_head * grid::kMaxSplits * (hd + 4);
@@ -576,7 +577,7 @@ int setup_grid(mg_engine* e) {
         {reinterpret_cast<void**>(&e->g_logits), sizeof(float) * S * e->grid_ldl}, {reinterpret_cast<void**>(&e->g_vals), sizeof(float) * S * e->grid_ldl},
         {reinterpret_cast<void**>(&e->g_part), sizeof(float) * part_floats},
         {reinterpret_cast<void**>(&e->g_xb), sizeof(bf16) * S * D}, {reinterpret_cast<void**>(&e->g_x1b), sizeof(bf16) * S * D},
-        {reinterpret_cast<void**>(&e->g_sx), sizeof(float) * S * (D / 16) * 2}, {reinterpret_cast<void**>(&e->g_sx1), sizeof(float) * S * (D / 16) * 2}, {reinterpret_cast<void**>(&e->d_grid_ctrl), 64}};
+        {reinterpret_cast<void**>(&e->g_sx), sizeof(float) * S * (D / 16) * 2}, {reinterpret_cast<void**>(&e->g_sx1), sizeof(float) * S * (D / 16) * 2}, {reinterpret_cast<void**>(&e->d_grid_ctrl), grid::kGridCtrlBytes}};
     for (auto& b : bufs) {
       MG_TRY(e->dmalloc(reinterpret_cast<uint8_t**>(b.p), b.bytes));
       MG_CUDA_OK(cudaMemsetAsync(*b.p, 0, b.bytes, e->stream));
@@ -584,8 +585,8 @@ int setup_grid(mg_engine* e) {
     MG_CUDA_OK(cudaMallocHost(&e->h_grid_ctrl, 64));
     std::memset(e->h_grid_ctrl, 0, 64);
   }
-  MG_TRY(grid::grid_pack_weights(e->stream, w_in.data(), w_out.data(), w1.data(), w2.data(), reinterpret_cast<const bf16*>(e->head_w), L, D,
-                                 g.d_ff, g.vocab_size, e->d_grid_packed, e->grid_layers, &e->grid_w_head));
+  MG_TRY(grid::grid_pack_weights(e->stream, src.data(), reinterpret_cast<const bf16*>(e->head_w), L, D, g.d_ff, g.vocab_size, e->d_grid_packed,
+                                 e->d_grid_fold, e->grid_layers, &e->grid_w_head));
   MG_CUDA_OK(cudaStreamSynchronize(e->stream));
   e->grid_plan_B = -1;
   e->grid_ok = true;
@@ -638,7 +639,7 @@ bool run_decode_grid(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
       p.prof = e->d_grid_prof; p.prof_step = std::atoi(ps);
     }
   }
-  if (!cuda_ok(cudaMemsetAsync(e->d_grid_ctrl, 0, 64, e->stream), "grid control reset")) return true;
+  if (!cuda_ok(cudaMemsetAsync(e->d_grid_ctrl, 0, grid::kGridCtrlBytes, e->stream), "grid control reset")) return true;
   {
     std::vector<const bf16*> kc(g.n_layer), vc(g.n_layer);
     std::vector<bf16*> kh(g.n_layer), vt(g.n_layer);
