@@ -112,9 +112,10 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic_bytes():
     """DRAM bytes (read + write) per launch of the persistent decode kernel from the committed `ncu --set full`
-    capture of this same workload (profiles/r1j_decode_mega_full_raw.csv); None when the file is missing."""
+    capture of this same workload (the newest of profiles/r2n_ / r2m_ / r1j_decode_mega_full_raw.csv); None when none is there."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1j_decode_mega_full_raw.csv")
+    path = next((q for q in (os.path.join(ROOT, "profiles", f"{r}_decode_mega_full_raw.csv") for r in ("r2n", "r2m", "r1j"))
+                 if os.path.exists(q)), "")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -303,7 +304,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": ncu_traffic_bytes(), "traffic_note": "DRAM read+write bytes per launch (= per job), ncu --set full, profiles/r1j_decode_mega_full_raw.csv",
+                     "traffic": ncu_traffic_bytes(), "traffic_note": "DRAM read+write bytes per launch (= per job), ncu --set full, profiles/r*_decode_mega_full_raw.csv (newest)",
                      "peak_source": peak_src,
                      "kernel": ("decode_mega_kernel: ONE persistent cluster launch per job runs all 1024 decode steps "
                                 "(embedding, 4 blocks, head, top-k sampler); achieved = algorithmic bytes of the decode "
@@ -396,26 +397,52 @@ def batch1_latency(mg):
     return out
 
 
+def _with_env(env, fn):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def long_context(mg, hbm_peak):
-    """BASELINE config 4: 256-token prompt prefill + 4096 new tokens, batch 16 (train_large blocks, 512-row position table)."""
+    """BASELINE config 4: 256-token prompt prefill + 4096 new tokens, batch 16 (train_large blocks, 512-row position table).
+    Default path = the cluster kernel (16 clusters x 4 CTAs = 64 SMs); the grid kernel (all SMs, every (sequence, head) split over
+    key ranges on different SMs) is timed beside it on the same box."""
     geo = mg.GEOMETRIES["train_large_pos512"]
     ck = mg.make_checkpoint(geo, 0)
     rng = np.random.default_rng(0)
     prompts = [rng.integers(0, geo.vocab_size, 256).tolist() for _ in range(16)]
-    eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=16, max_seq=4352)
-    best = None
-    for i in range(2):
-        eng.upload(prompts, 4096)
-        eng.run(1.0, 40, eos_id=-1, seed=i)
-        eng.synchronize()
-        t = eng.last_timing()
-        best = t if best is None or t["total_ms"] < best["total_ms"] else best
     alg, _, _ = algorithmic_bytes(geo, [256] * 16, 4096)
-    eng.close()
-    return {"workload": "config4: 256-token prompt + 4096 new tokens, batch 16, bf16", "tokens_per_s": 16 * 4096 / (best["total_ms"] * 1e-3),
+
+    def run(reps):
+        eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=16, max_seq=4352)
+        best = None
+        for i in range(reps):
+            eng.upload(prompts, 4096)
+            eng.run(1.0, 40, eos_id=-1, seed=i)
+            eng.synchronize()
+            t = eng.last_timing()
+            best = t if best is None or t["total_ms"] < best["total_ms"] else best
+        path = eng.last_decode_path()
+        eng.close()
+        return best, path
+
+    best, path = run(2)
+    gbest, gpath = _with_env({"MG_GRID": "1"}, lambda: run(2))
+    return {"workload": "config4: 256-token prompt + 4096 new tokens, batch 16, bf16", "path": path,
+            "tokens_per_s": 16 * 4096 / (best["total_ms"] * 1e-3),
             "prefill_ms": best["prefill_ms"], "decode_us_per_step": 1e3 * best["decode_ms"] / 4096,
             "hbm_gbs": alg / (best["decode_ms"] * 1e-3) / 1e9, "frac_of_measured_hbm": alg / (best["decode_ms"] * 1e-3) / 1e9 / hbm_peak,
-            "note": "16 sequences -> 16 clusters x 4 CTAs = 64 of 148 SMs busy (one sequence per cluster)"}
+            "note": "16 sequences -> 16 clusters x 4 CTAs = 64 of 148 SMs busy (one sequence per cluster)",
+            "grid_kernel": {"path": gpath, "decode_us_per_step": 1e3 * gbest["decode_ms"] / 4096,
+                            "frac_of_measured_hbm": alg / (gbest["decode_ms"] * 1e-3) / 1e9 / hbm_peak,
+                            "note": "all 148 SMs: attention split over key ranges on different SMs, one grid barrier per phase"}}
 
 
 def pipeline_512(mg, rank, world, local_rank, dist):
@@ -466,27 +493,36 @@ def pipeline_512(mg, rank, world, local_rank, dist):
 
 def production_geometry(mg, hbm_peak):
     """The geometry the paper's production model was trained with (train/train_large2.py:10-15: d 512, 8 heads of 64, 6 layers,
-    511 position rows, V 8324), batch 64, generation to max_len = SEQ_LEN like the service call (api_cache.py:204).  Not
-    admitted to the persistent cluster kernel (d_model 256 only): step graph, batched decode GEMMs on tcgen05 (M = 64)."""
+    511 position rows, V 8324), batch 64, generation to max_len = SEQ_LEN like the service call (api_cache.py:204).  The cluster
+    kernel does not take it (d_model 256 only); default path = the grid-synchronous persistent kernel (decode_grid.cu), with the
+    step graph (46 launches per step, batched decode GEMMs on tcgen05) timed beside it on the same box."""
     geo = mg.GEOMETRIES["train_large2"]
     ck = mg.make_checkpoint(geo, 0)
     prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], BATCH, seed=0)]
     n_new = geo.pos_rows - max(len(p) for p in prompts)
-    eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=BATCH, max_seq=544)
-    best = None
-    for i in range(3):
-        eng.upload(prompts, n_new)
-        eng.run(TEMPERATURE, TOP_K, eos_id=-1, seed=i)
-        eng.synchronize()
-        t = eng.last_timing()
-        best = t if best is None or t["decode_ms"] < best["decode_ms"] else best
+
+    def run():
+        eng = mg.Generator(ck["model"], n_head=geo.n_head, dtype="bf16", max_batch=BATCH, max_seq=544)
+        best = None
+        for i in range(3):
+            eng.upload(prompts, n_new)
+            eng.run(TEMPERATURE, TOP_K, eos_id=-1, seed=i)
+            eng.synchronize()
+            t = eng.last_timing()
+            best = t if best is None or t["decode_ms"] < best["decode_ms"] else best
+        path = eng.last_decode_path()
+        eng.close()
+        return best, path
+
+    best, path = run()
+    sbest, spath = _with_env({"MG_GRID": "0"}, run)
     alg, W, kappa = algorithmic_bytes(geo, [len(p) for p in prompts], n_new)
-    path = eng.last_decode_path()
-    eng.close()
     gbs = alg / (best["decode_ms"] * 1e-3) / 1e9
     return {"workload": f"train_large2 geometry (d 512, L 6, hd 64), batch 64, {n_new} new tokens, top-k 40, bf16", "path": path,
             "tokens_per_s": BATCH * n_new / (best["total_ms"] * 1e-3), "decode_us_per_step": 1e3 * best["decode_ms"] / n_new,
-            "hbm_gbs": gbs, "frac_of_measured_hbm": gbs / hbm_peak, "weight_bytes_per_step": W, "kv_bytes_per_position": kappa}
+            "hbm_gbs": gbs, "frac_of_measured_hbm": gbs / hbm_peak, "weight_bytes_per_step": W, "kv_bytes_per_position": kappa,
+            "step_graph": {"path": spath, "decode_us_per_step": 1e3 * sbest["decode_ms"] / n_new,
+                           "frac_of_measured_hbm": alg / (sbest["decode_ms"] * 1e-3) / 1e9 / hbm_peak}}
 
 
 def continuous_batching(mg):

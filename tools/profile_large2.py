@@ -1,4 +1,4 @@
-"""Short deterministic run of the train_large2 geometry (d 512, L 6, hd 64; step-graph path) for ncu / timing.
+"""Short deterministic run of the train_large2 geometry (d 512, L 6, hd 64; grid kernel, MG_GRID=0: step graph) for ncu / timing.
 
     python tools/profile_large2.py [new_tokens] [batch]
 """
