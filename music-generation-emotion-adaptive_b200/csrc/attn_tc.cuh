@@ -53,8 +53,7 @@ __device__ __forceinline__ uint4 ldg_strong16(const bf16* p) {
   return r;
 }
 template <int HD, bool STRONG = false>
-__device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int b, int lane,
-                                                uint4 (&kq)[4][HD / 32], uint4 (&vq)[HD / 8]) {
+__device__ __forceinline__ void attn_load_k(const bf16* __restrict__ kh, int b, int lane, uint4 (&kq)[4][HD / 32]) {
   const int g = lane >> 2, t = lane & 3;
   // rows past the end of the sequence are read too (finite: the cache is zero-filled once and only ever holds bf16 data; its
   // row count is rounded up to a multiple of 32) and masked in attn_tc: one pointer per block, immediate offsets per load
@@ -63,9 +62,19 @@ __device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, con
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) kq[j][c] = STRONG ? ldg_strong16(kb + j * 8 * HD + 32 * c) : ldg_stream16(kb + j * 8 * HD + 32 * c);
+}
+template <int HD, bool STRONG = false>
+__device__ __forceinline__ void attn_load_v(const bf16* __restrict__ vt, int b, int lane, uint4 (&vq)[HD / 8]) {
+  const int g = lane >> 2, t = lane & 3;
   const bf16* vb = vt + static_cast<size_t>(b) * (HD * 32) + g * 32 + 8 * t;
 #pragma unroll
   for (int n = 0; n < HD / 8; ++n) vq[n] = STRONG ? ldg_strong16(vb + n * 256) : ldg_stream16(vb + n * 256);
+}
+template <int HD, bool STRONG = false>
+__device__ __forceinline__ void attn_load_block(const bf16* __restrict__ kh, const bf16* __restrict__ vt, int len, int b, int lane,
+                                                uint4 (&kq)[4][HD / 32], uint4 (&vq)[HD / 8]) {
+  attn_load_k<HD, STRONG>(kh, b, lane, kq);
+  attn_load_v<HD, STRONG>(vt, b, lane, vq);
 }
 
 // kq0 / vq0: block `wi` of this worker, loaded by the caller ahead of time (before the QKV GEMM, whose result the loads do not
@@ -115,7 +124,8 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
 
   const int nblk = (len + 31) >> 5;
   auto load_block = [&](int b, uint4 (&kq)[4][KL], uint4 (&vq)[NT]) { attn_load_block<HD, STRONG>(kh, vt, len, b, lane, kq, vq); };
-  auto compute_block = [&](int b, const uint4 (&kq)[4][KL], const uint4 (&vq)[NT]) {
+  // next_b >= 0: the K rows / V block of block next_b are requested into the SAME registers as soon as this block's MMAs have consumed them
+  auto compute_block_h = [&](int b, uint4 (&kq)[4][KL], uint4 (&vq)[NT], int next_b) {
     const int key0 = b << 5;
     float sc[4][2];
 #pragma unroll
@@ -131,6 +141,7 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
       sc[j][0] = c4[0] + c4[2];                                  // row 0 (hi) + row 8 (lo)
       sc[j][1] = c4[1] + c4[3];
     }
+    if (next_b >= 0) attn_load_k<HD, STRONG>(kh, next_b, lane, kq);   // the K registers are free from here on
     if (key0 + 32 > len) {                                       // only the last block of a sequence is partial
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -166,6 +177,10 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
       mma_bf16_16816(oacc[n], a0, vq[n].x, vq[n].y);
       mma_bf16_16816(oacc[n], a1, vq[n].z, vq[n].w);
     }
+    if (next_b >= 0) attn_load_v<HD, STRONG>(vt, next_b, lane, vq);   // ... and the V registers from here on
+  };
+  auto compute_block = [&](int b, const uint4 (&kq)[4][KL], const uint4 (&vq)[NT]) {
+    compute_block_h(b, const_cast<uint4(&)[4][KL]>(kq), const_cast<uint4(&)[NT]>(vq), -1);
   };
   if (HD == 32 && MG_MEGA_KVSLOT && slot != nullptr) {
     // Three blocks in flight per warp: register sets A (kq0 / vq0) and B by 16-byte global loads, the staging slot S by bulk copy.
@@ -230,6 +245,9 @@ __device__ __forceinline__ void attn_tc(const bf16* __restrict__ kh, const bf16*
       }
     }
   } else {
+    // head_dim 64: ONE register set, load -> compute per block.  Measured and rejected on B200 (same box): a second register set
+    // (spills: train_large2 251 -> 297 us per step in the grid kernel) and requesting the next block's K rows behind the score MMAs /
+    // its V block behind the output MMAs into the same registers (251 -> 275; batch-1 cluster kernel 27.7 -> 29.8 us per token)
     for (int b = wi; b < nblk; b += nws) {
       if (!(PRE && b == wi)) load_block(b, kq0, vq0);
       compute_block(b, kq0, vq0);

@@ -458,45 +458,88 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
             mma_tile<npw>(p.packed + lw.w2 + static_cast<size_t>(rt) * (16 * DFF * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
           } else {
             const int nws_q = sm.nws[sq];
+            // partial results of the attention phase: (sequence, head) -> nsp partials (one per CTA its key ranges ran on)
+            int nsp_j[npw];
+            const float* pb_j[npw];
+            int fo_j[npw];
+            int nsp_max = 0;
 #pragma unroll
             for (int j = 0; j < npw; ++j) {
-              const int fb0 = 32 * (ksp * npw + j), hh = fb0 / HD, fo = fb0 - hh * HD + 8 * tq;
-              const float* pb = p.part + (static_cast<size_t>(sq) * H + hh) * kMaxSplits * PS;
+              const int fb0 = 32 * (ksp * npw + j), hh = fb0 / HD;
+              fo_j[j] = fb0 - hh * HD + 8 * tq;
+              pb_j[j] = p.part + (static_cast<size_t>(sq) * H + hh) * kMaxSplits * PS;
               const int g0 = sm.istart[sq] + hh * nws_q;
-              const int nsp = nws_q == 0 ? 0 : (g0 + nws_q - 1) / upc - g0 / upc + 1;     // CTAs the key ranges of this (sequence, head) ran on
-              float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY, Ls = 0.f;
-              for (int s4 = 0; s4 < nsp; s4 += 4) {
-                float2 ml[4];
-                float4 oa[4], ob[4];
+              nsp_j[j] = nws_q == 0 ? 0 : (g0 + nws_q - 1) / upc - g0 / upc + 1;
+              nsp_max = max(nsp_max, nsp_j[j]);
+            }
+            auto merge_pack = [&](const float2 (&ml)[4], const float4 (&oa)[4], const float4 (&ob)[4], float (&o)[8], float& M, float& Ls) {
+              float Mn = M;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float* pp = pb + static_cast<size_t>(s4 + u) * PS;
-                  ml[u] = make_float2(-INFINITY, 0.f);
-                  oa[u] = ob[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (s4 + u < nsp) {                                   // (at most two partials unless a run is cut by many CTA boundaries)
-                    ml[u] = ldv2f(pp + HD);
-                    oa[u] = ldv4f(pp + fo);
-                    ob[u] = ldv4f(pp + fo + 4);
+              for (int u = 0; u < 4; ++u) Mn = fmaxf(Mn, ml[u].x);
+              const float corr = fast_exp2(M - Mn);                    // M == -inf: exp2(-inf) = 0 (Mn is finite: worker 0 folds the new token)
+              Ls *= corr;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] *= corr;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float w = fast_exp2(ml[u].x - Mn);
+                Ls = fmaf(ml[u].y, w, Ls);
+                o[0] = fmaf(oa[u].x, w, o[0]); o[1] = fmaf(oa[u].y, w, o[1]); o[2] = fmaf(oa[u].z, w, o[2]); o[3] = fmaf(oa[u].w, w, o[3]);
+                o[4] = fmaf(ob[u].x, w, o[4]); o[5] = fmaf(ob[u].y, w, o[5]); o[6] = fmaf(ob[u].z, w, o[6]); o[7] = fmaf(ob[u].w, w, o[7]);
+              }
+              M = Mn;
+            };
+            if (npw <= 4 && __all_sync(0xffffffffu, nsp_max <= 2)) {
+              // the usual case (a run of key ranges is cut by at most one CTA boundary): ALL loads of the warp's operand first, one L2
+              // round trip instead of one per k-step pair
+              float2 ml[npw][2];
+              float4 oa[npw][2], ob[npw][2];
+#pragma unroll
+              for (int j = 0; j < npw; ++j)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  ml[j][u] = make_float2(-INFINITY, 0.f);
+                  oa[j][u] = ob[j][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (u < nsp_j[j]) {
+                    const float* pp = pb_j[j] + static_cast<size_t>(u) * PS;
+                    ml[j][u] = ldv2f(pp + HD);
+                    oa[j][u] = ldv4f(pp + fo_j[j]);
+                    ob[j][u] = ldv4f(pp + fo_j[j] + 4);
                   }
                 }
-                float Mn = M;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) Mn = fmaxf(Mn, ml[u].x);
-                const float corr = fast_exp2(M - Mn);                    // M == -inf: exp2(-inf) = 0 (Mn is finite: worker 0 folds the new token)
-                Ls *= corr;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] *= corr;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float w = fast_exp2(ml[u].x - Mn);
-                  Ls = fmaf(ml[u].y, w, Ls);
-                  o[0] = fmaf(oa[u].x, w, o[0]); o[1] = fmaf(oa[u].y, w, o[1]); o[2] = fmaf(oa[u].z, w, o[2]); o[3] = fmaf(oa[u].w, w, o[3]);
-                  o[4] = fmaf(ob[u].x, w, o[4]); o[5] = fmaf(ob[u].y, w, o[5]); o[6] = fmaf(ob[u].z, w, o[6]); o[7] = fmaf(ob[u].w, w, o[7]);
-                }
-                M = Mn;
+              for (int j = 0; j < npw; ++j) {
+                const float M = fmaxf(ml[j][0].x, ml[j][1].x);
+                const float w0 = fast_exp2(ml[j][0].x - M), w1 = fast_exp2(ml[j][1].x - M);
+                const float Ls = ml[j][0].y * w0 + ml[j][1].y * w1;
+                const float inv = Ls > 0.f ? __fdividef(1.0f, Ls) : 0.f;
+                const float4 a = oa[j][0], c = oa[j][1], e = ob[j][0], g = ob[j][1];
+                bq[j] = make_uint4(pk((a.x * w0 + c.x * w1) * inv, (a.y * w0 + c.y * w1) * inv), pk((a.z * w0 + c.z * w1) * inv, (a.w * w0 + c.w * w1) * inv),
+                                   pk((e.x * w0 + g.x * w1) * inv, (e.y * w0 + g.y * w1) * inv), pk((e.z * w0 + g.z * w1) * inv, (e.w * w0 + g.w * w1) * inv));
               }
-              const float inv = Ls > 0.f ? __fdividef(1.0f, Ls) : 0.f;
-              bq[j] = make_uint4(pk(o[0] * inv, o[1] * inv), pk(o[2] * inv, o[3] * inv), pk(o[4] * inv, o[5] * inv), pk(o[6] * inv, o[7] * inv));
+            } else {
+#pragma unroll
+              for (int j = 0; j < npw; ++j) {
+                float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, M = -INFINITY, Ls = 0.f;
+                for (int s4 = 0; s4 < nsp_j[j]; s4 += 4) {
+                  float2 ml[4];
+                  float4 oa[4], ob[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float* pp = pb_j[j] + static_cast<size_t>(s4 + u) * PS;
+                    ml[u] = make_float2(-INFINITY, 0.f);
+                    oa[u] = ob[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s4 + u < nsp_j[j]) {
+                      ml[u] = ldv2f(pp + HD);
+                      oa[u] = ldv4f(pp + fo_j[j]);
+                      ob[u] = ldv4f(pp + fo_j[j] + 4);
+                    }
+                  }
+                  merge_pack(ml, oa, ob, o, M, Ls);
+                }
+                const float inv = Ls > 0.f ? __fdividef(1.0f, Ls) : 0.f;
+                bq[j] = make_uint4(pk(o[0] * inv, o[1] * inv), pk(o[2] * inv, o[3] * inv), pk(o[4] * inv, o[5] * inv), pk(o[6] * inv, o[7] * inv));
+              }
             }
             mma_tile<npw>(p.packed + lw.w_out + static_cast<size_t>(rt) * (16 * DM * 2) + static_cast<size_t>(ksp) * npw * 1024, lane, bq, npw, acc);
           }
