@@ -893,8 +893,10 @@ __global__ void grid_pack_kernel(const bf16* __restrict__ w, int rows, int K, ui
 
 // prefill caches [B][d / 64][Tmax][64] -> kh [B][H][Tvt][hd], vt [B][H][Tvt / 32][hd][32] (attn_tc.cuh)
 __global__ void grid_relayout_kv_kernel(const bf16* __restrict__ ksrc0, const bf16* __restrict__ vsrc0, bf16* __restrict__ kdst0,
-                                        bf16* __restrict__ vdst0, const int32_t* __restrict__ lens, int ns, int Tmax, int Tvt, int hd) {
-  const int bs = blockIdx.x, b = bs / ns;
+                                        bf16* __restrict__ vdst0, const int32_t* __restrict__ lens, const int32_t* __restrict__ slots, int ns,
+                                        int Tmax, int Tvt, int hd) {
+  // (sequence, slice); `slots` (optional) = the sequences to convert (continuous batching: the newly admitted ones)
+  const int bs = slots ? slots[blockIdx.x / ns] * ns + blockIdx.x % ns : blockIdx.x, b = bs / ns;
   const int len = lens[b];
   const bf16* ksrc = ksrc0 + static_cast<size_t>(bs) * Tmax * 64;
   const bf16* vsrc = vsrc0 + static_cast<size_t>(bs) * Tmax * 64;
@@ -1025,10 +1027,10 @@ int grid_max_ctas(int d_model, int hd) {
 }
 
 int grid_relayout_kv(cudaStream_t s, const bf16* const* kc, const bf16* const* vc, bf16* const* kh, bf16* const* vt, const int32_t* lens,
-                     int B, int n_layer, int d_model, int hd, int Tmax, int Tvt) {
+                     const int32_t* slots, int B, int n_layer, int d_model, int hd, int Tmax, int Tvt) {
   const int ns = d_model / 64;
   for (int l = 0; l < n_layer; ++l) {
-    grid_relayout_kv_kernel<<<B * ns, 256, 0, s>>>(kc[l], vc[l], kh[l], vt[l], lens, ns, Tmax, Tvt, hd);
+    grid_relayout_kv_kernel<<<B * ns, 256, 0, s>>>(kc[l], vc[l], kh[l], vt[l], lens, slots, ns, Tmax, Tvt, hd);
     MG_LAUNCH_CHECK();
   }
   return MG_OK;

@@ -90,9 +90,10 @@ int grid_pack_weights(cudaStream_t s, const GridPackSrc* src, const bf16* head, 
 int grid_plan(int d_model, int d_ff, int n_layer, int V, int B, int n_cta, int* tn, int* ks, GridItem* items, int32_t* n_items);
 int grid_init();                                                     // cudaFuncSetAttribute; MG_OK / MG_E_CUDA
 int grid_max_ctas(int d_model, int hd);                              // co-resident CTAs (cooperative launch), 0 when the query fails
-// prefill caches kc / vc [B][d / 64][Tmax][64] -> kh / vt (host arrays of per-layer device pointers)
+// prefill caches kc / vc [B][d / 64][Tmax][64] -> kh / vt (host arrays of per-layer device pointers) for sequences 0 .. B - 1, or for the B
+// sequences named by the device array `slots` (continuous batching: the newly admitted ones)
 int grid_relayout_kv(cudaStream_t s, const bf16* const* kc, const bf16* const* vc, bf16* const* kh, bf16* const* vt, const int32_t* lens,
-                     int B, int n_layer, int d_model, int hd, int Tmax, int Tvt);
+                     const int32_t* slots, int B, int n_layer, int d_model, int hd, int Tmax, int Tvt);
 int launch_decode_grid(cudaStream_t s, const GridParams& p, int d_model, int hd);
 
 }  // namespace grid

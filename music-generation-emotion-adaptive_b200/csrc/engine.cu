@@ -91,7 +91,7 @@ struct mg_engine {
   DecodeState st{};
   int32_t* d_out_block = nullptr;      // [out_len (B) | out_ids (B * stride)] contiguous for one D2H
   // ---- slot session (continuous batching, mg_slots_*): persistent per-slot decode state outside the per-call arena ----
-  bool slots_active = false, slots_mega = false;
+  bool slots_active = false, slots_mega = false, slots_grid = false;
   int n_slots = 0, slots_eos = -1, slots_topk = 0;
   int32_t* d_slot_state = nullptr;      // cur_tok | lens | n_new | max_new | seq_idx | finished (bytes) | last_rows, n_slots each
   int32_t* d_slot_last_rows = nullptr;
@@ -597,7 +597,7 @@ bool run_decode_grid(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
                      const int32_t* dbg_slot) {
   *rc = MG_OK;
   const int B = e->cur_B;
-  if (!e->grid_ok || !e->use_grid || e->cur_steps <= 0 || B > grid::kMaxSeqs || e->slots_active) return false;
+  if (!e->grid_ok || !e->use_grid || e->cur_steps <= 0 || B > grid::kMaxSeqs || (e->slots_active && !e->slots_grid)) return false;
   const mg_geometry& g = e->geo;
   const int hd = g.d_model / g.n_head;
   auto cuda_ok = [&](cudaError_t ce, const char* what) {
@@ -628,6 +628,7 @@ bool run_decode_grid(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
   p.ldl = e->grid_ldl; p.n_cta = e->grid_ctas;
   for (int k = 0; k < 8; ++k) { p.tn[k] = e->grid_tn[k]; p.ks[k] = e->grid_ks[k]; }
   p.early_exit = (eos_id >= 0 && forced == nullptr) ? 1 : 0;
+  if (e->slots_active) p.early_exit = forced == nullptr ? 1 : 0;    // a chunk ends as soon as every slot is idle
   p.dbg_logits = dbg_logits; p.dbg_slot = dbg_slot; p.forced = forced; p.forced_stride = forced_stride;
   p.fence_mode = std::getenv("MG_GRID_FENCE") ? std::atoi(std::getenv("MG_GRID_FENCE")) : 0;
   p.prof = nullptr; p.prof_step = -1;
@@ -640,14 +641,16 @@ bool run_decode_grid(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
     }
   }
   if (!cuda_ok(cudaMemsetAsync(e->d_grid_ctrl, 0, grid::kGridCtrlBytes, e->stream), "grid control reset")) return true;
-  {
+  // slot sessions convert the caches of newly admitted sequences themselves (mg_slots_admit); the rows a previous chunk of decode steps
+  // appended exist only in the persistent layout and must not be overwritten from the prefill caches
+  if (!e->slots_active) {
     std::vector<const bf16*> kc(g.n_layer), vc(g.n_layer);
     std::vector<bf16*> kh(g.n_layer), vt(g.n_layer);
     for (int l = 0; l < g.n_layer; ++l) {
       kc[l] = reinterpret_cast<const bf16*>(e->layers[l].kc); vc[l] = reinterpret_cast<const bf16*>(e->layers[l].vc);
       kh[l] = reinterpret_cast<bf16*>(e->layers[l].kh); vt[l] = reinterpret_cast<bf16*>(e->layers[l].vt);
     }
-    *rc = grid::grid_relayout_kv(e->stream, kc.data(), vc.data(), kh.data(), vt.data(), e->st.lens, B, g.n_layer, g.d_model, hd, e->max_seq, p.Tvt);
+    *rc = grid::grid_relayout_kv(e->stream, kc.data(), vc.data(), kh.data(), vt.data(), e->st.lens, nullptr, B, g.n_layer, g.d_model, hd, e->max_seq, p.Tvt);
   }
   if (*rc == MG_OK) *rc = grid::launch_decode_grid(e->stream, p, g.d_model, hd);
   if (*rc == MG_OK && !cuda_ok(cudaMemcpyAsync(e->h_grid_ctrl, e->d_grid_ctrl, 64, cudaMemcpyDeviceToHost, e->stream), "grid status copy")) return true;
@@ -1603,6 +1606,9 @@ int mg_slots_begin(mg_engine* e, int n_slots, int max_len, float temperature, in
       const int avail = s_try <= 2 ? e->mega_clusters2 : e->mega_clusters4;
       e->slots_mega = avail > 0 && ceil_div(n_slots, s_try) <= avail;
     }
+  // ... or the grid-synchronous kernel where the cluster kernel does not take the geometry (train_large2) / MG_GRID=1
+  e->slots_grid = (!e->slots_mega || e->grid_mode == 1) && e->dtype == MG_DTYPE_BF16 && e->grid_ok && e->use_grid && n_slots <= grid::kMaxSeqs;
+  if (e->slots_grid) e->slots_mega = false;
   e->uploaded = false;                                                                  // batch-call read-outs do not apply
   e->slots_active = true;
   return MG_OK;
@@ -1667,6 +1673,16 @@ int mg_slots_admit(mg_engine* e, int n, const int32_t* slots, const int32_t* ids
   if (e->slots_mega)
     MG_TRY(mega::mega_relayout_kv_slots(e->stream, e->d_mega_layers, e->st.lens, da + o_slots, n, g.n_layer, e->max_seq,
                                         mega_tvt(e->max_seq), g.d_model / g.n_head));
+  if (e->slots_grid) {
+    std::vector<const bf16*> kc(g.n_layer), vc(g.n_layer);
+    std::vector<bf16*> kh(g.n_layer), vt(g.n_layer);
+    for (int l = 0; l < g.n_layer; ++l) {
+      kc[l] = reinterpret_cast<const bf16*>(e->layers[l].kc); vc[l] = reinterpret_cast<const bf16*>(e->layers[l].vc);
+      kh[l] = reinterpret_cast<bf16*>(e->layers[l].kh); vt[l] = reinterpret_cast<bf16*>(e->layers[l].vt);
+    }
+    MG_TRY(grid::grid_relayout_kv(e->stream, kc.data(), vc.data(), kh.data(), vt.data(), e->st.lens, da + o_slots, n, g.n_layer, g.d_model,
+                                  g.d_model / g.n_head, e->max_seq, mega_tvt(e->max_seq)));
+  }
   for (int j = 0; j < n; ++j) e->slot_busy[slots[j]] = max_new[j] > 0 ? 1 : 0;
   return MG_OK;
 }
@@ -1686,6 +1702,12 @@ int mg_slots_step(mg_engine* e, int n_steps, uint8_t* finished_out, int32_t* out
       return fail(MG_E_STATE, "slot session: the persistent kernel refused the launch");
     MG_TRY(rc);
     e->last_run_mega = true;
+  } else if (e->slots_grid) {
+    int rc = MG_OK;
+    if (!run_decode_grid(e, e->slots_topk, e->slots_eos, &rc, nullptr, nullptr, 0, nullptr))
+      return fail(MG_E_STATE, "slot session: the grid kernel refused the launch");
+    MG_TRY(rc);
+    e->last_run_mega = true;
   } else {
     MG_TRY(e->dtype == MG_DTYPE_BF16 ? run_decode_loop<bf16>(e, e->slots_eos >= 0 ? e->slots_eos : 0)
                                      : run_decode_loop<float>(e, e->slots_eos >= 0 ? e->slots_eos : 0));
@@ -1694,6 +1716,7 @@ int mg_slots_step(mg_engine* e, int n_steps, uint8_t* finished_out, int32_t* out
   MG_CUDA_OK(cudaMemcpyAsync(e->h_slot_flags, e->st.finished, n, cudaMemcpyDeviceToHost, e->stream));
   MG_CUDA_OK(cudaMemcpyAsync(e->h_slot_flags + fin_ints, e->st.out_len, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   MG_CUDA_OK(cudaStreamSynchronize(e->stream));
+  MG_TRY(persistent_status(e));
   e->d2h += n + n * sizeof(int32_t);
   std::memcpy(finished_out, e->h_slot_flags, n);
   std::memcpy(out_len_out, e->h_slot_flags + fin_ints, n * sizeof(int32_t));

@@ -845,6 +845,48 @@ def test_slot_session_persistent_kernel_late_admission_does_not_change_a_request
     assert c == d
 
 
+def test_slot_session_grid_kernel_on_the_production_geometry():
+    """Continuous batching on the geometry the cluster kernel does not take (train_large2: d 512, 6 layers, head_dim 64): the slot
+    session runs the grid-synchronous kernel; a late admission changes nobody's tokens, and a session decoded in chunks equals the
+    one-launch batch call with the same Philox streams."""
+    geo = mg.GEOMETRIES["train_large2"]
+    ck = checkpoint("train_large2", 0)
+    n = 40
+    prompts = [mg.encode(ck["vocab"], p) for p in mg.synthetic_prompts(ck["vocab"], n, seed=9)]
+    e = engine("train_large2", 0, "bf16", max_batch=n, max_seq=256)
+    others = [b for b in range(n) if b != 5]
+
+    def run(late):
+        e.slots_begin(n, 128, 1.0, 40, eos_id=-1, seed=77)
+        e.slots_admit(others, [prompts[b] for b in others], [30 + b % 7 for b in others], [2000 + b for b in others])
+        if late:
+            for _ in range(2):
+                e.slots_step(8)
+        e.slots_admit([5], [prompts[5]], [24], [1005])
+        for _ in range(12):
+            fin, ln = e.slots_step(8)
+            if fin.all():
+                break
+        assert fin.all() and e.last_decode_path() == "grid_kernel"
+        rows = [e.slots_fetch(b) for b in range(n)]
+        e.slots_end()
+        return rows
+
+    a, b = run(False), run(True)
+    assert a[5] == b[5] and len(a[5]) == len(prompts[5]) + 24
+    assert all(len(a[i]) == len(prompts[i]) + 30 + i % 7 for i in others)
+    assert all(a[i] == b[i] for i in others)
+    e.slots_begin(n, 128, 1.0, 40, eos_id=-1, seed=77)
+    e.slots_admit(list(range(n)), prompts, [24] * n, [1000 + b for b in range(n)])
+    for _ in range(3):
+        fin, ln = e.slots_step(8)
+    assert fin.all()
+    d = e.slots_fetch_many(list(range(n)))
+    e.slots_end()
+    c = e.generate(prompts, 24, 1.0, 40, seed=77, seq_index_base=1000)
+    assert e.last_decode_path() == "grid_kernel" and c == d
+
+
 def test_continuous_batcher_serves_a_request_stream():
     geo = mg.GEOMETRIES["tiny_hd64"]
     ck = checkpoint("tiny_hd64", 0)
