@@ -596,14 +596,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
     // Between the arrival at a grid barrier and the wait: pull the weight tile of this CTA's first item of the NEXT phase into L1
     // (immutable data, independent of the barrier), so that the phase starts with ONE L2 round trip (its operand) instead of two
     auto prefetch_next = [&](int ph_next) {
-      if (!(it < n_items && sm.items[it].phase == ph_next)) return;
-      const int rt = sm.items[it].row_tile;
       const int kind = ph_next >= 5 * L ? K_HEAD : ph_next % 5, l = ph_next >= 5 * L ? 0 : ph_next / 5;
       const GridLayer& lw = p.layers[l];
       const size_t mat = kind == K_QKV ? lw.w_in : (kind == K_OUT ? lw.w_out : (kind == K_MLP1 ? lw.w1 : (kind == K_MLP2 ? lw.w2 : p.w_head)));
       const int bytes = 32 * (kind == K_MLP2 ? DFF : DM);
-      const uint8_t* base = p.packed + mat + static_cast<size_t>(rt) * bytes;
-      for (int i = tid; i < bytes / 128; i += kThreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + i * 128));
+      for (int k = it; k < n_items && sm.items[k].phase == ph_next; ++k) {        // every item of the phase (the head: 3-4 tiles per CTA)
+        const uint8_t* base = p.packed + mat + static_cast<size_t>(sm.items[k].row_tile) * bytes;
+        for (int i = tid; i < bytes / 128; i += kThreads) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + i * 128));
+      }
     };
     auto sync_phase = [&](int ph_next) { stamp(); arrive(); prefetch_next(ph_next); wait(); stamp(); };
 
