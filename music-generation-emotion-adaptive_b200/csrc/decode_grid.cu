@@ -978,7 +978,9 @@ int grid_plan(int d_model, int d_ff, int n_layer, int V, int B, int n_cta, int* 
     while ((K / 32) / s > 16 && s < 8) { s *= 2; t = 8 / s; }   // <= 16 k-step pairs per warp (registers)
     tn[kind] = t; ks[kind] = s;
   };
-  int want_out = 2, want_mlp2 = 2;
+  // n-tiles per item of the k-split phases, measured (profiles/r2n_grid_tn_sweep.txt): one n-tile x 8 k-splits for d_model 256
+  // (config 3 105.3 -> 102.6, config 4 94.5 -> 92.3 us per step), two n-tiles x 4 k-splits for d_model 512 (240 vs 252)
+  int want_out = d_model <= 256 ? 1 : 2, want_mlp2 = d_model <= 256 ? 1 : 2;
   if (const char* e = std::getenv("MG_GRID_TN_OUT")) want_out = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("MG_GRID_TN_MLP2")) want_mlp2 = std::max(1, std::atoi(e));
   shape(K_OUT, d_model, want_out);
