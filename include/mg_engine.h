@@ -223,6 +223,11 @@ int mg_bert_stats(mg_bert* b, uint64_t* kernel_launches, uint64_t* h2d_bytes, ui
 int mg_test_gemm_bf16(int device, const float* A, const float* W, const float* bias, int M, int N, int K,
                       int act, float* C);
 
+/* Host-only: the work plan of the grid-synchronous decode kernel (decode_grid.cu) for a batch of B sequences on n_cta CTAs.
+ * tn_ks[16]: n-tiles per item (8) then k-splits (8) per phase kind; items: n_cta x 96 records of 4 int16 {phase, row_tile,
+ * sequence group, 0} in phase order; n_items[n_cta].  No device work (runs without a GPU). */
+int mg_test_grid_plan(int d_model, int d_ff, int n_layer, int vocab, int B, int n_cta, int32_t* tn_ks, int16_t* items, int32_t* n_items);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,14 +13,14 @@ from .vocab import (build_prompt, build_synthetic_vocab, closest_bpm_token, enco
 
 from .bert_checkpoint import (DISTILBERT_BASE, ID2LABEL, TINY_BERT, BertGeometry, make_bert_state_dict,  # noqa: F401
                               merge_lora_state_dict)
-from .engine import (Classifier, Generator, KVModel, load_library, sample, sample_kvcache, tc_gemm)  # noqa: F401
+from .engine import (Classifier, Generator, KVModel, grid_plan, load_library, sample, sample_kvcache, tc_gemm)  # noqa: F401
 from .batcher import ContinuousBatcher, RequestBatcher  # noqa: F401
 from .pipeline import (classify_prompt_generate, clf_capacity, eats_music_params, load_eats_table,  # noqa: F401
                        synthetic_music_params)
 from .replicas import gather_token_lists, shard, shard_range  # noqa: F401
 
 __all__ = [
-    "Classifier", "Generator", "KVModel", "RequestBatcher", "ContinuousBatcher", "load_library", "sample", "sample_kvcache", "tc_gemm", "gather_token_lists",
+    "Classifier", "Generator", "KVModel", "RequestBatcher", "ContinuousBatcher", "load_library", "sample", "sample_kvcache", "tc_gemm", "grid_plan", "gather_token_lists",
     "shard", "shard_range", "classify_prompt_generate", "clf_capacity", "synthetic_music_params", "eats_music_params", "load_eats_table", "DISTILBERT_BASE", "ID2LABEL", "TINY_BERT", "BertGeometry", "make_bert_state_dict",
     "merge_lora_state_dict",
     "GEOMETRIES", "Geometry", "expected_keys", "infer_geometry", "make_checkpoint", "make_state_dict",

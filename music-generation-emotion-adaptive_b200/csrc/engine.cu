@@ -1863,6 +1863,16 @@ int mg_last_step_times(mg_engine* e, float* us_out, int cap, int* n_out) {
   return MG_OK;
 }
 
+int mg_test_grid_plan(int d_model, int d_ff, int n_layer, int vocab, int B, int n_cta, int32_t* tn_ks, int16_t* items, int32_t* n_items) {
+  if (!tn_ks || !items || !n_items || n_cta <= 0 || B <= 0 || B > grid::kMaxSeqs) return fail(MG_E_ARG, "bad argument");
+  if (!grid::grid_eligible(d_model, d_ff, d_model / 32 >= 8 ? 8 : d_model / 32, n_layer, vocab)) return fail(MG_E_SHAPE, "geometry not eligible");
+  static_assert(sizeof(grid::GridItem) == 4 * sizeof(int16_t), "GridItem is four int16");
+  int tn[8], ks[8];
+  const int rc = grid::grid_plan(d_model, d_ff, n_layer, vocab, B, n_cta, tn, ks, reinterpret_cast<grid::GridItem*>(items), n_items);
+  for (int k = 0; k < 8; ++k) { tn_ks[k] = tn[k]; tn_ks[8 + k] = ks[k]; }
+  return rc == MG_OK ? MG_OK : fail(rc, "grid plan: a CTA would get more than kMaxItems items");
+}
+
 int mg_test_gemm_bf16(int device, const float* A, const float* W, const float* bias, int M, int N, int K, int act, float* C) {
   if (!A || !W || !C) return fail(MG_E_ARG, "null argument");
   if (M <= 0 || N <= 0 || K <= 0 || K % 8) return fail(MG_E_SHAPE, "M, N, K must be positive, K a multiple of 8");

@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
     "mg_engine_stream", "mg_step_logits", "mg_step_logits_at", "mg_generate_nocache", "mg_forward_nocache", "mg_sample_logits",
     "mg_engine_stats", "mg_slots_begin", "mg_slots_admit", "mg_slots_step", "mg_slots_fetch", "mg_slots_fetch_many", "mg_slots_end", "mg_set_note_table", "mg_note_events", "mg_last_run_timing", "mg_last_step_times", "mg_last_decode_path", "mg_bert_create", "mg_bert_destroy", "mg_bert_load_weight",
     "mg_bert_finalize", "mg_classify", "mg_bert_upload", "mg_bert_run", "mg_bert_download", "mg_bert_synchronize",
-    "mg_bert_stream", "mg_bert_stats", "mg_test_gemm_bf16",
+    "mg_bert_stream", "mg_bert_stats", "mg_test_gemm_bf16", "mg_test_grid_plan",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mg_bert_stream": (vp, [vp]),
         "mg_bert_stats": (c.c_int, [vp, u64p, u64p, u64p]),
         "mg_test_gemm_bf16": (c.c_int, [c.c_int, f32p, f32p, f32p, c.c_int, c.c_int, c.c_int, c.c_int, f32p]),
+        "mg_test_grid_plan": (c.c_int, [c.c_int] * 6 + [i32p, c.POINTER(c.c_int16), i32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -638,3 +639,17 @@ def tc_gemm(A: np.ndarray, W: np.ndarray, bias: Optional[np.ndarray] = None, act
     _check(lib, lib.mg_test_gemm_bf16(device, _ptr(A, ctypes.c_float), _ptr(W, ctypes.c_float), _ptr(b, ctypes.c_float), M,
                                       N, K, act, _ptr(C, ctypes.c_float)))
     return C
+
+
+def grid_plan(d_model: int, d_ff: int, n_layer: int, vocab: int, B: int, n_cta: int = 148):
+    """Work plan of the grid-synchronous decode kernel (decode_grid.cu) for a batch of B sequences: returns
+    (tn, ks, items) with tn / ks = n-tiles per item / k-splits per phase kind (qkv, attention, out_proj, mlp.0, mlp.2, head) and
+    items[c] = [(phase, row_tile, sequence_group), ...] of CTA c in phase order.  Host-only test hook (no GPU needed)."""
+    lib = load_library()
+    tn_ks = np.zeros(16, np.int32)
+    items = np.zeros((n_cta, 96, 4), np.int16)
+    n_items = np.zeros(n_cta, np.int32)
+    _check(lib, lib.mg_test_grid_plan(int(d_model), int(d_ff), int(n_layer), int(vocab), int(B), int(n_cta), _ptr(tn_ks, ctypes.c_int32),
+                                      items.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)), _ptr(n_items, ctypes.c_int32)))
+    per_cta = [[tuple(int(v) for v in items[c, i, :3]) for i in range(int(n_items[c]))] for c in range(n_cta)]
+    return tn_ks[:8].tolist(), tn_ks[8:].tolist(), per_cta

@@ -448,3 +448,38 @@ def test_continuous_batcher_admits_between_chunks_reuses_slots_and_isolates_bad_
     assert sorted(i for _, i in eng.log) == list(range(100, 108))          # one Philox stream index per admitted request
     assert max(s for s, _ in eng.log) <= 2 and len(eng.log) == 8           # 8 requests through 3 slots
     assert len(cb.admissions) >= 3 and eng.ended
+
+
+@pytest.mark.parametrize("geo_name,B", [("train_large", 64), ("train_large", 16), ("train_large", 1), ("train_large2", 64), ("train_large2", 9),
+                                        ("train_mini", 3)])
+def test_grid_kernel_plan_covers_every_weight_tile_exactly_once(geo_name, B):
+    """Host logic of the grid-synchronous decode kernel (decode_grid.cu: grid_plan): per phase every 16-row tile of the phase's
+    matrix meets every sequence group exactly once, items of a CTA come in phase order, n-tiles x k-splits = the 8 warps of a CTA,
+    a warp never holds more than 16 k-step pairs, and the items are spread evenly over the CTAs."""
+    geo = mg.GEOMETRIES[geo_name]
+    n_cta = 148
+    tn, ks, items = mg.grid_plan(geo.d_model, geo.d_ff, geo.n_layer, geo.vocab_size, B, n_cta)
+    K_QKV, K_OUT, K_MLP1, K_MLP2 = 0, 2, 3, 4
+    nt = (B + 7) // 8
+    for kind, K in ((K_OUT, geo.d_model), (K_MLP2, geo.d_ff)):
+        assert tn[kind] * ks[kind] == 8 and (K // 32) % ks[kind] == 0 and (K // 32) // ks[kind] <= 16
+    want = {}
+    for l in range(geo.n_layer):
+        want[5 * l + K_QKV] = (3 * geo.d_model // 16, 1)
+        want[5 * l + K_OUT] = (geo.d_model // 16, -(-nt // tn[K_OUT]))
+        want[5 * l + K_MLP1] = (geo.d_ff // 16, 1)
+        want[5 * l + K_MLP2] = (geo.d_model // 16, -(-nt // tn[K_MLP2]))
+    want[5 * geo.n_layer] = (-(-geo.vocab_size // 16), 1)
+    seen = {}
+    for c, lst in enumerate(items):
+        assert [it[0] for it in lst] == sorted(it[0] for it in lst), c                 # phase order inside a CTA
+        for ph, rt, g in lst:
+            key = (ph, rt, g)
+            assert key not in seen, key
+            seen[key] = c
+    for ph, (tiles, groups) in want.items():
+        got = sorted((rt, g) for (p, rt, g) in seen if p == ph)
+        assert got == [(rt, g) for rt in range(tiles) for g in range(groups)], ph
+    assert set(p for (p, _, _) in seen) == set(want)
+    counts = [len(lst) for lst in items]
+    assert max(counts) - min(counts) <= 1 and max(counts) <= 96
