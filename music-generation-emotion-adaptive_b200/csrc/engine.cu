@@ -1207,6 +1207,7 @@ void mg_engine_destroy(mg_engine* e) {
   if (e->h_sp) cudaFreeHost(e->h_sp);
   if (e->h_active) cudaFreeHost(e->h_active);
   if (e->h_flow_status) cudaFreeHost(e->h_flow_status);
+  if (e->h_grid_ctrl) cudaFreeHost(e->h_grid_ctrl);
   if (e->h_slot_flags) cudaFreeHost(e->h_slot_flags);
   if (e->h_slot_rows) cudaFreeHost(e->h_slot_rows);
   if (e->h_detok) cudaFreeHost(e->h_detok);
