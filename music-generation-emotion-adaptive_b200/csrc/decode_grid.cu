@@ -610,7 +610,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
     for (int l = 0; l < L && alive; ++l) {
       const GridLayer& lw = p.layers[l];
       phase_rows(5 * l + K_QKV, std::integral_constant<int, K_QKV>{}, l);
-      sync_phase(5 * l + K_ATT);
+      stamp(); arrive();
+      // the first K/V block of this warp's attention unit holds older tokens only (the row this step appends is folded from the
+      // in_proj output, not read from the cache): requested behind the barrier arrival, its HBM round trip overlaps the barrier
+      uint4 kq0[4][HD / 32], vq0[HD / 8];
+      const size_t hb = at_b >= 0 ? (static_cast<size_t>(at_b) * H + at_h) * p.Tvt * HD : 0;
+      constexpr bool kAttnPre = HD == 32;          // head_dim 64: 64 more live registers across the barrier spill (240 -> 263 us per step)
+      if (kAttnPre && at_b >= 0 && (at_wi << 5) < at_len) attn_load_block<HD, true>(lw.kh + hb, lw.vt + hb, at_len, at_wi, lane, kq0, vq0);
+      wait(); stamp();
       if (!alive) break;
       // ---------------- attention: this warp's (sequence, head, key range) unit ----------------
       if (at_b >= 0) {
@@ -621,10 +628,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
           *reinterpret_cast<uint4*>(&sm.vn[warp][lane * 8]) = ldv4u(p.vnew + so + lane * 8);
         }
         __syncwarp();
-        const size_t hb = (static_cast<size_t>(at_b) * H + at_h) * p.Tvt * HD;
-        uint4 kq0[4][HD / 32], vq0[HD / 8];
-        attn_tc<HD, false, true>(lw.kh + hb, lw.vt + hb, at_len, at_wi, at_nws, lane, sm.qs[warp], sm.kn[warp], sm.vn[warp], at_wi == 0,
-                           sm.part[warp], kq0, vq0);
+        attn_tc<HD, kAttnPre, true>(lw.kh + hb, lw.vt + hb, at_len, at_wi, at_nws, lane, sm.qs[warp], sm.kn[warp], sm.vn[warp], at_wi == 0,
+                                sm.part[warp], kq0, vq0);
         __syncwarp();
       }
       __syncthreads();
