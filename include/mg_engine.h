@@ -189,7 +189,8 @@ int mg_note_events(mg_engine* e, int max_inst, int max_notes, int32_t* n_inst, i
 int mg_last_step_times(mg_engine* e, float* us_out, int cap, int* n);
 
 /* Which decode path served the last mg_run / mg_generate / mg_step_logits of this engine: 0 = step graph (one launch per
- * kernel and step), 1 = persistent cluster kernel (decode_mega.cu), 2 = weight-stationary flow kernel (decode_flow.cu).
+ * kernel and step), 1 = persistent cluster kernel (decode_mega.cu), 2 = weight-stationary flow kernel (decode_flow.cu), 3 = grid-synchronous
+ * persistent kernel (decode_grid.cu: the geometries the cluster kernel does not take, or MG_GRID=1).
  * Tests assert that parity was checked on the path the benchmark runs. */
 int mg_last_decode_path(mg_engine* e);
 
