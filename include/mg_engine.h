@@ -190,7 +190,7 @@ int mg_last_step_times(mg_engine* e, float* us_out, int cap, int* n);
 
 /* Which decode path served the last mg_run / mg_generate / mg_step_logits of this engine: 0 = step graph (one launch per
  * kernel and step), 1 = persistent cluster kernel (decode_mega.cu), 2 = weight-stationary flow kernel (decode_flow.cu), 3 = grid-synchronous
- * persistent kernel (decode_grid.cu: the geometries the cluster kernel does not take, or MG_GRID=1).
+ * persistent kernel (decode_grid.cu: the geometries the cluster kernel does not take, few sequences with long caches, or MG_GRID=1).
  * Tests assert that parity was checked on the path the benchmark runs. */
 int mg_last_decode_path(mg_engine* e);
 

@@ -545,7 +545,7 @@ static int alloc_persistent_caches(mg_engine* e) {
 int setup_grid(mg_engine* e) {
   const mg_geometry& g = e->geo;
   e->grid_ok = false;
-  if (e->grid_mode == 2) e->use_grid = !e->mega_ok && e->use_mega;   // MG_NO_MEGA=1 means "no persistent kernel": the step graph
+  if (e->grid_mode == 2) e->use_grid = e->use_mega;   // MG_NO_MEGA=1 means "no persistent kernel": the step graph
   if (!e->use_grid || e->dtype != MG_DTYPE_BF16 || !grid::grid_eligible(g.d_model, g.d_ff, g.n_head, g.n_layer, g.vocab_size)) return MG_OK;
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
@@ -823,7 +823,17 @@ bool run_decode_flow(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_lo
 bool run_decode_persistent(mg_engine* e, int top_k, int eos_id, int* rc, float* dbg_logits, const int32_t* forced, int forced_stride,
                            const int32_t* dbg_slot) {
   e->last_run_flow = e->last_run_grid = false;
-  if (run_decode_grid(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
+  // Which persistent kernel: the grid-synchronous one where the cluster kernel does not take the geometry (or MG_GRID=1), and for FEW
+  // sequences with LONG caches: a cluster streams its sequences' K/V at ~180 GB/s (4 SMs), the grid kernel spreads every (sequence, head)
+  // over all SMs but pays ~20 us more per step for its grid barriers.  Measured crossovers (profiles/r2n_*: config 4 = 16 sequences,
+  // mean cache length 2304: 91.8 vs 93.6-94.7 us per step): mean cache length >= 1000 / 1200 / 1800 for <= 4 / 8 / 16 sequences.
+  bool grid_first = e->grid_mode == 1 || !e->mega_ok;
+  if (!grid_first && e->grid_mode == 2 && e->grid_ok && !e->slots_active && e->cur_B > 0) {
+    const int B = e->cur_B;
+    const double mean_len = static_cast<double>(e->cur_M) / B + 0.5 * e->cur_steps;
+    grid_first = (B <= 4 && mean_len >= 1000) || (B <= 8 && mean_len >= 1200) || (B <= 16 && mean_len >= 1800);
+  }
+  if (grid_first && run_decode_grid(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
   if (run_decode_flow(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
   return run_decode_mega(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot);
 }

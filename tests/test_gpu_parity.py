@@ -562,7 +562,8 @@ def test_config4_bf16_logits_at_cache_lengths_up_to_4351():
     """BASELINE config 4 as benchmarked: 256-token prompts (bidirectional prefill) + 4096 decode steps, batch 16 (one sequence
     per cluster), bf16; logits at cache lengths 256 / 2047 / 2048 / 4095 / 4351 vs the fp64 oracle."""
     steps = [0, 2047 - 256, 2048 - 256, 4095 - 256, 4095]
-    path, worst = _long_cache_case("train_large_pos512", 16, 256, 4096, steps, rows=(0, 7, 15), max_seq=4352)
+    # (MG_GRID=0: few sequences with long caches go to the grid kernel by default -- tested in test_grid_kernel_config3_and_config4_*)
+    path, worst = _long_cache_case("train_large_pos512", 16, 256, 4096, steps, rows=(0, 7, 15), max_seq=4352, env={"MG_GRID": "0"})
     assert path == "cluster_kernel"
     print(f"config-4 worst |logit error| {worst:.4f}")
 
@@ -649,6 +650,23 @@ def test_grid_kernel_config3_and_config4_cache_lengths():
                                    max_seq=4352, env={"MG_GRID": "1"})
     assert path == "grid_kernel"
     print(f"grid kernel config-4 worst |logit error| {worst:.4f}")
+
+
+def test_kernel_choice_few_sequences_with_long_caches_run_on_all_sms():
+    """Default policy (no environment switch): config 4 (16 sequences, mean cache length 2304) runs the grid kernel -- every
+    (sequence, head) split over key ranges on different SMs --, config 3 (64 sequences) and short batch-1 runs the cluster kernel."""
+    geo = mg.GEOMETRIES["train_large_pos512"]
+    ck = checkpoint("train_large_pos512", 0)
+    rng = np.random.default_rng(3)
+    e = engine("train_large_pos512", 0, "bf16", max_batch=64, max_seq=4352)
+    long_prompts = [rng.integers(0, geo.vocab_size, 256).tolist() for _ in range(16)]
+    out = e.generate(long_prompts, 3600, 1.0, 40, seed=1)
+    assert e.last_decode_path() == "grid_kernel" and all(len(o) == 256 + 3600 for o in out)
+    out = e.generate(long_prompts[:1], 40, 1.0, 40, seed=1)
+    assert e.last_decode_path() == "cluster_kernel" and len(out[0]) == 296
+    short = [rng.integers(0, geo.vocab_size, 6).tolist() for _ in range(64)]
+    out = e.generate(short, 64, 1.0, 40, seed=1)
+    assert e.last_decode_path() == "cluster_kernel" and all(len(o) == 70 for o in out)
 
 
 def test_grid_kernel_generation_determinism_ragged_budgets_eos_and_general_sampler():
