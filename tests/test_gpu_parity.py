@@ -627,6 +627,7 @@ def test_flow_kernel_sampler_distribution_chi_square():
     ("train_mini", 3, 5, 80, [0, 26, 27, 79], 512),
     ("train_large2", 64, 6, 72, [0, 26, 58, 71], 256),
     ("train_large2", 5, [9, 40, 64, 65, 130], 40, [0, 39], 256),
+    ("train_large2", 33, 7, 40, [0, 26, 39], 256),                     # five n-tiles, the last one with a single sequence
 ])
 def test_grid_kernel_logits_match_the_oracle(geo_name, B, tp, n_steps, steps, max_seq):
     """Teacher-forced bf16 logits of the grid-synchronous kernel against the fp64 oracle: full and ragged batches, one
@@ -706,6 +707,25 @@ def test_grid_kernel_generation_determinism_ragged_budgets_eos_and_general_sampl
     # general sampler path (top_k = None: whole vocabulary) runs and is deterministic
     w = e.generate(prompts[:5], 6, 1.0, None, seed=3)
     assert e.last_decode_path() == "grid_kernel" and w == e.generate(prompts[:5], 6, 1.0, None, seed=3)
+    e.close()
+
+
+def test_grid_kernel_sampler_wide_top_k_distribution_chi_square():
+    """top_k = 100 takes the other threshold path of the grid kernel's sampler (k-th largest of the 256 per-thread maxima instead of
+    the 64 quad maxima): 51200 draws of one decode step against the top-k softmax of the engine's own logits."""
+    geo = mg.GEOMETRIES["train_large"]
+    ck = checkpoint("train_large", 0)
+    prompt = mg.encode(ck["vocab"], mg.synthetic_prompts(ck["vocab"], 1, seed=0)[0])
+    e = _engine_with_env("train_large", 0, {"MG_GRID": "1"}, max_batch=64, max_seq=320)
+    lg = e.step_logits([prompt], None, 1)[0, 0]
+    probs = gpt_kv.topk_probs(torch.from_numpy(lg.astype(np.float64)), 0.9, 100).numpy()
+    counts = np.zeros(geo.vocab_size, np.int64)
+    for it in range(800):
+        out = e.generate([prompt] * 64, 1, 0.9, 100, seed=9000 + it, as_arrays=True)
+        counts += np.bincount([int(o[-1]) for o in out], minlength=geo.vocab_size)
+    assert e.last_decode_path() == "grid_kernel"
+    assert counts[probs == 0].sum() == 0
+    assert _chi_square_p(counts, probs / probs.sum()) > 1e-3
     e.close()
 
 
