@@ -835,7 +835,9 @@ bool run_decode_persistent(mg_engine* e, int top_k, int eos_id, int* rc, float* 
   }
   if (grid_first && run_decode_grid(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
   if (run_decode_flow(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
-  return run_decode_mega(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot);
+  if (run_decode_mega(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot)) return true;
+  // what the cluster kernel refuses (top_k = None or > 64) still beats the step graph on the grid kernel (any top_k, <= 64 sequences)
+  return !grid_first && e->grid_mode == 2 && !e->slots_active && run_decode_grid(e, top_k, eos_id, rc, dbg_logits, forced, forced_stride, dbg_slot);
 }
 
 // After the stream has been synchronised: did the flow kernel's watchdog fire?

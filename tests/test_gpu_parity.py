@@ -485,9 +485,10 @@ def test_persistent_kernel_ragged_max_new_eos_and_fallbacks():
     assert [len(o) - len(p) for o, p in zip(out, prompts)] == max_new
     full = e.generate(prompts, 40, 1.0, 40, seed=2)
     assert all(o == f[:len(o)] for o, f in zip(out, full))        # a shorter budget is a prefix of the longer run
-    # top_k above the in-kernel sampler's limit and top_k=None go through the step-graph path
+    # top_k above the cluster kernel's in-kernel sampler limit and top_k=None go to the grid kernel (any top_k, <= 64 sequences)
     for k in (100, None):
         o = e.generate(prompts, 12, 1.0, k, seed=3)
+        assert e.last_decode_path() == "grid_kernel"
         assert all(len(x) == len(p) + 12 for x, p in zip(o, prompts))
         assert o == e.generate(prompts, 12, 1.0, k, seed=3)
     # greedy through the persistent kernel == greedy through the step graph for the first tokens of most rows
