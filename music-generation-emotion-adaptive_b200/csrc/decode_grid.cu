@@ -108,7 +108,6 @@ struct GridSmem {
   int istart[kMaxSeqs];                // first attention unit of the sequence
   int len[kMaxSeqs];
   int fin[kMaxSeqs];
-  int tok[kMaxSeqs];
   int total_units;
   int upc;                             // attention units per CTA in this step (consecutive units = consecutive warps of one CTA)
   // sampler
@@ -245,7 +244,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_grid_kernel(const GridPara
       const bool in = tid < B;
       sm.len[tid] = in ? ldvi(p.st.lens + tid) : 0;
       sm.fin[tid] = in ? ldvb(p.st.finished + tid) : 1;
-      sm.tok[tid] = in ? ldvi(p.st.cur_tok + tid) : 0;
     }
     __syncthreads();
     if (warp == 0) {
